@@ -1,0 +1,37 @@
+# cusift_b200 — builds the product library (sm_100a only) and the test oracles.
+#   make lib     -> cusift_b200/libcusift_b200.so   (C ABI + reference-compatible C++ API)
+#   make demo    -> build/csb_demo                  (C++ consumer of the reference-style API)
+#   make oracle  -> oracle/_build/liboracle.so      (CPU restatement, test infrastructure)
+#   make ref     -> oracle/_ref/ref_driver          (unmodified reference; only where /root/reference exists)
+NVCC    ?= nvcc
+ARCH    := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v -cudart shared -Iinclude -Iinclude/cusift -Icusift_b200/csrc
+SRC     := $(wildcard cusift_b200/csrc/*.cu)
+OBJ     := $(patsubst cusift_b200/csrc/%.cu,build/obj/%.o,$(SRC))
+LIB     := cusift_b200/libcusift_b200.so
+
+.PHONY: all lib demo oracle ref clean
+all: lib demo oracle ref
+
+lib: $(LIB)
+
+build/obj/%.o: cusift_b200/csrc/%.cu cusift_b200/csrc/csb_internal.h include/cusift_b200.h $(wildcard include/cusift/*.h include/cusift/extras/*.h)
+	@mkdir -p build/obj
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/obj/$*.ptxas.log || (cat build/obj/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -cudart shared -o $@ $(OBJ)
+
+demo: build/csb_demo
+build/csb_demo: tests/cpp/csb_demo.cpp $(LIB)
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O2 -std=c++17 -cudart shared -Iinclude -Iinclude/cusift -o $@ $< -Lcusift_b200 -lcusift_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../cusift_b200'
+
+oracle:
+	$(MAKE) -C oracle oracle
+ref:
+	$(MAKE) -C oracle ref
+
+clean:
+	rm -rf build $(LIB)
+	$(MAKE) -C oracle clean

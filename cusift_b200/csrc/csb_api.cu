@@ -1,0 +1,765 @@
+// C ABI of cusift_b200 (include/cusift_b200.h): per-GPU context, frame slots,
+// host-side orchestration of the extraction / matching / homography kernels.
+//
+// Host-side behaviour restated from the reference (danielsuo/cuSIFT):
+//   SiftData::Extract / ExtractSiftLoop / ExtractSiftOctave  cuSIFT.cu:61-120,175-270
+//   ScaleDown weights   cuSIFT.cu:320-338      LaplaceMulti weights  cuSIFT.cu:399-412
+//   FindPointsMulti constants  cuSIFT.cu:424-444
+// but with none of its per-frame cudaMalloc/cudaFree, cudaMemcpyToSymbol,
+// cudaMemcpyFromSymbol round trips or texture-object churn: a slot owns a
+// persistent pyramid workspace + texture objects, every parameter travels as a
+// kernel argument, and a frame costs exactly one stream synchronisation.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "csb_internal.h"
+
+namespace {
+
+inline int iAlignUp(int a, int b) { return (a % b != 0) ? (a - a % b + b) : a; }
+
+struct Octave {
+  int w = 0, h = 0, pitch = 0;
+  float *base = nullptr;   // octave base image (octave 0: the caller's frame or slot->img0)
+  float *dog = nullptr;    // 7 planes, plane stride pitch*h
+  cudaTextureObject_t tex = 0;
+};
+
+struct TexCacheEntry {
+  const float *ptr;
+  int w, h, pitch;
+  cudaTextureObject_t tex;
+};
+
+struct ProfRec {
+  int name_id;
+  cudaEvent_t a, b;
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  int w = 0, h = 0, n_oct = 0;
+  float *arena = nullptr;
+  size_t arena_bytes = 0;
+  float *img0 = nullptr;   // upload target for host frames
+  Octave oct[CSB_MAX_OCTAVES];
+  std::vector<TexCacheEntry> tex_cache;   // textures over caller-owned octave-0 frames
+  unsigned int *d_counter = nullptr;
+  int *d_oct = nullptr;
+  int oct_cap = 0;
+  int *h_count = nullptr;                 // pinned + mapped: {stored, found}
+  csb_sift_point *h_stage = nullptr;      // pinned + mapped staging for pageable destinations
+  size_t stage_cap = 0;
+  // frame in flight
+  bool busy = false;
+  void *user_h = nullptr;
+  bool staged = false;
+  int *user_num = nullptr;
+  std::vector<ProfRec> prof_pending;
+  std::vector<ProfRec> prof_free;
+};
+
+struct ProfEntry {
+  std::string name;
+  double total_ms = 0.0;
+  long long launches = 0;
+};
+
+}  // namespace
+
+struct csb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int n_slots = 0;
+  Slot *slots = nullptr;
+  std::string err;
+  bool profile = false;
+  bool no_fuse = false;
+  std::vector<ProfEntry> prof;
+  long long launches = 0;
+  // homography scratch
+  float *d_coord = nullptr, *d_homo = nullptr;
+  int *d_rand = nullptr, *d_counts = nullptr;
+  size_t coord_cap = 0, loops_cap = 0;
+  int *h_counts = nullptr;
+};
+
+namespace {
+
+#define CSB_CHECK(ctx, call)                                                                         \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      char buf_[512];                                                                                \
+      snprintf(buf_, sizeof(buf_), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,              \
+               cudaGetErrorString(e_));                                                              \
+      (ctx)->err = buf_;                                                                             \
+      return (int)e_;                                                                                \
+    }                                                                                                \
+  } while (0)
+
+int fail(csb_ctx *ctx, int code, const char *msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+int prof_id(csb_ctx *ctx, const char *name) {
+  for (size_t i = 0; i < ctx->prof.size(); i++)
+    if (ctx->prof[i].name == name) return (int)i;
+  ProfEntry e;
+  e.name = name;
+  ctx->prof.push_back(e);
+  return (int)ctx->prof.size() - 1;
+}
+
+// Brackets one kernel launch with events on the slot's stream when profiling.
+struct LaunchScope {
+  csb_ctx *ctx;
+  Slot *s;
+  ProfRec rec;
+  bool on;
+  LaunchScope(csb_ctx *c, Slot *sl, const char *name) : ctx(c), s(sl), on(c->profile) {
+    ctx->launches++;
+    if (!on) return;
+    if (!s->prof_free.empty()) {
+      rec = s->prof_free.back();
+      s->prof_free.pop_back();
+    } else {
+      cudaEventCreate(&rec.a);
+      cudaEventCreate(&rec.b);
+    }
+    rec.name_id = prof_id(ctx, name);
+    cudaEventRecord(rec.a, s->stream);
+  }
+  ~LaunchScope() {
+    if (!on) return;
+    cudaEventRecord(rec.b, s->stream);
+    s->prof_pending.push_back(rec);
+  }
+};
+
+void prof_collect(csb_ctx *ctx, Slot *s) {
+  for (ProfRec &r : s->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ctx->prof[r.name_id].total_ms += ms;
+      ctx->prof[r.name_id].launches++;
+    }
+    s->prof_free.push_back(r);
+  }
+  s->prof_pending.clear();
+}
+
+int make_texture(csb_ctx *ctx, const float *ptr, int w, int h, int pitch, cudaTextureObject_t *out) {
+  // same descriptor as the reference, cuSIFT.cu:218-236
+  cudaResourceDesc res;
+  memset(&res, 0, sizeof(res));
+  res.resType = cudaResourceTypePitch2D;
+  res.res.pitch2D.devPtr = const_cast<float *>(ptr);
+  res.res.pitch2D.width = w;
+  res.res.pitch2D.height = h;
+  res.res.pitch2D.pitchInBytes = (size_t)pitch * sizeof(float);
+  res.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+  cudaTextureDesc td;
+  memset(&td, 0, sizeof(td));
+  td.addressMode[0] = cudaAddressModeClamp;
+  td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 0;
+  CSB_CHECK(ctx, cudaCreateTextureObject(out, &res, &td, nullptr));
+  return 0;
+}
+
+void slot_release_workspace(Slot *s) {
+  for (int o = 0; o < CSB_MAX_OCTAVES; o++) {
+    if (s->oct[o].tex) cudaDestroyTextureObject(s->oct[o].tex);
+    s->oct[o] = Octave();
+  }
+  for (TexCacheEntry &e : s->tex_cache) cudaDestroyTextureObject(e.tex);
+  s->tex_cache.clear();
+  if (s->arena) cudaFree(s->arena);
+  s->arena = nullptr;
+  s->arena_bytes = 0;
+  s->img0 = nullptr;
+  s->w = s->h = s->n_oct = 0;
+}
+
+// (Re)builds the pyramid workspace of a slot for frames of w x h with n_oct octaves.
+int slot_prepare(csb_ctx *ctx, Slot *s, int w, int h, int n_oct) {
+  if (s->arena && s->w == w && s->h == h && s->n_oct == n_oct) return 0;
+  slot_release_workspace(s);
+  auto align512 = [](size_t b) { return (b + 511) & ~(size_t)511; };
+  size_t total = 0;
+  int ww = w, hh = h;
+  size_t off_img0 = 0, off_base[CSB_MAX_OCTAVES], off_dog[CSB_MAX_OCTAVES];
+  for (int o = 0; o < n_oct; o++) {
+    const int p = iAlignUp(ww, 128);
+    const size_t img = align512((size_t)p * (hh + 1) * sizeof(float));
+    if (o == 0) { off_img0 = total; total += img; off_base[0] = off_img0; }
+    else { off_base[o] = total; total += img; }
+    off_dog[o] = total;
+    total += align512((size_t)p * hh * CSB_NUM_DOG * sizeof(float));
+    s->oct[o].w = ww; s->oct[o].h = hh; s->oct[o].pitch = p;
+    ww /= 2; hh /= 2;
+  }
+  CSB_CHECK(ctx, cudaMalloc((void **)&s->arena, total));
+  CSB_CHECK(ctx, cudaMemsetAsync(s->arena, 0, total, s->stream));
+  s->arena_bytes = total;
+  char *base = reinterpret_cast<char *>(s->arena);
+  s->img0 = reinterpret_cast<float *>(base + off_img0);
+  for (int o = 0; o < n_oct; o++) {
+    s->oct[o].base = reinterpret_cast<float *>(base + off_base[o]);
+    s->oct[o].dog = reinterpret_cast<float *>(base + off_dog[o]);
+    if (o > 0) {
+      int rc = make_texture(ctx, s->oct[o].base, s->oct[o].w, s->oct[o].h, s->oct[o].pitch, &s->oct[o].tex);
+      if (rc) return rc;
+    }
+  }
+  s->w = w; s->h = h; s->n_oct = n_oct;
+  return 0;
+}
+
+int slot_tex0(csb_ctx *ctx, Slot *s, const float *ptr, int w, int h, int pitch, cudaTextureObject_t *out) {
+  for (TexCacheEntry &e : s->tex_cache)
+    if (e.ptr == ptr && e.w == w && e.h == h && e.pitch == pitch) { *out = e.tex; return 0; }
+  if (s->tex_cache.size() >= 256) {   // bounded: drop the oldest
+    cudaDestroyTextureObject(s->tex_cache.front().tex);
+    s->tex_cache.erase(s->tex_cache.begin());
+  }
+  TexCacheEntry e{ptr, w, h, pitch, 0};
+  int rc = make_texture(ctx, ptr, w, h, pitch, &e.tex);
+  if (rc) return rc;
+  s->tex_cache.push_back(e);
+  *out = e.tex;
+  return 0;
+}
+
+// ---- host-side constants, restated verbatim from the reference -----------------
+void scale_down_kernel(float k3[3]) {     // cuSIFT.cu:320-338 with variance = 0.5f (cuSIFT.cu:185)
+  const float variance = 0.5f;
+  float h_Kernel[5], kernelSum = 0.0f;
+  for (int j = 0; j < 5; j++) {
+    h_Kernel[j] = (float)expf(-(double)(j - 2) * (j - 2) / 2.0 / variance);
+    kernelSum += h_Kernel[j];
+  }
+  for (int j = 0; j < 5; j++) h_Kernel[j] /= kernelSum;
+  k3[0] = h_Kernel[0]; k3[1] = h_Kernel[1]; k3[2] = h_Kernel[2];
+}
+
+void laplace_weights(float initBlur, DogWeights *W) {   // cuSIFT.cu:239-240,399-412
+  const float baseBlur = pow(2.0f, -1.0f / CSB_NUM_SCALES);
+  const float diffScale = pow(2.0f, 1.0f / CSB_NUM_SCALES);
+  float kernel[12 * 16];
+  float scale = baseBlur;
+  for (int i = 0; i < CSB_NUM_LEVELS; i++) {
+    float kernelSum = 0.0f;
+    float var = scale * scale - initBlur * initBlur;
+    for (int j = -4; j <= 4; j++) {
+      kernel[16 * i + j + 4] = (float)expf(-(double)j * j / 2.0 / var);
+      kernelSum += kernel[16 * i + j + 4];
+    }
+    for (int j = -4; j <= 4; j++) kernel[16 * i + j + 4] /= kernelSum;
+    scale *= diffScale;
+  }
+  for (int i = 0; i < CSB_NUM_LEVELS; i++)
+    for (int j = 0; j < 5; j++) W->k[i][j] = kernel[16 * i + j];
+}
+
+void extrema_params(const csb_params *p, int octave, float subsampling, ExtremaParams *E) {   // cuSIFT.cu:239-247,424-444
+  const float baseBlur = pow(2.0f, -1.0f / CSB_NUM_SCALES);
+  const float diffScaleL = pow(2.0f, 1.0f / CSB_NUM_SCALES);
+  const double sigma = baseBlur * diffScaleL;
+  const float factor = 1.0f / CSB_NUM_SCALES;
+  float scale = (float)sigma;
+  const float diffScale = pow(2.0f, factor);
+  for (int i = 0; i < CSB_NUM_SCALES; i++) {
+    E->scales[i] = scale;
+    scale *= diffScale;
+  }
+  E->thresh = p->peak_thresh;
+  E->edge_limit = p->edge_thresh;
+  E->factor = factor;
+  E->subsampling = subsampling;
+  E->octave = octave;
+}
+
+// Enqueues one frame on a slot.  d_img0/pitch0: octave-0 image on the device.
+int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int pitch0, const csb_params *p,
+                  csb_sift_point *d_sift, int max_pts, void *h_sift, int *num_pts) {
+  const int n_oct = p->num_octaves;
+  cudaStream_t st = s->stream;
+
+  if (s->oct_cap < max_pts) {
+    if (s->d_oct) cudaFree(s->d_oct);
+    s->d_oct = nullptr;
+    CSB_CHECK(ctx, cudaMalloc((void **)&s->d_oct, sizeof(int) * (size_t)max_pts));
+    s->oct_cap = max_pts;
+  }
+
+  // result destination: directly into the caller's buffer when it is page-locked
+  csb_sift_point *h_dst = nullptr;
+  s->staged = false;
+  if (h_sift) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, h_sift);
+    if (e == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+      h_dst = reinterpret_cast<csb_sift_point *>(attr.devicePointer);
+    } else {
+      cudaGetLastError();
+      const size_t need = (size_t)max_pts * sizeof(csb_sift_point);
+      if (s->stage_cap < need) {
+        if (s->h_stage) cudaFreeHost(s->h_stage);
+        s->h_stage = nullptr;
+        CSB_CHECK(ctx, cudaHostAlloc((void **)&s->h_stage, need, cudaHostAllocMapped));
+        s->stage_cap = need;
+      }
+      void *dev = nullptr;
+      CSB_CHECK(ctx, cudaHostGetDevicePointer(&dev, s->h_stage, 0));
+      h_dst = reinterpret_cast<csb_sift_point *>(dev);
+      s->staged = true;
+    }
+  }
+  s->user_h = h_sift;
+  s->user_num = num_pts;
+
+  CSB_CHECK(ctx, cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), st));
+
+  // octave geometry, blur schedule (cuSIFT.cu:188) and per-octave constants
+  Octave oct[CSB_MAX_OCTAVES];
+  for (int o = 0; o < n_oct; o++) oct[o] = s->oct[o];
+  oct[0].base = const_cast<float *>(d_img0);
+  oct[0].pitch = pitch0;
+  if (d_img0 == s->img0) {
+    if (!s->oct[0].tex) {
+      int rc = make_texture(ctx, s->img0, w, h, pitch0, &s->oct[0].tex);
+      if (rc) return rc;
+    }
+    oct[0].tex = s->oct[0].tex;
+  } else {
+    int rc = slot_tex0(ctx, s, d_img0, w, h, pitch0, &oct[0].tex);
+    if (rc) return rc;
+  }
+
+  double initBlur[CSB_MAX_OCTAVES];
+  float subs[CSB_MAX_OCTAVES];
+  bool active[CSB_MAX_OCTAVES];
+  initBlur[0] = p->init_blur;
+  subs[0] = p->subsampling;
+  for (int o = 0; o < n_oct; o++) {
+    if (o > 0) {
+      initBlur[o] = (float)sqrt(initBlur[o - 1] * initBlur[o - 1] + 0.5f * 0.5f) / 2.0f;   // cuSIFT.cu:188
+      subs[o] = subs[o - 1] * 2.0f;
+    }
+    active[o] = p->lowest_scale < subs[o] * 2.0f;                                          // cuSIFT.cu:194
+  }
+  float k3[3];
+  scale_down_kernel(k3);
+
+  // pyramid: fine -> coarse (each octave base feeds its DoG stack and the next base)
+  for (int o = 0; o < n_oct; o++) {
+    const bool need_down = (o + 1 < n_oct);
+    DogWeights W;
+    if (active[o]) laplace_weights((float)initBlur[o], &W);
+    if (active[o] && need_down && !ctx->no_fuse) {
+      LaunchScope ls(ctx, s, "blur_dog_down");
+      launch_blur_dog_down(oct[o].base, oct[o].w, oct[o].h, oct[o].pitch, oct[o].dog, W, oct[o + 1].base,
+                           oct[o + 1].pitch, k3, st);
+    } else {
+      if (need_down) {
+        LaunchScope ls(ctx, s, "scale_down");
+        launch_scale_down(oct[o].base, oct[o].w, oct[o].h, oct[o].pitch, oct[o + 1].base, oct[o + 1].pitch, k3, st);
+      }
+      if (active[o]) {
+        LaunchScope ls(ctx, s, "blur_dog");
+        launch_blur_dog(oct[o].base, oct[o].w, oct[o].h, oct[o].pitch, oct[o].dog, W, st);
+      }
+    }
+  }
+  // extrema: coarse -> fine, the reference's output order (cuSIFT.cu:181-196)
+  for (int o = n_oct - 1; o >= 0; o--) {
+    if (!active[o]) continue;
+    ExtremaParams E;
+    extrema_params(p, o, subs[o], &E);
+    LaunchScope ls(ctx, s, "find_points");
+    launch_find_points(oct[o].dog, oct[o].w, oct[o].h, oct[o].pitch, E, d_sift, s->d_oct, s->d_counter, max_pts, st);
+  }
+  {
+    OctaveTexSet T;
+    for (int o = 0; o < CSB_MAX_OCTAVES; o++) T.tex[o] = (o < n_oct) ? oct[o].tex : 0;
+    LaunchScope ls(ctx, s, "orient_desc");
+    launch_orient_desc(T, d_sift, s->d_oct, s->d_counter, max_pts, p->rootsift, ctx->sm_count, st);
+  }
+  {
+    void *dev_cnt = nullptr;
+    CSB_CHECK(ctx, cudaHostGetDevicePointer(&dev_cnt, s->h_count, 0));
+    LaunchScope ls(ctx, s, "copy_out");
+    launch_copy_out(d_sift, s->d_counter, max_pts, h_dst, reinterpret_cast<int *>(dev_cnt), ctx->sm_count, st);
+  }
+  CSB_CHECK(ctx, cudaGetLastError());
+  s->busy = true;
+  return 0;
+}
+
+int finalize_frame(csb_ctx *ctx, Slot *s) {
+  if (!s->busy) return 0;
+  CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+  s->busy = false;
+  const int n = s->h_count[0];
+  if (s->staged && s->user_h && n > 0) memcpy(s->user_h, s->h_stage, (size_t)n * sizeof(csb_sift_point));
+  if (s->user_num) *s->user_num = n;
+  if (ctx->profile) prof_collect(ctx, s);
+  return 0;
+}
+
+int check_params(csb_ctx *ctx, int w, int h, const csb_params *p, int max_pts) {
+  if (!ctx) return CSB_E_INVALID;
+  if (!p || w < 16 || h < 16 || max_pts < 1) return fail(ctx, CSB_E_INVALID, "csb_extract: bad frame size / params");
+  if (p->num_octaves < 1 || p->num_octaves > CSB_MAX_OCTAVES) return fail(ctx, CSB_E_TOOMANY, "num_octaves out of range");
+  if ((w >> (p->num_octaves - 1)) < 2 || (h >> (p->num_octaves - 1)) < 2)
+    return fail(ctx, CSB_E_INVALID, "frame too small for num_octaves");
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+int csb_version(void) { return CSB_VERSION; }
+int csb_sizeof_sift_point(void) { return (int)sizeof(csb_sift_point); }
+
+int csb_ctx_create(int device, int num_slots, csb_ctx **out) {
+  if (!out) return CSB_E_INVALID;
+  *out = nullptr;
+  if (num_slots <= 0) num_slots = 4;
+  if (num_slots > 64) return CSB_E_TOOMANY;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess) return (int)e;
+  if (ndev == 0) return (int)cudaErrorNoDevice;
+  if (device < 0) device = 0;
+  if (device > ndev - 1) device = ndev - 1;   // InitCuda clamps the same way, cutils.h:71-80
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return (int)e;
+  csb_ctx *ctx = new csb_ctx();
+  ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  const char *nf = getenv("CSB_NO_FUSE");
+  ctx->no_fuse = nf && nf[0] == '1';
+  ctx->n_slots = num_slots;
+  ctx->slots = new Slot[num_slots];
+  for (int i = 0; i < num_slots; i++) {
+    Slot *s = &ctx->slots[i];
+    if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) goto bad;
+    if ((e = cudaMalloc((void **)&s->d_counter, 256)) != cudaSuccess) goto bad;
+    if ((e = cudaHostAlloc((void **)&s->h_count, 256, cudaHostAllocMapped)) != cudaSuccess) goto bad;
+    s->h_count[0] = s->h_count[1] = 0;
+  }
+  *out = ctx;
+  return 0;
+bad:
+  csb_ctx_destroy(ctx);
+  return (int)e;
+}
+
+void csb_ctx_destroy(csb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < ctx->n_slots; i++) {
+    Slot *s = &ctx->slots[i];
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    slot_release_workspace(s);
+    for (ProfRec &r : s->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (ProfRec &r : s->prof_free) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (s->d_counter) cudaFree(s->d_counter);
+    if (s->d_oct) cudaFree(s->d_oct);
+    if (s->h_count) cudaFreeHost(s->h_count);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    if (s->stream) cudaStreamDestroy(s->stream);
+  }
+  delete[] ctx->slots;
+  if (ctx->d_coord) cudaFree(ctx->d_coord);
+  if (ctx->d_homo) cudaFree(ctx->d_homo);
+  if (ctx->d_rand) cudaFree(ctx->d_rand);
+  if (ctx->d_counts) cudaFree(ctx->d_counts);
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  delete ctx;
+}
+
+int csb_ctx_device(const csb_ctx *ctx) { return ctx ? ctx->device : -1; }
+int csb_ctx_num_slots(const csb_ctx *ctx) { return ctx ? ctx->n_slots : 0; }
+const char *csb_last_error(const csb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int csb_host_alloc(void **ptr, unsigned long long bytes) {
+  if (!ptr) return CSB_E_INVALID;
+  return (int)cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+}
+int csb_host_free(void *ptr) { return ptr ? (int)cudaFreeHost(ptr) : 0; }
+
+int csb_device_alloc(csb_ctx *ctx, void **d_ptr, unsigned long long bytes) {
+  if (!ctx || !d_ptr) return CSB_E_INVALID;
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  CSB_CHECK(ctx, cudaMalloc(d_ptr, (size_t)bytes));
+  return 0;
+}
+int csb_device_free(csb_ctx *ctx, void *d_ptr) {
+  if (!ctx) return CSB_E_INVALID;
+  if (!d_ptr) return 0;
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  for (int i = 0; i < ctx->n_slots; i++) {   // drop cached textures over this buffer
+    Slot *s = &ctx->slots[i];
+    for (size_t k = 0; k < s->tex_cache.size();) {
+      if (s->tex_cache[k].ptr == d_ptr) {
+        cudaStreamSynchronize(s->stream);
+        cudaDestroyTextureObject(s->tex_cache[k].tex);
+        s->tex_cache.erase(s->tex_cache.begin() + k);
+      } else {
+        k++;
+      }
+    }
+  }
+  CSB_CHECK(ctx, cudaFree(d_ptr));
+  return 0;
+}
+int csb_memcpy_h2d(csb_ctx *ctx, void *d_dst, const void *h_src, unsigned long long bytes) {
+  if (!ctx) return CSB_E_INVALID;
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  CSB_CHECK(ctx, cudaMemcpy(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+int csb_memcpy_d2h(csb_ctx *ctx, void *h_dst, const void *d_src, unsigned long long bytes) {
+  if (!ctx) return CSB_E_INVALID;
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  CSB_CHECK(ctx, cudaMemcpy(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int csb_upload_image(csb_ctx *ctx, float *d_img, int pitch_floats, const float *h_img, int w, int h) {
+  if (!ctx || !d_img || !h_img || pitch_floats < w) return fail(ctx, CSB_E_INVALID, "csb_upload_image: bad argument");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  CSB_CHECK(ctx, cudaMemcpy2D(d_img, sizeof(float) * pitch_floats, h_img, sizeof(float) * w, sizeof(float) * w, h,
+                              cudaMemcpyHostToDevice));
+  return 0;
+}
+int csb_download_image(csb_ctx *ctx, float *h_img, const float *d_img, int pitch_floats, int w, int h) {
+  if (!ctx || !d_img || !h_img || pitch_floats < w) return fail(ctx, CSB_E_INVALID, "csb_download_image: bad argument");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  CSB_CHECK(ctx, cudaMemcpy2D(h_img, sizeof(float) * w, d_img, sizeof(float) * pitch_floats, sizeof(float) * w, h,
+                              cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int csb_extract(csb_ctx *ctx, const float *d_img, int w, int h, int pitch_floats, const csb_params *p, void *d_sift,
+                int max_pts, void *h_sift, int *num_pts) {
+  int rc = check_params(ctx, w, h, p, max_pts);
+  if (rc) return rc;
+  if (!d_img || !d_sift || pitch_floats < w) return fail(ctx, CSB_E_INVALID, "csb_extract: null image/output or pitch < width");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  if ((rc = finalize_frame(ctx, s))) return rc;
+  if ((rc = slot_prepare(ctx, s, w, h, p->num_octaves))) return rc;
+  if ((rc = enqueue_frame(ctx, s, d_img, w, h, pitch_floats, p, (csb_sift_point *)d_sift, max_pts, h_sift, num_pts)))
+    return rc;
+  return finalize_frame(ctx, s);
+}
+
+int csb_extract_host(csb_ctx *ctx, const float *h_img, int w, int h, const csb_params *p, void *d_sift, int max_pts,
+                     void *h_sift, int *num_pts) {
+  int rc = check_params(ctx, w, h, p, max_pts);
+  if (rc) return rc;
+  if (!h_img || !d_sift) return fail(ctx, CSB_E_INVALID, "csb_extract_host: null image/output");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  if ((rc = finalize_frame(ctx, s))) return rc;
+  if ((rc = slot_prepare(ctx, s, w, h, p->num_octaves))) return rc;
+  const int pitch = s->oct[0].pitch;
+  CSB_CHECK(ctx, cudaMemcpy2DAsync(s->img0, sizeof(float) * pitch, h_img, sizeof(float) * w, sizeof(float) * w, h,
+                                   cudaMemcpyHostToDevice, s->stream));
+  if ((rc = enqueue_frame(ctx, s, s->img0, w, h, pitch, p, (csb_sift_point *)d_sift, max_pts, h_sift, num_pts)))
+    return rc;
+  return finalize_frame(ctx, s);
+}
+
+int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int imgs_on_host, int w, int h,
+                      int pitch_floats, const csb_params *p, void *const *d_sifts, void *const *h_sifts, int max_pts,
+                      int *num_pts) {
+  int rc = check_params(ctx, w, h, p, max_pts);
+  if (rc) return rc;
+  if (n_frames < 0 || !imgs || !d_sifts || !num_pts) return fail(ctx, CSB_E_INVALID, "csb_extract_batch: null argument");
+  if (!imgs_on_host && pitch_floats < w) return fail(ctx, CSB_E_INVALID, "csb_extract_batch: pitch < width");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  for (int f = 0; f < n_frames; f++) {
+    Slot *s = &ctx->slots[f % ctx->n_slots];
+    if ((rc = finalize_frame(ctx, s))) return rc;
+    if ((rc = slot_prepare(ctx, s, w, h, p->num_octaves))) return rc;
+    const float *d_img = imgs[f];
+    int pitch = pitch_floats;
+    if (imgs_on_host) {
+      pitch = s->oct[0].pitch;
+      CSB_CHECK(ctx, cudaMemcpy2DAsync(s->img0, sizeof(float) * pitch, imgs[f], sizeof(float) * w, sizeof(float) * w,
+                                       h, cudaMemcpyHostToDevice, s->stream));
+      d_img = s->img0;
+    }
+    void *hs = h_sifts ? h_sifts[f] : nullptr;
+    if ((rc = enqueue_frame(ctx, s, d_img, w, h, pitch, p, (csb_sift_point *)d_sifts[f], max_pts, hs, &num_pts[f])))
+      return rc;
+  }
+  for (int i = 0; i < ctx->n_slots; i++)
+    if ((rc = finalize_frame(ctx, &ctx->slots[i]))) return rc;
+  return 0;
+}
+
+int csb_scale_down(csb_ctx *ctx, const float *d_src, int w, int h, int src_pitch, float *d_dst, int dst_pitch) {
+  if (!ctx || !d_src || !d_dst || w < 2 || h < 2) return fail(ctx, CSB_E_INVALID, "csb_scale_down: bad argument");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  float k3[3];
+  scale_down_kernel(k3);
+  {
+    LaunchScope ls(ctx, s, "scale_down");
+    launch_scale_down(d_src, w, h, src_pitch, d_dst, dst_pitch, k3, s->stream);
+  }
+  CSB_CHECK(ctx, cudaGetLastError());
+  CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+  if (ctx->profile) prof_collect(ctx, s);
+  return 0;
+}
+
+int csb_rootsift(csb_ctx *ctx, void *d_sift, int n) {
+  if (!ctx || !d_sift || n < 0) return fail(ctx, CSB_E_INVALID, "csb_rootsift: bad argument");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  {
+    LaunchScope ls(ctx, s, "rootsift");
+    launch_rootsift((csb_sift_point *)d_sift, n, s->stream);
+  }
+  CSB_CHECK(ctx, cudaGetLastError());
+  CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+  if (ctx->profile) prof_collect(ctx, s);
+  return 0;
+}
+
+int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, int distance, void *h_sift1) {
+  if (!ctx || n1 < 0 || n2 < 0 || (distance != 0 && distance != 1)) return fail(ctx, CSB_E_INVALID, "csb_match: bad argument");
+  if (n1 == 0 || n2 == 0) return 0;   // matching.cu:282-283: nothing to do
+  if (!d_sift1 || !d_sift2) return fail(ctx, CSB_E_INVALID, "csb_match: null device data");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  {
+    LaunchScope ls(ctx, s, "match");
+    launch_match((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, distance, s->stream);
+  }
+  CSB_CHECK(ctx, cudaGetLastError());
+  if (h_sift1) {   // the five match fields, strided (matching.cu:352-356)
+    const csb_sift_point *d = (const csb_sift_point *)d_sift1;
+    csb_sift_point *hp = (csb_sift_point *)h_sift1;
+    CSB_CHECK(ctx, cudaMemcpy2DAsync(&hp[0].score, sizeof(csb_sift_point), &d[0].score, sizeof(csb_sift_point),
+                                     5 * sizeof(float), n1, cudaMemcpyDeviceToHost, s->stream));
+  }
+  CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+  if (ctx->profile) prof_collect(ctx, s);
+  return 0;
+}
+
+int csb_find_homography(csb_ctx *ctx, const void *d_sift, int n, const int *h_rand_pts, int num_loops, float thresh,
+                        float *H9, int *num_inliers) {
+  if (!ctx || !H9 || !num_inliers) return fail(ctx, CSB_E_INVALID, "csb_find_homography: null output");
+  *num_inliers = 0;
+  H9[0] = H9[4] = H9[8] = 1.0f;
+  H9[1] = H9[2] = H9[3] = H9[5] = H9[6] = H9[7] = 0.0f;
+  if (!d_sift || !h_rand_pts || num_loops <= 0 || (num_loops % 16) != 0)
+    return fail(ctx, CSB_E_INVALID, "csb_find_homography: bad argument (num_loops must be a positive multiple of 16)");
+  if (n < 8) return 0;   // homography.cu:207-208
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  const int n_up = ((n + 15) / 16) * 16;
+  if (ctx->coord_cap < (size_t)n_up) {
+    if (ctx->d_coord) cudaFree(ctx->d_coord);
+    ctx->d_coord = nullptr;
+    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->d_coord, sizeof(float) * 4 * (size_t)n_up));
+    ctx->coord_cap = n_up;
+  }
+  if (ctx->loops_cap < (size_t)num_loops) {
+    if (ctx->d_homo) cudaFree(ctx->d_homo);
+    if (ctx->d_rand) cudaFree(ctx->d_rand);
+    if (ctx->d_counts) cudaFree(ctx->d_counts);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    ctx->d_homo = nullptr; ctx->d_rand = nullptr; ctx->d_counts = nullptr; ctx->h_counts = nullptr;
+    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->d_homo, sizeof(float) * 8 * (size_t)num_loops));
+    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->d_rand, sizeof(int) * 4 * (size_t)num_loops));
+    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->d_counts, sizeof(int) * (size_t)num_loops));
+    CSB_CHECK(ctx, cudaHostAlloc((void **)&ctx->h_counts, sizeof(int) * (size_t)num_loops, cudaHostAllocDefault));
+    ctx->loops_cap = num_loops;
+  }
+  for (int i = 0; i < 4 * num_loops; i++)
+    if (h_rand_pts[i] < 0 || h_rand_pts[i] >= n) return fail(ctx, CSB_E_INVALID, "csb_find_homography: sample index out of range");
+  CSB_CHECK(ctx, cudaMemcpyAsync(ctx->d_rand, h_rand_pts, sizeof(int) * 4 * (size_t)num_loops, cudaMemcpyHostToDevice,
+                                 s->stream));
+  {
+    LaunchScope ls(ctx, s, "homography");
+    ctx->launches += 2;
+    launch_homography((const csb_sift_point *)d_sift, n, n_up, ctx->d_coord, ctx->d_rand, ctx->d_homo, ctx->d_counts,
+                      num_loops, thresh * thresh, s->stream);
+  }
+  CSB_CHECK(ctx, cudaGetLastError());
+  CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(int) * (size_t)num_loops, cudaMemcpyDeviceToHost,
+                                 s->stream));
+  CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+  int maxIndex = -1, maxCount = -1;   // first maximum wins, homography.cu:259-264
+  for (int i = 0; i < num_loops; i++)
+    if (ctx->h_counts[i] > maxCount) { maxCount = ctx->h_counts[i]; maxIndex = i; }
+  *num_inliers = maxCount;
+  CSB_CHECK(ctx, cudaMemcpy2D(H9, sizeof(float), &ctx->d_homo[maxIndex], sizeof(float) * num_loops, sizeof(float), 8,
+                              cudaMemcpyDeviceToHost));
+  H9[8] = 1.0f;
+  if (ctx->profile) prof_collect(ctx, s);
+  return 0;
+}
+
+int csb_debug_octave(csb_ctx *ctx, int oct, float *h_base, float *h_dog, int *w, int *h) {
+  if (!ctx) return CSB_E_INVALID;
+  Slot *s = &ctx->slots[0];
+  if (oct < 0 || oct >= s->n_oct) return fail(ctx, CSB_E_INVALID, "csb_debug_octave: no such octave in slot 0");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+  const Octave &o = s->oct[oct];
+  if (w) *w = o.w;
+  if (h) *h = o.h;
+  if (h_base) {
+    if (oct == 0) return fail(ctx, CSB_E_INVALID, "csb_debug_octave: octave 0 base is the caller's frame");
+    CSB_CHECK(ctx, cudaMemcpy2D(h_base, sizeof(float) * o.w, o.base, sizeof(float) * o.pitch, sizeof(float) * o.w, o.h,
+                                cudaMemcpyDeviceToHost));
+  }
+  if (h_dog) {
+    for (int i = 0; i < CSB_NUM_DOG; i++)
+      CSB_CHECK(ctx, cudaMemcpy2D(h_dog + (size_t)i * o.w * o.h, sizeof(float) * o.w, o.dog + (size_t)i * o.pitch * o.h,
+                                  sizeof(float) * o.pitch, sizeof(float) * o.w, o.h, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int csb_profile_enable(csb_ctx *ctx, int on) {
+  if (!ctx) return CSB_E_INVALID;
+  ctx->profile = on != 0;
+  return 0;
+}
+int csb_profile_reset(csb_ctx *ctx) {
+  if (!ctx) return CSB_E_INVALID;
+  for (ProfEntry &e : ctx->prof) { e.total_ms = 0.0; e.launches = 0; }
+  return 0;
+}
+int csb_profile_count(const csb_ctx *ctx) { return ctx ? (int)ctx->prof.size() : 0; }
+int csb_profile_get(csb_ctx *ctx, int idx, const char **name, double *total_ms, long long *launches) {
+  if (!ctx || idx < 0 || idx >= (int)ctx->prof.size()) return CSB_E_INVALID;
+  if (name) *name = ctx->prof[idx].name.c_str();
+  if (total_ms) *total_ms = ctx->prof[idx].total_ms;
+  if (launches) *launches = ctx->prof[idx].launches;
+  return 0;
+}
+long long csb_launch_count(const csb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

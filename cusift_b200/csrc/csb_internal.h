@@ -1,0 +1,53 @@
+// Internal declarations shared by the kernels and the C-ABI layer of cusift_b200.
+#ifndef CSB_INTERNAL_H
+#define CSB_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cusift_b200.h"
+
+#define CSB_NUM_LEVELS (CSB_NUM_SCALES + 3)   // blur levels per octave (LAPLACE_S, cuSIFT_D.h:23)
+#define CSB_NUM_DOG (CSB_NUM_SCALES + 2)      // DoG planes per octave
+
+// 9-tap symmetric Gaussian weights of the 8 blur levels of one octave, k[s][0..4]
+// = taps at distance 4,3,2,1,0 (same indexing as d_Kernel2, cuSIFT.cu:405-410).
+struct DogWeights {
+  float k[CSB_NUM_LEVELS][5];
+};
+
+// Parameters of the extrema kernel (d_Threshold/d_EdgeLimit/d_Scales/d_Factor in
+// the reference, cuSIFT_D.cu:13-15, pushed per launch at cuSIFT.cu:441-444).
+struct ExtremaParams {
+  float thresh;                    // peakThresh
+  float edge_limit;                // edgeThresh
+  float scales[CSB_NUM_SCALES];    // sigma * 2^(i/5)
+  float factor;                    // 1/NUM_SCALES
+  float subsampling;               // of this octave
+  int octave;
+};
+
+// Per-octave view handed to the orientation/descriptor kernel.
+struct OctaveTexSet {
+  cudaTextureObject_t tex[CSB_MAX_OCTAVES];
+};
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------
+void launch_scale_down(const float *src, int w, int h, int spitch, float *dst, int dpitch, const float k[3],
+                       cudaStream_t st);
+void launch_blur_dog(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, cudaStream_t st);
+void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next,
+                          int npitch, const float k[3], cudaStream_t st);
+void launch_find_points(const float *dog, int w, int h, int pitch, const ExtremaParams &ep, csb_sift_point *d_sift,
+                        int *d_oct, unsigned int *d_counter, int max_pts, cudaStream_t st);
+void launch_orient_desc(const OctaveTexSet &texs, csb_sift_point *d_sift, const int *d_oct,
+                        const unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st);
+void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st);
+void launch_copy_out(const csb_sift_point *d_sift, const unsigned int *d_counter, int max_pts, csb_sift_point *h_mapped,
+                     int *h_count_mapped, int sm_count, cudaStream_t st);
+void launch_match(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
+                  cudaStream_t st);
+void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
+                       int *d_counts, int num_loops, float thresh2, cudaStream_t st);
+
+#endif

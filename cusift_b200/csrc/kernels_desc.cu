@@ -1,0 +1,281 @@
+// Orientation assignment + 4x4x8 descriptor (+ optional RootSIFT), one warp per
+// keypoint, fused into a single persistent launch that reads the keypoint count
+// from device memory (the reference reads it back to the host three times per
+// octave to size two launches, cuSIFT.cu:243,251,255).
+//
+// Replaces (reference, danielsuo/cuSIFT):
+//   ComputeOrientations_D     cuSIFT_D.cu:319-396   (128-thread block per keypoint)
+//   ExtractSiftDescriptors_D  cuSIFT_D.cu:184-297   (16x8-thread block per keypoint)
+//   ConvertSiftToRootSift_D   cuSIFT_D.cu:299-317
+//
+// Sampling goes through the texture unit exactly like the reference (bilinear,
+// clamp, unnormalised coordinates, raw — not +0.5 — coordinates), because the
+// hardware filter's 1.8 fixed-point weights are part of the reference's results.
+// The sample-coordinate and weight arithmetic follows the reference's sm_100a
+// SASS (which products are fused, which are not); the histogram sums are
+// accumulated with shared-memory atomics whose order is unspecified in the
+// reference as well (cuSIFT_D.cu:234-253,343), hence the comparison tolerances.
+#include "csb_internal.h"
+
+namespace {
+
+constexpr int WARPS = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// Sum of squares of 128 values held 4 per lane (element i = lane + 32 j), in the
+// reference's tree order (cuSIFT_D.cu:260-271): s[i] = b[i]^2 + b[i+64]^2 for
+// i<64, then +32, +16, +8, +4, then ((s0+s1)+s2)+s3.
+__device__ __forceinline__ float sumsq_tree(const float (&b)[4], int lane) {
+  float sA = __fmaf_rn(b[0], b[0], __fmul_rn(b[2], b[2]));   // idx = lane
+  float sB = __fmaf_rn(b[1], b[1], __fmul_rn(b[3], b[3]));   // idx = lane + 32
+  float s = __fadd_rn(sA, sB);                               // sums[idx] += sums[idx+32]
+  s = __fadd_rn(s, __shfl_down_sync(FULL, s, 16));           // idx < 16
+  s = __fadd_rn(s, __shfl_down_sync(FULL, s, 8));            // idx < 8
+  s = __fadd_rn(s, __shfl_down_sync(FULL, s, 4));            // idx < 4
+  const float s0 = __shfl_sync(FULL, s, 0), s1 = __shfl_sync(FULL, s, 1);
+  const float s2 = __shfl_sync(FULL, s, 2), s3 = __shfl_sync(FULL, s, 3);
+  return __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
+}
+
+__device__ __forceinline__ void vote(float *buf, int idx, float v) {
+  // votes past buffer[128] exist in the reference (cuSIFT_D.cu:243 guard is off by
+  // one; angi can be 8) and land beyond its last shared array: dropped here.
+  if (idx >= 0 && idx < 128) atomicAdd(buf + idx, v);
+}
+
+__global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constant__ OctaveTexSet T,
+                                                            csb_sift_point *__restrict__ d_sift,
+                                                            const int *__restrict__ d_oct,
+                                                            const unsigned int *__restrict__ counter, int max_pts,
+                                                            int rootsift) {
+  __shared__ float s_hist[WARPS][64];
+  __shared__ float s_gauss[WARPS][16];
+  __shared__ float s_buf[WARPS][128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *hist = s_hist[warp], *gauss = s_gauss[warp], *buf = s_buf[warp];
+  const unsigned int cnt = *counter;
+  const int n = (int)min(cnt, (unsigned int)max_pts);
+
+  for (int k = blockIdx.x * WARPS + warp; k < n; k += gridDim.x * WARPS) {
+    csb_sift_point *pt = d_sift + k;
+    const float px = pt->coords2D[0], py = pt->coords2D[1], pscale = pt->scale, psub = pt->subsampling;
+    const cudaTextureObject_t tex = T.tex[d_oct[k]];
+
+    // ---------------- orientation (cuSIFT_D.cu:319-396) ----------------
+    const float i2sigma2 = __fdiv_rn(-1.0f, __fmul_rn(__fmul_rn(pscale, 4.5f), pscale));
+    if (lane < 11) {
+      const float d = (float)(lane - 5);
+      gauss[lane] = expf(__fmul_rn(__fmul_rn(d, i2sigma2), d));
+    }
+    hist[lane] = 0.0f;
+    hist[lane + 32] = 0.0f;
+    __syncwarp();
+    const float xp = __fsub_rn(px, 5.0f), yp = __fsub_rn(py, 5.0f);
+    for (int s = lane; s < 121; s += 32) {
+      const int yd = s / 11, xd = s - yd * 11;
+      const float xf = __fadd_rn(xp, (float)xd), yf = __fadd_rn(yp, (float)yd);
+      const float dx = __fsub_rn(tex2D<float>(tex, __fadd_rn(xf, 1.0f), yf), tex2D<float>(tex, __fsub_rn(xf, 1.0f), yf));
+      const float dy = __fsub_rn(tex2D<float>(tex, xf, __fadd_rn(yf, 1.0f)), tex2D<float>(tex, xf, __fsub_rn(yf, 1.0f)));
+      int bin = (int)__fadd_rn(__fdiv_rn(__fmul_rn(16.0f, atan2f(dy, dx)), 3.1416f), 16.5f);
+      if (bin > 31) bin = 0;
+      const float grad = sqrtf(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+      atomicAdd(hist + bin, __fmul_rn(__fmul_rn(grad, gauss[xd]), gauss[yd]));
+    }
+    __syncwarp();
+    {
+      const float h0 = hist[lane];
+      const float h1 = __fadd_rn(hist[(lane + 31) & 31], hist[(lane + 1) & 31]);
+      const float h2 = __fadd_rn(hist[(lane + 30) & 31], hist[(lane + 2) & 31]);
+      hist[32 + lane] = __fadd_rn(__fmaf_rn(h0, 6.0f, __fmul_rn(h1, 4.0f)), h2);
+    }
+    __syncwarp();
+    float orient;
+    {
+      const float v = hist[32 + lane];
+      const float pk = (v > hist[32 + ((lane + 31) & 31)] && v >= hist[32 + ((lane + 1) & 31)]) ? v : 0.0f;
+      // serial scan of the reference (strict >, first maximum wins) == lowest lane holding the maximum
+      const float maxval1 = warp_max(pk);
+      const unsigned int who = __ballot_sync(FULL, pk == maxval1);
+      const int i1 = (maxval1 > 0.0f) ? (__ffs(who) - 1) : -1;
+      const float val1 = hist[32 + ((i1 + 1) & 31)];
+      const float val2 = hist[32 + ((i1 + 31) & 31)];
+      const float peak = __fadd_rn(
+          (float)i1, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(val1, val2)),
+                               __fsub_rn(__fsub_rn(__fadd_rn(maxval1, maxval1), val1), val2)));
+      orient = __fmul_rn(11.25f, (peak < 0.0f ? __fadd_rn(peak, 32.0f) : peak));
+    }
+    __syncwarp();
+
+    // ---------------- descriptor (cuSIFT_D.cu:184-297) ----------------
+    if (lane < 16) {
+      const float d = __fsub_rn((float)lane, 7.5f);
+      gauss[lane] = expf(__fdiv_rn(__fmul_rn(-d, d), 128.0f));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) buf[lane + 32 * j] = 0.0f;
+    __syncwarp();
+    const float theta = __fmul_rn(2.0f * 3.1415f / 360.0f, orient);
+    const float sina = sinf(theta), cosa = cosf(theta);
+    const float sc = __fmul_rn(pscale, 0.75f);
+    const float ssina = __fmul_rn(sina, sc), scosa = __fmul_rn(cosa, sc);
+    for (int s = lane; s < 256; s += 32) {
+      const int tx = s & 15, y = s >> 4;
+      const float ftx = __fsub_rn((float)tx, 7.5f), fy = __fsub_rn((float)y, 7.5f);
+      const float xpos = __fmaf_rn(-ssina, fy, __fadd_rn(__fmul_rn(ftx, scosa), px));
+      const float ypos = __fmaf_rn(scosa, fy, __fadd_rn(__fmul_rn(ftx, ssina), py));
+      const float dx = __fsub_rn(tex2D<float>(tex, __fadd_rn(xpos, cosa), __fadd_rn(ypos, sina)),
+                                 tex2D<float>(tex, __fsub_rn(xpos, cosa), __fsub_rn(ypos, sina)));
+      const float dy = __fsub_rn(tex2D<float>(tex, __fsub_rn(xpos, sina), __fadd_rn(ypos, cosa)),
+                                 tex2D<float>(tex, __fadd_rn(xpos, sina), __fsub_rn(ypos, cosa)));
+      const float grad = __fmul_rn(__fmul_rn(gauss[y], gauss[tx]), sqrtf(__fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
+      float angf = __fmaf_rn(atan2f(dy, dx), 4.0f / 3.1415f, 4.0f);
+      const int hori = (tx + 2) / 4 - 1;
+      const float horf = __fmaf_rn(__fsub_rn((float)tx, 1.5f), 0.25f, -(float)hori);
+      const float ihorf = __fsub_rn(1.0f, horf);
+      const int veri = (y + 2) / 4 - 1;
+      const float verf = __fmaf_rn(__fsub_rn((float)y, 1.5f), 0.25f, -(float)veri);
+      const float iverf = __fsub_rn(1.0f, verf);
+      const int angi = (int)angf;
+      const int angp = (angi < 7 ? angi + 1 : 0);
+      angf = __fsub_rn(angf, (float)angi);
+      const float iangf = __fsub_rn(1.0f, angf);
+      const int hbase = 8 * (4 * veri + hori);
+      const int p1 = angi + hbase, p2 = angp + hbase;
+      if (tx >= 2) {
+        const float grad1 = __fmul_rn(ihorf, grad);
+        if (y >= 2) {
+          const float grad2 = __fmul_rn(iverf, grad1);
+          vote(buf, p1, __fmul_rn(iangf, grad2));
+          vote(buf, p2, __fmul_rn(angf, grad2));
+        }
+        if (y <= 13) {
+          const float grad2 = __fmul_rn(verf, grad1);
+          vote(buf, p1 + 32, __fmul_rn(iangf, grad2));
+          vote(buf, p2 + 32, __fmul_rn(angf, grad2));
+        }
+      }
+      if (tx <= 14) {   // sic: reproduces the reference's guard (cuSIFT_D.cu:243)
+        const float grad1 = __fmul_rn(horf, grad);
+        if (y >= 2) {
+          const float grad2 = __fmul_rn(iverf, grad1);
+          vote(buf, p1 + 8, __fmul_rn(iangf, grad2));
+          vote(buf, p2 + 8, __fmul_rn(angf, grad2));
+        }
+        if (y <= 13) {
+          const float grad2 = __fmul_rn(verf, grad1);
+          vote(buf, p1 + 40, __fmul_rn(iangf, grad2));
+          vote(buf, p2 + 40, __fmul_rn(angf, grad2));
+        }
+      }
+    }
+    __syncwarp();
+
+    // normalise, clamp at 0.2, normalise (cuSIFT_D.cu:259-291)
+    float b[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) b[j] = buf[lane + 32 * j];
+    const float r1 = rsqrtf(sumsq_tree(b, lane));
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float v = __fmul_rn(b[j], r1);
+      b[j] = (v > 0.2f) ? 0.2f : v;
+    }
+    const float r2 = rsqrtf(sumsq_tree(b, lane));
+#pragma unroll
+    for (int j = 0; j < 4; j++) b[j] = __fmul_rn(b[j], r2);
+
+    if (rootsift) {
+      // ConvertSiftToRootSift_D (cuSIFT_D.cu:299-317): serial fp32 sum over i=0..127,
+      // then sqrtf((float)(max(0.0,(double)d) / (double)sum)).
+#pragma unroll
+      for (int j = 0; j < 4; j++) buf[lane + 32 * j] = b[j];
+      __syncwarp();
+      float sum = 0.0f;
+      for (int i = 0; i < 128; i++) sum = __fadd_rn(sum, buf[i]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = sqrtf((float)(fmax(0.0, (double)b[j]) / (double)sum));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) pt->data[lane + 32 * j] = b[j];
+    if (lane == 0) {
+      pt->orientation = orient;
+      pt->coords2D[0] = __fmul_rn(px, psub);
+      pt->coords2D[1] = __fmul_rn(py, psub);
+      pt->scale = __fmul_rn(pscale, psub);
+    }
+    __syncwarp();
+  }
+}
+
+// Stand-alone SiftData::ConvertSiftToRootSift (cuSIFT.cu:383-395): one warp per point.
+__global__ void __launch_bounds__(128) k_rootsift(csb_sift_point *__restrict__ d_sift, int n) {
+  __shared__ float s_buf[4][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *buf = s_buf[warp];
+  for (int k = blockIdx.x * 4 + warp; k < n; k += gridDim.x * 4) {
+    float b[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      b[j] = d_sift[k].data[lane + 32 * j];
+      buf[lane + 32 * j] = b[j];
+    }
+    __syncwarp();
+    float sum = 0.0f;
+    for (int i = 0; i < 128; i++) sum = __fadd_rn(sum, buf[i]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) d_sift[k].data[lane + 32 * j] = sqrtf((float)(fmax(0.0, (double)b[j]) / (double)sum));
+    __syncwarp();
+  }
+}
+
+// Result hand-off: copies the first min(count,max_pts) records (147 words each)
+// and the count into page-locked, device-mapped host memory with coalesced
+// stores, so one stream synchronise is the only host<->device round trip of a
+// frame (the reference: cudaMemcpyFromSymbol + cudaMemcpy, cuSIFT.cu:107-113).
+__global__ void __launch_bounds__(256) k_copy_out(const csb_sift_point *__restrict__ d_sift,
+                                                  const unsigned int *__restrict__ counter, int max_pts,
+                                                  csb_sift_point *__restrict__ h_sift, int *__restrict__ h_count) {
+  const unsigned int cnt = *counter;
+  const int n = (int)min(cnt, (unsigned int)max_pts);
+  if (h_sift != nullptr) {
+    const size_t words = (size_t)n * (sizeof(csb_sift_point) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(d_sift);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(h_sift);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
+      dst[i] = src[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    h_count[0] = n;
+    h_count[1] = (int)cnt;
+  }
+}
+
+}  // namespace
+
+void launch_orient_desc(const OctaveTexSet &texs, csb_sift_point *d_sift, const int *d_oct,
+                        const unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st) {
+  int blocks = sm_count * 8;
+  const int need = (max_pts + WARPS - 1) / WARPS;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  k_orient_desc<<<blocks, WARPS * 32, 0, st>>>(texs, d_sift, d_oct, d_counter, max_pts, rootsift);
+}
+
+void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st) {
+  if (n <= 0) return;
+  int blocks = (n + 3) / 4;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_rootsift<<<blocks, 128, 0, st>>>(d_sift, n);
+}
+
+void launch_copy_out(const csb_sift_point *d_sift, const unsigned int *d_counter, int max_pts, csb_sift_point *h_mapped,
+                     int *h_count_mapped, int sm_count, cudaStream_t st) {
+  k_copy_out<<<sm_count * 2, 256, 0, st>>>(d_sift, d_counter, max_pts, h_mapped, h_count_mapped);
+}

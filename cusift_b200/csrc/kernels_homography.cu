@@ -1,0 +1,165 @@
+// RANSAC homography: hypothesis generation and scoring.
+//
+// Replaces ComputeHomographies + InvertMatrix<8> (reference
+// extras/homography.cu:98-139, 12-96) and TestHomographies (:144-187), plus the
+// four strided cudaMemcpy2D gathers of FindHomography (:246-249), with three
+// launches on one stream and no intermediate host synchronisation.
+//   k_gather_coords : AoS SiftPoint -> SoA x1,y1,x2,y2 (pad slots zeroed; the
+//                     reference leaves them uninitialised, homography.cu:215)
+//   k_hypotheses    : one thread per 4-point sample, 8x8 DLT system solved by
+//                     the same Crout LU / implicit pivoting as the reference
+//   k_score         : one warp per hypothesis, inlier test with the reference's
+//                     round-toward-zero products (__fmul_rz), shuffle sum
+#include "csb_internal.h"
+
+namespace {
+
+__global__ void k_gather_coords(const csb_sift_point *__restrict__ d_sift, int n, int n_up, float *__restrict__ coord) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_up) return;
+  float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+  if (i < n) {
+    x1 = d_sift[i].coords2D[0];
+    y1 = d_sift[i].coords2D[1];
+    x2 = d_sift[i].match_xpos;
+    y2 = d_sift[i].match_ypos;
+  }
+  coord[i + 0 * n_up] = x1;
+  coord[i + 1 * n_up] = y1;
+  coord[i + 2 * n_up] = x2;
+  coord[i + 3 * n_up] = y2;
+}
+
+// Numerical-Recipes style LU inverse, restated from homography.cu:12-96.
+__device__ void invert8(float elem[8][8], float res[8][8]) {
+  const int size = 8;
+  int indx[8];
+  float b[8], vv[8];
+  for (int i = 0; i < size; i++) indx[i] = 0;
+  int imax = 0;
+  for (int i = 0; i < size; i++) {
+    float big = 0.0f;
+    for (int j = 0; j < size; j++) {
+      const float temp = fabsf(elem[i][j]);
+      if (temp > big) big = temp;
+    }
+    if (big > 0.0f) vv[i] = (float)(1.0 / (double)big);
+    else vv[i] = 1e16f;
+  }
+  for (int j = 0; j < size; j++) {
+    for (int i = 0; i < j; i++) {
+      float sum = elem[i][j];
+      for (int k = 0; k < i; k++) sum -= elem[i][k] * elem[k][j];
+      elem[i][j] = sum;
+    }
+    float big = 0.0f;
+    for (int i = j; i < size; i++) {
+      float sum = elem[i][j];
+      for (int k = 0; k < j; k++) sum -= elem[i][k] * elem[k][j];
+      elem[i][j] = sum;
+      const float dum = vv[i] * fabsf(sum);
+      if (dum >= big) {
+        big = dum;
+        imax = i;
+      }
+    }
+    if (j != imax) {
+      for (int k = 0; k < size; k++) {
+        const float dum = elem[imax][k];
+        elem[imax][k] = elem[j][k];
+        elem[j][k] = dum;
+      }
+      vv[imax] = vv[j];
+    }
+    indx[j] = imax;
+    if (elem[j][j] == 0.0f) elem[j][j] = 1e-16f;
+    if (j != (size - 1)) {
+      const float dum = (float)(1.0 / (double)elem[j][j]);
+      for (int i = j + 1; i < size; i++) elem[i][j] *= dum;
+    }
+  }
+  for (int j = 0; j < size; j++) {
+    for (int k = 0; k < size; k++) b[k] = 0.0f;
+    b[j] = 1.0f;
+    int ii = -1;
+    for (int i = 0; i < size; i++) {
+      const int ip = indx[i];
+      float sum = b[ip];
+      b[ip] = b[i];
+      if (ii != -1) {
+        for (int jj = ii; jj < i; jj++) sum -= elem[i][jj] * b[jj];
+      } else if (sum != 0.0f) {
+        ii = i;
+      }
+      b[i] = sum;
+    }
+    for (int i = size - 1; i >= 0; i--) {
+      float sum = b[i];
+      for (int jj = i + 1; jj < size; jj++) sum -= elem[i][jj] * b[jj];
+      b[i] = sum / elem[i][i];
+    }
+    for (int i = 0; i < size; i++) res[i][j] = b[i];
+  }
+}
+
+__global__ void __launch_bounds__(64) k_hypotheses(const float *__restrict__ coord, const int *__restrict__ randPts,
+                                                   float *__restrict__ homo, int numPts, int numLoops) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= numLoops) return;
+  float a[8][8], ia[8][8], b[8];
+  for (int i = 0; i < 4; i++) {
+    const int pt = randPts[i * numLoops + idx];
+    const float x1 = coord[pt + 0 * numPts], y1 = coord[pt + 1 * numPts];
+    const float x2 = coord[pt + 2 * numPts], y2 = coord[pt + 3 * numPts];
+    float *row1 = a[2 * i + 0];
+    row1[0] = x1; row1[1] = y1; row1[2] = 1.0f;
+    row1[3] = row1[4] = row1[5] = 0.0f;
+    row1[6] = -x2 * x1; row1[7] = -x2 * y1;
+    float *row2 = a[2 * i + 1];
+    row2[0] = row2[1] = row2[2] = 0.0f;
+    row2[3] = x1; row2[4] = y1; row2[5] = 1.0f;
+    row2[6] = -y2 * x1; row2[7] = -y2 * y1;
+    b[2 * i + 0] = x2;
+    b[2 * i + 1] = y2;
+  }
+  invert8(a, ia);
+  for (int j = 0; j < 8; j++) {
+    float sum = 0.0f;
+    for (int i = 0; i < 8; i++) sum += ia[j][i] * b[i];
+    homo[j * numLoops + idx] = sum;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_score(const float *__restrict__ coord, const float *__restrict__ homo,
+                                               int *__restrict__ counts, int numPts, int numLoops, float thresh2) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= numLoops) return;
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = homo[warp + i * numLoops];
+  int cnt = 0;
+  for (int i = lane; i < numPts; i += 32) {
+    const float x1 = coord[i + 0 * numPts], y1 = coord[i + 1 * numPts];
+    const float x2 = coord[i + 2 * numPts], y2 = coord[i + 3 * numPts];
+    // homography.cu:165-171, every product rounded toward zero
+    const float nomx = __fadd_rn(__fadd_rn(__fmul_rz(a[0], x1), __fmul_rz(a[1], y1)), a[2]);
+    const float nomy = __fadd_rn(__fadd_rn(__fmul_rz(a[3], x1), __fmul_rz(a[4], y1)), a[5]);
+    const float deno = __fadd_rn(__fadd_rn(__fmul_rz(a[6], x1), __fmul_rz(a[7], y1)), 1.0f);
+    const float errx = __fsub_rn(__fmul_rz(x2, deno), nomx);
+    const float erry = __fsub_rn(__fmul_rz(y2, deno), nomy);
+    const float err2 = __fadd_rn(__fmul_rz(errx, errx), __fmul_rz(erry, erry));
+    if (err2 < __fmul_rz(thresh2, __fmul_rz(deno, deno))) cnt++;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) counts[warp] = cnt;
+}
+
+}  // namespace
+
+void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
+                       int *d_counts, int num_loops, float thresh2, cudaStream_t st) {
+  k_gather_coords<<<(n_up + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord);
+  k_hypotheses<<<(num_loops + 63) / 64, 64, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
+  k_score<<<(num_loops * 32 + 255) / 256, 256, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
+}

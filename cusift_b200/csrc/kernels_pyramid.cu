@@ -1,0 +1,213 @@
+// Gaussian scale-space for one octave: 8 blur levels -> 7 DoG planes, fused with
+// the 2x downsample that seeds the next octave, so the octave base image is read
+// from HBM once.
+//
+// Replaces (reference, danielsuo/cuSIFT):
+//   LaplaceMulti_D  cuSIFT_D.cu:525-553  (8 x separable 9-tap on texture fetches + DoG)
+//   ScaleDown_D     cuSIFT_D.cu:37-182   (5x5 separable blur + decimation)
+//
+// Results are bit-identical to the reference's: every multiply-add below is
+// pinned with __fmul_rn/__fmaf_rn/__fadd_rn in the order the reference's own
+// sm_100a SASS evaluates it (FMUL k3*(a1+b1); FFMA c*k4; FFMA k2; k1; k0).
+//
+// Data movement: a CTA owns a strip of 120 output columns x ROWS output rows.
+// Thread t streams source column x0-4+t (clamped) downwards with coalesced 512-B
+// row reads, keeping the 9-row vertical window in registers.  Per batch of 4 rows
+// the 8 vertically-blurred levels go to shared memory ([4][8][128] floats), then
+// warp b filters row b horizontally, 4 adjacent outputs per lane from three
+// 128-bit shared loads per level, and stores the 7 DoG rows as 128-bit words.
+// Algorithmic HBM traffic: 4 B read + 28 B (+1 B next octave) written per pixel.
+#include "csb_internal.h"
+
+namespace {
+
+constexpr int TW = 120;       // output columns per CTA
+constexpr int NT = 128;       // threads = TW + 2*4 halo columns
+constexpr int BATCH = 4;      // rows per shared-memory batch (= warps per CTA)
+constexpr int ROWS = 32;      // output rows per CTA
+constexpr int NLEV = CSB_NUM_LEVELS;
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// cuSIFT_D.cu:536-540 / 544-548 in the reference's evaluation order.
+__device__ __forceinline__ float tap9(const float (&k)[5], float c, float s1, float s2, float s3, float s4) {
+  float t = __fmul_rn(k[3], s1);
+  t = __fmaf_rn(c, k[4], t);
+  t = __fmaf_rn(k[2], s2, t);
+  t = __fmaf_rn(k[1], s3, t);
+  t = __fmaf_rn(k[0], s4, t);
+  return t;
+}
+
+// ScaleDown_D row filter (cuSIFT_D.cu:111-113): k0*(c-2+c+2) + k1*(c-1+c+1) + k2*c0.
+__device__ __forceinline__ float down_h(float c0, float c1, float c2, float c3, float c4, float k0, float k1, float k2) {
+  float t = __fmul_rn(__fadd_rn(c1, c3), k1);
+  t = __fmaf_rn(__fadd_rn(c0, c4), k0, t);
+  t = __fmaf_rn(c2, k2, t);
+  return t;
+}
+// ScaleDown_D column filter, fork behaviour (cuSIFT_D.cu:123-125 and the four
+// rotated copies): k2*r[2j] + k0*(r[2j+2]+r[2j+3]) + k1*(r[2j-1]+r[2j+1]).
+__device__ __forceinline__ float down_v(float rm1, float r0, float r1, float r2, float r3, float k0, float k1, float k2) {
+  float t = __fmul_rn(__fadd_rn(r2, r3), k0);
+  t = __fmaf_rn(r0, k2, t);
+  t = __fmaf_rn(__fadd_rn(rm1, r1), k1, t);
+  return t;
+}
+
+struct DownK {
+  float k0, k1, k2;
+};
+
+template <bool kDown>
+__global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, int w, int h, int pitch,
+                                                 float *__restrict__ dog, const __grid_constant__ DogWeights W,
+                                                 float *__restrict__ next, int npitch, DownK dk) {
+  __shared__ __align__(16) float V[BATCH][NLEV][NT];
+  __shared__ float Raw[kDown ? BATCH : 1][NT];
+
+  const int t = threadIdx.x;
+  const int x0 = blockIdx.x * TW;
+  const int y0 = blockIdx.y * ROWS;
+  const int cx = clampi(x0 + t - 4, 0, w - 1);
+  const size_t plane = (size_t)pitch * h;
+  const int warp = t >> 5, lane = t & 31;
+
+  float win[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) win[i] = 0.0f;
+  float hw[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // down-sample window (threads < TW/2)
+
+  // source rows y0-4 .. y0+ROWS+3 stream through in batches of 4; the window is
+  // full (an output row exists) from the third batch on.
+  float pre[BATCH];
+#pragma unroll
+  for (int b = 0; b < BATCH; b++) pre[b] = src[(size_t)clampi(y0 - 4 + b, 0, h - 1) * pitch + cx];
+
+  constexpr int NB = (ROWS + 8) / BATCH;
+  for (int nb = 0; nb < NB; nb++) {
+    const int r0 = y0 - 4 + nb * BATCH;      // first source row of this batch
+    float cur[BATCH];
+#pragma unroll
+    for (int b = 0; b < BATCH; b++) cur[b] = pre[b];
+    if (nb + 1 < NB) {
+#pragma unroll
+      for (int b = 0; b < BATCH; b++) pre[b] = src[(size_t)clampi(r0 + BATCH + b, 0, h - 1) * pitch + cx];
+    }
+    const bool hasOut = nb >= 2;             // block-uniform
+#pragma unroll
+    for (int b = 0; b < BATCH; b++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) win[i] = win[i + 1];
+      win[8] = cur[b];
+      if constexpr (kDown) Raw[b][t] = cur[b];
+      if (hasOut) {
+        const float c = win[4];
+        const float s1 = __fadd_rn(win[3], win[5]);
+        const float s2 = __fadd_rn(win[2], win[6]);
+        const float s3 = __fadd_rn(win[1], win[7]);
+        const float s4 = __fadd_rn(win[0], win[8]);
+#pragma unroll
+        for (int s = 0; s < NLEV; s++) V[b][s][t] = tap9(W.k[s], c, s1, s2, s3, s4);
+      }
+    }
+    __syncthreads();
+
+    if (hasOut) {
+      // warp `warp` filters batch row `warp` horizontally; lane q -> outputs 4q..4q+3
+      const int y = r0 - 4 + warp;           // output row of V[warp]
+      const int xo = x0 + 4 * lane;
+      if (lane < TW / 4 && y < h && xo < w) {
+        float prev[4];
+#pragma unroll
+        for (int s = 0; s < NLEV; s++) {
+          const float4 a = *reinterpret_cast<const float4 *>(&V[warp][s][4 * lane]);
+          const float4 bq = *reinterpret_cast<const float4 *>(&V[warp][s][4 * lane + 4]);
+          const float4 cq = *reinterpret_cast<const float4 *>(&V[warp][s][4 * lane + 8]);
+          const float v[12] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, cq.x, cq.y, cq.z, cq.w};
+          float L[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            L[j] = tap9(W.k[s], v[j + 4], __fadd_rn(v[j + 3], v[j + 5]), __fadd_rn(v[j + 2], v[j + 6]),
+                        __fadd_rn(v[j + 1], v[j + 7]), __fadd_rn(v[j], v[j + 8]));
+          if (s > 0) {
+            float *o = dog + (size_t)(s - 1) * plane + (size_t)y * pitch + xo;
+            const float d0 = __fsub_rn(prev[0], L[0]), d1 = __fsub_rn(prev[1], L[1]);
+            const float d2 = __fsub_rn(prev[2], L[2]), d3 = __fsub_rn(prev[3], L[3]);
+            if (xo + 3 < w) {
+              *reinterpret_cast<float4 *>(o) = make_float4(d0, d1, d2, d3);
+            } else {
+              o[0] = d0;
+              if (xo + 1 < w) o[1] = d1;
+              if (xo + 2 < w) o[2] = d2;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++) prev[j] = L[j];
+        }
+      }
+    }
+
+    if constexpr (kDown) {
+      // threads 0..59: next-octave column x0/2+t, fed by source rows r0..r0+3
+      if (t < TW / 2) {
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+          const int r = r0 + b;
+          const float hv = down_h(Raw[b][2 * t + 2], Raw[b][2 * t + 3], Raw[b][2 * t + 4], Raw[b][2 * t + 5],
+                                  Raw[b][2 * t + 6], dk.k0, dk.k1, dk.k2);
+#pragma unroll
+          for (int i = 0; i < 4; i++) hw[i] = hw[i + 1];
+          hw[4] = hv;
+          // window now holds rows r-4..r; output row j needs rows 2j-1..2j+3 = r-4..r
+          const int twoj = r - 3;
+          if (twoj >= y0 && twoj < y0 + ROWS && !(twoj & 1)) {
+            const int j = twoj >> 1, i = (x0 >> 1) + t;
+            if (j < (h >> 1) && i < (w >> 1))
+              next[(size_t)j * npitch + i] = down_v(hw[0], hw[1], hw[2], hw[3], hw[4], dk.k0, dk.k1, dk.k2);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Stand-alone ScaleDown (cuSIFT.h:76): one thread per destination pixel.
+__global__ void k_scale_down(const float *__restrict__ src, int w, int h, int spitch, float *__restrict__ dst,
+                             int dpitch, DownK dk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= (w >> 1) || j >= (h >> 1)) return;
+  float hr[5];
+#pragma unroll
+  for (int d = 0; d < 5; d++) {
+    const float *r = src + (size_t)clampi(2 * j - 1 + d, 0, h - 1) * spitch;
+    hr[d] = down_h(r[clampi(2 * i - 2, 0, w - 1)], r[clampi(2 * i - 1, 0, w - 1)], r[clampi(2 * i, 0, w - 1)],
+                   r[clampi(2 * i + 1, 0, w - 1)], r[clampi(2 * i + 2, 0, w - 1)], dk.k0, dk.k1, dk.k2);
+  }
+  dst[(size_t)j * dpitch + i] = down_v(hr[0], hr[1], hr[2], hr[3], hr[4], dk.k0, dk.k1, dk.k2);
+}
+
+}  // namespace
+
+void launch_scale_down(const float *src, int w, int h, int spitch, float *dst, int dpitch, const float k[3],
+                       cudaStream_t st) {
+  dim3 blk(32, 8), grd(((w >> 1) + 31) / 32, ((h >> 1) + 7) / 8);
+  if (grd.x == 0 || grd.y == 0) return;
+  DownK dk{k[0], k[1], k[2]};
+  k_scale_down<<<grd, blk, 0, st>>>(src, w, h, spitch, dst, dpitch, dk);
+}
+
+void launch_blur_dog(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, cudaStream_t st) {
+  dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
+  DownK dk{0.f, 0.f, 0.f};
+  k_blur_dog<false><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, nullptr, 0, dk);
+}
+
+void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next,
+                          int npitch, const float k[3], cudaStream_t st) {
+  dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
+  DownK dk{k[0], k[1], k[2]};
+  k_blur_dog<true><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, next, npitch, dk);
+}

@@ -1,0 +1,164 @@
+/*
+ * cusift_b200 — C ABI of the B200-native SIFT hot path.
+ *
+ * This is the drop-in boundary underneath the reference-compatible C++ headers in
+ * include/cusift/ (cuImage.h, cuSIFT.h, extras/matching.h, extras/homography.h).
+ * Plain pointers and sizes only; every entry point returns 0 on success or a
+ * non-zero status (a cudaError_t value, or CSB_E_* below) and never exits the
+ * process.  Each declaration cites the reference interface it replaces
+ * (file:line under danielsuo/cuSIFT).
+ *
+ * SiftPoint records crossing this boundary use the reference layout
+ * (cuSIFT.h:10-30): 588 bytes, see csb_sift_point below.
+ */
+#ifndef CUSIFT_B200_H
+#define CUSIFT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSB_VERSION 100
+#define CSB_MAX_OCTAVES 8
+#define CSB_NUM_SCALES 5            /* cuSIFT_D.h:8  NUM_SCALES */
+
+#define CSB_E_INVALID   10001       /* bad argument */
+#define CSB_E_NOMEM     10002
+#define CSB_E_TOOMANY   10003       /* more octaves / slots than supported */
+
+/* cuSIFT.h:10-30 (class SiftPoint), byte-for-byte. */
+typedef struct csb_sift_point {
+  float coords2D[2];
+  float scale;
+  float sharpness;
+  float edgeness;
+  float orientation;     /* degrees, [0,360) */
+  float score;
+  float ambiguity;
+  int   match;
+  float match_xpos;
+  float match_ypos;
+  float match_error;
+  float subsampling;
+  float empty[3];
+  float data[128];
+  float coords3D[3];
+} csb_sift_point;
+
+/* Extraction parameters: the public fields of SiftData (cuSIFT.h:45-51) plus the
+ * subsampling argument of SiftData::Extract (cuSIFT.h:63). */
+typedef struct csb_params {
+  int    num_octaves;    /* SiftData::numOctaves                                  */
+  double init_blur;      /* SiftData::initBlur                                    */
+  float  peak_thresh;    /* SiftData::peakThresh  (DoG contrast threshold)        */
+  float  edge_thresh;    /* SiftData::edgeThresh  (tra^2 < edge*det)              */
+  float  lowest_scale;   /* SiftData::lowestScale (octave skipped unless < 2*sub) */
+  float  subsampling;    /* Extract(..., subsampling = 1.0f)                      */
+  int    rootsift;       /* !=0: ConvertSiftToRootSift after extraction           */
+                         /* (legacy ExtractRootSift, cuSIFT.cu:122-134)           */
+} csb_params;
+
+typedef struct csb_ctx csb_ctx;
+
+/* ---- context -------------------------------------------------------------
+ * One context per GPU (replaces the reference's file-scope __constant__/__device__
+ * state, cuSIFT_D.cu:13-20, and InitCuda, cutils.h:71-92).  `num_slots` frames may
+ * be in flight at once (each slot owns a stream, a pyramid workspace, per-octave
+ * texture objects and pinned staging); 0 picks the default (4). */
+int  csb_ctx_create(int device, int num_slots, csb_ctx **out);
+void csb_ctx_destroy(csb_ctx *ctx);
+int  csb_ctx_device(const csb_ctx *ctx);
+int  csb_ctx_num_slots(const csb_ctx *ctx);
+const char *csb_last_error(const csb_ctx *ctx);
+int  csb_version(void);
+int  csb_sizeof_sift_point(void);
+
+/* ---- pinned host buffers ---------------------------------------------------
+ * Host SiftPoint arrays handed to csb_extract* may be any host memory; arrays
+ * obtained here are page-locked + device-mapped, which lets the result be written
+ * by the GPU directly (no staging copy).  Replaces malloc/free of
+ * SiftData::h_data (cuSIFT.cu:22-25,43-46). */
+int  csb_host_alloc(void **ptr, unsigned long long bytes);
+int  csb_host_free(void *ptr);
+
+/* ---- device buffers (for FFI callers without a CUDA runtime binding) ---------
+ * Replace cudaMalloc in the SiftData constructor (cuSIFT.cu:27-30) and
+ * cuImage::Allocate / HostToDevice / DeviceToHost (cuImage.cu:16-45,83-117).
+ * csb_upload_image / csb_download_image copy a dense host frame (row stride w)
+ * to / from a pitched device image (pitch in floats). */
+int  csb_device_alloc(csb_ctx *ctx, void **d_ptr, unsigned long long bytes);
+int  csb_device_free(csb_ctx *ctx, void *d_ptr);
+int  csb_memcpy_h2d(csb_ctx *ctx, void *d_dst, const void *h_src, unsigned long long bytes);
+int  csb_memcpy_d2h(csb_ctx *ctx, void *h_dst, const void *d_src, unsigned long long bytes);
+int  csb_upload_image(csb_ctx *ctx, float *d_img, int pitch_floats, const float *h_img, int w, int h);
+int  csb_download_image(csb_ctx *ctx, float *h_img, const float *d_img, int pitch_floats, int w, int h);
+
+/* ---- extraction ------------------------------------------------------------
+ * csb_extract: legacy ExtractSift / ExtractRootSift contract (main.cpp:102,327;
+ *   cuSIFT.cu:122-134,175-270): the frame is already on the device as a pitched
+ *   fp32 image (cuImage, cuImage.h:8-26; pitch in floats).  On return d_sift
+ *   holds *num_pts SiftPoints (at most max_pts), h_sift (optional) a copy.
+ * csb_extract_host: HEAD SiftData::Extract(float*, w, h, subsampling)
+ *   (cuSIFT.cu:61-120): dense host frame (row stride = w), upload included.
+ * Both block until the result is complete.  Octaves are processed coarsest
+ * first like ExtractSiftLoop (cuSIFT.cu:175-202); the order of points inside an
+ * octave is unspecified (it is in the reference too: atomicInc, cuSIFT_D.cu:513).
+ * Points beyond max_pts are dropped (the reference overwrites slot max_pts-1).  */
+int csb_extract(csb_ctx *ctx, const float *d_img, int w, int h, int pitch_floats, const csb_params *p,
+                void *d_sift, int max_pts, void *h_sift, int *num_pts);
+int csb_extract_host(csb_ctx *ctx, const float *h_img, int w, int h, const csb_params *p,
+                     void *d_sift, int max_pts, void *h_sift, int *num_pts);
+
+/* Pipelined batch of independent frames of one shape (the frame-sharded
+ * throughput path; the reference has no equivalent — a caller would loop over
+ * SiftData::Extract).  imgs[i] is a device pitched image (imgs_on_host == 0) or a
+ * dense host frame (imgs_on_host != 0).  d_sifts[i] / h_sifts[i] receive frame i
+ * (h_sifts or any h_sifts[i] may be NULL); num_pts[i] its count. */
+int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int imgs_on_host, int w, int h,
+                      int pitch_floats, const csb_params *p, void *const *d_sifts, void *const *h_sifts,
+                      int max_pts, int *num_pts);
+
+/* ScaleDown(cuImage &res, cuImage &src, 0.5f) (cuSIFT.h:76, cuSIFT.cu:313-353):
+ * dst is (w/2) x (h/2).  Stores are guarded (the reference's are not). */
+int csb_scale_down(csb_ctx *ctx, const float *d_src, int w, int h, int src_pitch, float *d_dst, int dst_pitch);
+
+/* SiftData::ConvertSiftToRootSift (cuSIFT.cu:383-395) on n device points. */
+int csb_rootsift(csb_ctx *ctx, void *d_sift, int n);
+
+/* ---- matching --------------------------------------------------------------
+ * Device part of MatchSiftData (extras/matching.cu:272-357): for every point of
+ * d_sift1 finds the best and second-best point of d_sift2 and writes score,
+ * ambiguity, match, match_xpos, match_ypos into d_sift1 (and, when h_sift1 is
+ * given, into the same five fields of the host copy, matching.cu:352-356).
+ * distance: 0 = MatchSiftDistanceDotProduct, 1 = MatchSiftDistanceL2
+ * (extras/matching.h:10-13). */
+int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, int distance, void *h_sift1);
+
+/* ---- homography -------------------------------------------------------------
+ * FindHomography (extras/homography.h:8, homography.cu:191-278).  Valid points
+ * are those with score > min_score && ambiguity < max_ambiguity.  The 4-point
+ * samples are drawn by the caller — h_rand_pts is int[4][num_loops] holding
+ * indices into the point array (the reference draws them with libc rand(),
+ * homography.cu:232-244; the C++ shim does exactly that) — so results are
+ * reproducible.  num_loops must be a multiple of 16.  H9 gets the best
+ * hypothesis (H9[8] = 1), num_inliers its inlier count over all n points. */
+int csb_find_homography(csb_ctx *ctx, const void *d_sift, int n, const int *h_rand_pts, int num_loops,
+                        float thresh, float *H9, int *num_inliers);
+
+/* ---- debugging / measurement --------------------------------------------------
+ * csb_debug_octave: after a csb_extract* call on slot 0, copies octave `oct`'s
+ *   base image (dense w x h) and/or its 7 DoG planes (dense [7][h][w]) to host.
+ * csb_profile_*: when enabled every kernel launch of the extraction path is
+ *   bracketed by CUDA events on its own stream; csb_profile_get returns the
+ *   accumulated device time (ms) and launch count per kernel name. */
+int csb_debug_octave(csb_ctx *ctx, int oct, float *h_base, float *h_dog, int *w, int *h);
+int csb_profile_enable(csb_ctx *ctx, int on);
+int csb_profile_reset(csb_ctx *ctx);
+int csb_profile_count(const csb_ctx *ctx);
+int csb_profile_get(csb_ctx *ctx, int idx, const char **name, double *total_ms, long long *launches);
+long long csb_launch_count(const csb_ctx *ctx);   /* kernels launched since creation */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUSIFT_B200_H */
