@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Headline benchmark: 1080p ExtractSift frames/s (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            product arm (one rank per GPU)
+  python bench.py --impl reference --gpus N ...            the unmodified reference (oracle/_ref)
+
+Workload (BASELINE config 4 / SURVEY.md 8d "C4"): a pool of synthetic 1920x1080 fp32
+frames synth(1920,1080,1000+i) resident in HBM, logical frame f uses pool[f % pool],
+5 octaves, peakThresh 1.0, edgeThresh 10, maxPts 16384 (~7.6 k keypoints / frame).
+A step is one pass of the hot path over `frames_per_step` frames per GPU (512 = C4's
+4096 frames / 8 GPUs); frames are sharded cyclically over ranks, no data-path
+collective (weak scaling: per-GPU work is fixed).
+
+  value : frames/s, frame already in HBM -> SiftPoint array + count in (pinned) host
+          memory — the legacy ExtractSift contract (main.cpp:317-328, cuSIFT.cu:113)
+  e2e   : the same through csb_extract_batch with HOST frames: pinned-host upload of
+          every frame and result download inside the timed region
+          (HEAD SiftData::Extract(float*) contract, cuSIFT.cu:61-120)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H = 1920, 1080
+N_OCT, PEAK, EDGE, MAXPTS = 5, 1.0, 10.0, 16384
+# octave sizes of a 1080p frame: sum = 2 762 040 octave pixels
+OCT_PX = [1920 * 1080, 960 * 540, 480 * 270, 240 * 135, 120 * 67]
+# algorithmic HBM bytes per octave pixel: pyramid 4 read + 28 DoG written
+# (+1 next-octave base), extrema 28 read
+BYTES_PYR, BYTES_PYR_LAST, BYTES_EXT = 33.0, 32.0, 28.0
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_arm(args, rank: int, world: int):
+    """The unmodified reference through its own API (SiftData::Extract, cuSIFT.cu:61-120) on the same
+    config.  The reference is a CUDA library with no CPU implementation, so its arm runs on the GPU of
+    the box (rank 0 only); if oracle/_ref is absent the CPU oracle port is timed instead."""
+    if rank != 0:
+        return
+    import cusift_b200 as csb
+    from oracle import oracle as O
+    frames = max(4, min(args.frames_per_step, 24))      # bounded sample per step
+    img = csb.synth(W, H, 1000)
+    work = ROOT / "gpurun_out"
+    work.mkdir(exist_ok=True)
+    line = {"impl": "reference", "metric": "1080p ExtractSift frames/s", "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4: 1080p ExtractSift, synth(1920,1080,1000), 5 octaves, peakThresh 1.0, "
+                                   "edgeThresh 10, maxPts 16384", "frames_per_step": frames}}
+    if O.ref_available():
+        raw = work / "bench_ref_frame.f32"
+        np.ascontiguousarray(img, np.float32).tofile(raw)
+        iters = frames * args.steps
+        cmd = [O.REF_DRIVER, "bench", raw, W, H, N_OCT, 0.0, PEAK, EDGE, 0.0, MAXPTS, max(3, args.warmup), iters, 0]
+        out = subprocess.run([str(x) for x in cmd], capture_output=True, text=True, timeout=1200)
+        raw.unlink(missing_ok=True)
+        if out.returncode != 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"ref_driver failed rc={out.returncode}: "
+                                                                  f"{out.stderr[-200:]}"}))
+            return
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+        fps = 1000.0 / res["ms_per_frame"]
+        line.update({"value": fps, "ms_per_step": res["ms_per_frame"] * frames,
+                     "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                      "sample": f"{iters} x SiftData::Extract on one 1080p frame, unmodified reference "
+                                                "(CUDA library: 1 host thread + the box's GPU 0)"},
+                     "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "keypoints_per_frame": res["keypoints"]})
+    else:
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(2):
+            O.extract(img, N_OCT, 0.0, PEAK, EDGE, 0.0, False, MAXPTS)
+            n += 1
+        fps = n / (time.perf_counter() - t0)
+        line.update({"value": fps, "ms_per_step": 1000.0 * frames / fps,
+                     "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                      "sample": f"{n} frames, oracle/oracle.c (OpenMP)"},
+                     "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=512)
+    ap.add_argument("--pool", type=int, default=32)
+    ap.add_argument("--slots", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import cusift_b200 as csb
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = csb.Context(local_rank, args.slots)
+    prm = csb.make_params(N_OCT, 0.0, PEAK, EDGE, 0.0)
+    F = args.frames_per_step
+    # logical frames of this rank: global frame g = rank + world*i (cyclic shard), pool image g % pool
+    my_frames = csb.shard_frames(F * world, rank, world)
+    pool_ids = sorted({g % args.pool for g in my_frames})
+    pool_host = {i: csb.synth(W, H, 1000 + i) for i in pool_ids}
+    pool_dev = {}
+    pitch = csb.align_up(W, 128)
+    for i, im in pool_host.items():
+        pool_dev[i], pitch = ctx.upload_image(im)
+    # pinned host copies of the pool for the e2e arm
+    pins_img = {}
+    for i, im in pool_host.items():
+        pa = csb.PinnedArray(W * H, np.float32)
+        pa.array[:] = im.ravel()
+        pins_img[i] = pa
+    nbuf = max(2 * args.slots, 8)
+    d_sifts = [ctx.alloc(588 * MAXPTS) for _ in range(nbuf)]
+    pins = [csb.PinnedArray(MAXPTS) for _ in range(nbuf)]
+
+    dev_list = [pool_dev[g % args.pool] for g in my_frames]
+    host_list = [pins_img[g % args.pool].ptr for g in my_frames]
+    ds_list = [d_sifts[k % nbuf] for k in range(len(my_frames))]
+    hs_list = [pins[k % nbuf].ptr for k in range(len(my_frames))]
+
+    def step_device():
+        return ctx.extract_batch(dev_list, W, H, pitch, prm, ds_list, hs_list, MAXPTS)
+
+    def step_host():
+        return ctx.extract_batch(host_list, W, H, W, prm, ds_list, hs_list, MAXPTS, on_host=True)
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; device-clock time via CUDA events recorded on an idle
+        stream right after each synchronisation; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record()
+        t0 = time.perf_counter()
+        counts = None
+        for _ in range(steps):
+            counts = fn()
+        torch.cuda.synchronize()
+        e1.record()
+        e1.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count() - l0
+        t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t[0]), float(t[1]), launches, counts
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, wall_ms, launches, counts = timed(step_device, args.steps)
+    clocks = sampler.stop()
+    frames_total = F * world * args.steps
+    value = frames_total / (ms / 1e3)
+
+    for _ in range(args.warmup):
+        step_host()
+    ms_e, wall_e, launches_e, counts_e = timed(step_host, args.steps)
+    e2e_value = frames_total / (ms_e / 1e3)
+    kp_sum = int(np.sum(counts_e))
+    h2d = len(my_frames) * W * H * 4
+    d2h = kp_sum * 588 + len(my_frames) * 8
+
+    # single-frame latency (BASELINE config 2): median of 200 synchronous csb_extract calls
+    lat = []
+    for i in range(220):
+        t0 = time.perf_counter()
+        ctx.extract_batch(dev_list[:1], W, H, pitch, prm, ds_list[:1], hs_list[:1], MAXPTS)
+        if i >= 20:
+            lat.append((time.perf_counter() - t0) * 1e3)
+
+    # per-kernel device time, CUDA events on each launching stream, same workload (profiled pass)
+    ctx.profile(True)
+    ctx.profile_reset()
+    nprof = min(len(my_frames), 64)
+    ctx.extract_batch(dev_list[:nprof], W, H, pitch, prm, ds_list[:nprof], hs_list[:nprof], MAXPTS)
+    tab = ctx.profile_table()
+    ctx.profile(False)
+    peak, peak_src = peaks()
+    kernels = {}
+    for name, v in tab.items():
+        if not v["launches"]:
+            continue
+        avg_ms = v["total_ms"] / v["launches"]
+        ent = {"avg_us": round(avg_ms * 1e3, 2), "launches_per_frame": v["launches"] / nprof,
+               "us_per_frame": round(v["total_ms"] * 1e3 / nprof, 2)}
+        alg = None
+        if name.startswith("blur_dog") and name[-1].isdigit():
+            o = int(name[-1])
+            alg = OCT_PX[o] * (BYTES_PYR if name.startswith("blur_dog_down") else BYTES_PYR_LAST)
+        elif name.startswith("find_points") and name[-1].isdigit():
+            alg = OCT_PX[int(name[-1])] * BYTES_EXT
+        if alg:
+            ent["alg_bytes"] = alg
+            ent["achieved_gbs"] = round(alg / (avg_ms * 1e-3) / 1e9, 1)
+            ent["frac"] = round(ent["achieved_gbs"] / peak, 4)
+        kernels[name] = ent
+    hbm_kernels = {k: v for k, v in kernels.items() if "alg_bytes" in v}
+    dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["us_per_frame"]) if hbm_kernels else None
+    roofline = None
+    if dom:
+        d = hbm_kernels[dom]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": d["frac"], "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": d["alg_bytes"], "avg_launch_us": d["avg_us"]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        img = pool_host[pool_ids[0]]
+        t0 = time.perf_counter()
+        O.extract(img, N_OCT, 0.0, PEAK, EDGE, 0.0, False, MAXPTS)
+        one = time.perf_counter() - t0
+        n = int(max(2, min(12, 15.0 / max(one, 1e-3))))
+        t0 = time.perf_counter()
+        for k in range(n):
+            O.extract(pool_host[pool_ids[k % len(pool_ids)]], N_OCT, 0.0, PEAK, EDGE, 0.0, False, MAXPTS)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"{n} frames of the pool through oracle/oracle.c (OpenMP, all host cores)"}
+        try:
+            import cv2
+            cv2.setNumThreads(os.cpu_count())
+            sift = cv2.SIFT_create(nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6)
+            u8 = np.clip(img, 0, 255).astype(np.uint8)
+            t0 = time.perf_counter()
+            kps, _ = sift.detectAndCompute(u8, None)
+            cpu_baseline["opencv_sift"] = {"frames_per_s": 1.0 / (time.perf_counter() - t0), "keypoints": len(kps),
+                                           "threads": os.cpu_count()}
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline["opencv_sift"] = {"unavailable": repr(e)}
+
+    if rank == 0:
+        line = {
+            "metric": "1080p ExtractSift frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4: 1080p ExtractSift throughput, frames sharded cyclically over GPUs; pool of "
+                                   f"{args.pool} frames synth(1920,1080,1000+i) resident in HBM; 5 octaves, peakThresh 1.0, "
+                                   "edgeThresh 10, maxPts 16384",
+                       "frames_per_step_per_gpu": F, "frames_per_step": F * world, "slots_per_gpu": args.slots,
+                       "l2": f"inputs larger than L2: {len(pool_ids)} x 8.3 MB frame pool + {args.slots} x 90 MB pyramid "
+                             "workspaces cycle through HBM between reuses",
+                       "timed_region": "device frame -> SiftPoint array + count in pinned host memory"},
+            "ms_per_frame": ms / args.steps / (F * world), "wall_ms_per_step": wall_ms / args.steps,
+            "latency_ms_single_frame": {"median": statistics.median(lat), "p99": sorted(lat)[int(len(lat) * 0.99) - 1]},
+            "keypoints_per_frame": float(np.mean(counts)),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e / args.steps},
+            "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e),
+            "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    barrier()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -361,12 +361,20 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
   scale_down_kernel(k3);
 
   // pyramid: fine -> coarse (each octave base feeds its DoG stack and the next base)
+  static const char *kNameFused[CSB_MAX_OCTAVES] = {"blur_dog_down_o0", "blur_dog_down_o1", "blur_dog_down_o2",
+                                                    "blur_dog_down_o3", "blur_dog_down_o4", "blur_dog_down_o5",
+                                                    "blur_dog_down_o6", "blur_dog_down_o7"};
+  static const char *kNameBlur[CSB_MAX_OCTAVES] = {"blur_dog_o0", "blur_dog_o1", "blur_dog_o2", "blur_dog_o3",
+                                                   "blur_dog_o4", "blur_dog_o5", "blur_dog_o6", "blur_dog_o7"};
+  static const char *kNameFind[CSB_MAX_OCTAVES] = {"find_points_o0", "find_points_o1", "find_points_o2",
+                                                   "find_points_o3", "find_points_o4", "find_points_o5",
+                                                   "find_points_o6", "find_points_o7"};
   for (int o = 0; o < n_oct; o++) {
     const bool need_down = (o + 1 < n_oct);
     DogWeights W;
     if (active[o]) laplace_weights((float)initBlur[o], &W);
     if (active[o] && need_down && !ctx->no_fuse) {
-      LaunchScope ls(ctx, s, "blur_dog_down");
+      LaunchScope ls(ctx, s, kNameFused[o]);
       launch_blur_dog_down(oct[o].base, oct[o].w, oct[o].h, oct[o].pitch, oct[o].dog, W, oct[o + 1].base,
                            oct[o + 1].pitch, k3, st);
     } else {
@@ -375,7 +383,7 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
         launch_scale_down(oct[o].base, oct[o].w, oct[o].h, oct[o].pitch, oct[o + 1].base, oct[o + 1].pitch, k3, st);
       }
       if (active[o]) {
-        LaunchScope ls(ctx, s, "blur_dog");
+        LaunchScope ls(ctx, s, kNameBlur[o]);
         launch_blur_dog(oct[o].base, oct[o].w, oct[o].h, oct[o].pitch, oct[o].dog, W, st);
       }
     }
@@ -385,7 +393,7 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
     if (!active[o]) continue;
     ExtremaParams E;
     extrema_params(p, o, subs[o], &E);
-    LaunchScope ls(ctx, s, "find_points");
+    LaunchScope ls(ctx, s, kNameFind[o]);
     launch_find_points(oct[o].dog, oct[o].w, oct[o].h, oct[o].pitch, E, d_sift, s->d_oct, s->d_counter, max_pts, st);
   }
   {

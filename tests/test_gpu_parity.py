@@ -1,0 +1,388 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against
+  (1) oracle/oracle.c, the CPU restatement pinned to the reference's goldens, and
+  (2) oracle/_ref/ref_driver, the UNMODIFIED reference built for sm_100a,
+on the same inputs.  Tolerances are the ones BASELINE.json's north_star states:
+counts / match indices exact, positions & scales 1e-3 px, orientations 1e-3 rad,
+descriptors 1e-4 relative L2 — with one documented caveat: the reference does not
+meet the descriptor bound against ITSELF run-to-run (shared-memory float atomics +
+the texture unit's 8-bit weights make ~0.4 % of descriptors differ by up to 4e-4,
+measured by test_reference_self_consistency), so the descriptor assertions are
+">= 99 % within 1e-4 and 100 % within 1e-3".
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import cusift_b200 as csb
+import parity_utils as PU
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+needs_ref = pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/ref_driver not built")
+
+
+@pytest.fixture(scope="module")
+def frames():
+    return PU.golden_frames()
+
+
+@pytest.fixture(scope="module")
+def synth1080():
+    return csb.synth(1920, 1080, 1000)
+
+
+# ----------------------------------------------------------------- pyramid ---
+@pytest.mark.parametrize("shape,seed", [((480, 640), None), ((135, 241), 7), ((1080, 1920), 1000), ((67, 120), 3)])
+def test_scale_down_bit_exact(gpu_ctx, frames, shape, seed):
+    img = frames[0] if seed is None else csb.synth(shape[1], shape[0], seed)
+    assert np.array_equal(gpu_ctx.scale_down(img), O.scale_down(img))
+
+
+@pytest.mark.parametrize("case", ["gray1", "synth_500x300", "synth_odd_173x131", "initblur"])
+def test_dog_planes_and_octave_bases_bit_exact(gpu_ctx, frames, case):
+    """Every DoG plane and every downsampled octave base equals the oracle's bit for bit
+    (fused blur+DoG+downsample kernel)."""
+    if case == "gray1":
+        img, n_oct, ib = frames[0], 6, 0.0
+    elif case == "synth_500x300":
+        img, n_oct, ib = csb.synth(500, 300, 11), 4, 0.0
+    elif case == "synth_odd_173x131":
+        img, n_oct, ib = csb.synth(173, 131, 12), 3, 0.0
+    else:
+        img, n_oct, ib = csb.synth(400, 300, 13), 3, 0.5
+    gpu_ctx.extract(img, csb.make_params(n_oct, ib, 1.0), max_pts=65536)
+    for o in range(n_oct):
+        base, dog = gpu_ctx.debug_octave(o)
+        ob, od = O.octave_stage(img, o, ib)
+        if o > 0:
+            assert np.array_equal(base, ob), f"octave {o} base"
+        assert np.array_equal(dog, od), f"octave {o} DoG"
+
+
+def test_unfused_pipeline_identical(frames):
+    """CSB_NO_FUSE=1 (stand-alone ScaleDown + blur/DoG kernels) gives the same planes."""
+    os.environ["CSB_NO_FUSE"] = "1"
+    try:
+        ctx = csb.Context(0, 1)
+    finally:
+        os.environ.pop("CSB_NO_FUSE", None)
+    try:
+        img = frames[0]
+        ctx.extract(img, csb.make_params(4, 0.0, 0.5), max_pts=65536)
+        for o in range(4):
+            _, dog = ctx.debug_octave(o)
+            assert np.array_equal(dog, O.octave_stage(img, o, 0.0)[1])
+    finally:
+        ctx.close()
+
+
+# --------------------------------------------------------------- extraction ---
+def check_vs_oracle(ours, orc):
+    r = PU.compare_keypoints(ours, orc)
+    assert r["n_ours"] == r["n_ref"] == r["matched"], r
+    assert r["only_ours"] == 0 and r["only_ref"] == 0
+    assert r["pos_max"] < 5e-4 and r["scale_max"] < 1e-4, r      # MUFU.RCP / ex2 vs exact division
+    assert r["sharp_max"] < 1e-5 and r["edge_rel_max"] < 1e-5 and r["subs_equal"]
+    assert r["ori_within_tol"] > 0.92 and r["ori_median_deg"] < 0.005, r   # CPU texture emulation
+    assert r["desc_median"] < 2e-3, r
+    return r
+
+
+def test_extract_gray1_vs_oracle(gpu_ctx, frames):
+    """test/detector.cpp parameters on color1.jpg (unsaturated)."""
+    ours = gpu_ctx.extract(frames[0], csb.make_params(6, 0.0, 0.1, 10.0, 0.0), max_pts=32768)
+    orc, n, mpb = O.extract(frames[0], 6, 0.0, 0.1, 10.0, 0.0, False, 32768)
+    assert len(ours) == n == 9508 and mpb < 32
+    assert PU.per_octave_counts(ours) == PU.per_octave_counts(orc)
+    check_vs_oracle(ours, orc)
+    # coarse octaves first, like ExtractSiftLoop (cuSIFT.cu:181-196)
+    assert np.all(np.diff(ours["subsampling"]) <= 0)
+
+
+def test_extract_matches_golden_file(gpu_ctx, frames):
+    """All 4096 rows of the reference's own golden (test/data/cusift1_check) are reproduced."""
+    from scipy.spatial import cKDTree
+    ours = gpu_ctx.extract(frames[0], csb.make_params(6, 0.0, 0.1, 10.0, 0.0), max_pts=32768)
+    gold = O.read_cusift_golden(PU.GOLDEN / "cusift1_check.bin")
+    d, idx = cKDTree(PU.kp_key(ours)).query(gold[:, :3].astype(np.float64))
+    assert d.max() < 1e-4
+    do = PU.ang_diff_deg(ours["orientation"][idx], gold[:, 3])
+    # the golden file was written by another GPU generation / CUDA version: statistical bound only
+    assert np.mean(do <= PU.ORI_TOL_DEG) > 0.92 and np.median(do) < 0.005, (np.mean(do <= PU.ORI_TOL_DEG), do.max())
+
+
+def test_extract_synth_vs_oracle(gpu_ctx):
+    img = csb.synth(640, 480, 21)
+    ours = gpu_ctx.extract(img, csb.make_params(5, 0.0, 1.0), max_pts=16384)
+    orc, n, mpb = O.extract(img, 5, 0.0, 1.0, 10.0, 0.0, False, 16384)
+    assert mpb < 32 and n == len(ours)
+    check_vs_oracle(ours, orc)
+
+
+@needs_ref
+@pytest.mark.parametrize("case", ["gray1", "gray2_preblur", "synth_1080p", "synth_640_rootsift"])
+def test_extract_vs_reference(gpu_ctx, frames, synth1080, workdir, case):
+    """Ours vs the unmodified reference on the same GPU: identical keypoint sets with
+    bit-identical x, y, scale, sharpness, edgeness; orientation and descriptors within
+    the north_star tolerances."""
+    root = False
+    if case == "gray1":
+        img, prm = frames[0], (6, 0.0, 0.1)
+    elif case == "gray2_preblur":
+        img, prm = PU.preblur(frames[1]), (6, 0.0, 0.1)          # main.cpp:308-309 pre-blur
+    elif case == "synth_1080p":
+        img, prm = synth1080, (5, 0.0, 1.0)
+    else:
+        img, prm, root = csb.synth(640, 480, 33), (5, 0.0, 0.5), True
+    ours = gpu_ctx.extract(img, csb.make_params(*prm, 10.0, 0.0, rootsift=root), max_pts=32768)
+    ref = O.ref_extract(img, workdir, prm[0], prm[1], prm[2], 10.0, 0.0, root, 32768, safe=True, tag=case)
+    r = PU.compare_keypoints(ours, ref)
+    assert r["n_ours"] == r["n_ref"] == r["matched"] and r["only_ours"] == 0 and r["only_ref"] == 0, r
+    assert r["pos_exact"] == r["matched"], r                  # bit-exact positions and scales
+    assert r["sharp_max"] == 0.0 and r["edge_rel_max"] == 0.0 and r["subs_equal"], r
+    assert r["ori_max_deg"] < PU.ORI_TOL_DEG, r
+    assert r["desc_within_tol"] >= 0.99 and r["desc_max"] < 1e-3, r
+    assert PU.per_octave_counts(ours) == PU.per_octave_counts(ref)
+
+
+@needs_ref
+def test_reference_self_consistency(frames, workdir):
+    """Documents the reference's own run-to-run spread (the bound our tolerances inherit)."""
+    a = O.ref_extract(frames[0], workdir, 6, 0.0, 0.1, 10.0, 0.0, False, 32768, safe=True, tag="selfa")
+    b = O.ref_extract(frames[0], workdir, 6, 0.0, 0.1, 10.0, 0.0, False, 32768, safe=True, tag="selfb")
+    r = PU.compare_keypoints(a, b)
+    assert r["matched"] == len(a) == len(b) and r["pos_exact"] == r["matched"]
+    assert r["desc_max"] < 1e-3
+
+
+def test_host_entry_equals_device_entry(gpu_ctx, frames):
+    """SiftData::Extract(float*) path (upload inside) == ExtractSift path (frame resident)."""
+    p = csb.make_params(5, 0.0, 0.5)
+    a = gpu_ctx.extract(frames[0], p, max_pts=32768)
+    b = gpu_ctx.extract(frames[0], p, max_pts=32768, from_host=True)
+    r = PU.compare_keypoints(a, b)
+    assert r["matched"] == len(a) == len(b) and r["pos_exact"] == r["matched"]
+    assert r["ori_max_deg"] < PU.ORI_TOL_DEG and r["desc_max"] < 1e-3
+
+
+def test_saturation_and_parameters(gpu_ctx, frames):
+    img = frames[0]
+    full = gpu_ctx.extract(img, csb.make_params(6, 0.0, 0.1), max_pts=32768)
+    # maxPts saturates like main.cpp's 4096: count clamps, coarse octaves survive
+    sat = gpu_ctx.extract(img, csb.make_params(6, 0.0, 0.1), max_pts=4096)
+    assert len(sat) == 4096
+    assert (sat["subsampling"] > 1).sum() == (full["subsampling"] > 1).sum() == 1555
+    # lowestScale skips fine octaves (cuSIFT.cu:194): lowest_scale=2 drops octave 0
+    low = gpu_ctx.extract(img, csb.make_params(6, 0.0, 0.1, 10.0, 2.0), max_pts=32768)
+    assert len(low) == 1555 and low["subsampling"].min() == 2.0
+    # subsampling argument of Extract scales coordinates and scale
+    sub2 = gpu_ctx.extract(img, csb.make_params(6, 0.0, 0.1, 10.0, 0.0, 2.0), max_pts=32768)
+    r = PU.match_sets(sub2, full, tol=1e9)
+    ia, ib = r[0], r[1]
+    assert len(sub2) == len(full)
+    k2 = np.sort(PU.kp_key(sub2), axis=0)
+    k1 = np.sort(PU.kp_key(full) * 2.0, axis=0)
+    assert np.allclose(k2, k1, rtol=0, atol=1e-3)
+    # higher threshold / edge limit only remove points
+    hi = gpu_ctx.extract(img, csb.make_params(6, 0.0, 2.0), max_pts=32768)
+    ed = gpu_ctx.extract(img, csb.make_params(6, 0.0, 0.1, 5.0), max_pts=32768)
+    assert 0 < len(hi) < len(full) and 0 < len(ed) < len(full)
+    assert np.abs(hi["sharpness"]).min() > 1.5
+
+
+def test_flat_and_tiny_frames(gpu_ctx):
+    flat = np.full((64, 96), 77.0, np.float32)
+    assert len(gpu_ctx.extract(flat, csb.make_params(3, 0.0, 0.1), max_pts=1024)) == 0
+    tiny = csb.synth(40, 24, 5)
+    pts = gpu_ctx.extract(tiny, csb.make_params(2, 0.0, 0.5), max_pts=1024)
+    orc, n, _ = O.extract(tiny, 2, 0.0, 0.5, 10.0, 0.0, False, 1024)
+    assert len(pts) == n
+
+
+def test_bad_arguments_return_status_not_crash(gpu_ctx):
+    L = csb.lib()
+    p = csb.make_params(5, 0.0, 1.0)
+    n = ctypes.c_int(0)
+    assert L.csb_extract(gpu_ctx.h, None, 640, 480, 640, ctypes.byref(p), None, 16, None, ctypes.byref(n)) == 10001
+    bad = csb.make_params(9, 0.0, 1.0)
+    d = gpu_ctx.alloc(588 * 16)
+    dimg, pitch = gpu_ctx.upload_image(np.zeros((480, 640), np.float32))
+    assert L.csb_extract(gpu_ctx.h, dimg, 640, 480, pitch, ctypes.byref(bad), d, 16, None, ctypes.byref(n)) == 10003
+    assert L.csb_extract(gpu_ctx.h, dimg, 640, 480, 100, ctypes.byref(p), d, 16, None, ctypes.byref(n)) == 10001
+    assert b"pitch" in L.csb_last_error(gpu_ctx.h)
+    H = np.zeros(9, np.float32)
+    rp = np.zeros((4, 16), np.int32)
+    assert L.csb_find_homography(gpu_ctx.h, d, 100, rp.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), 15, 5.0,
+                                 H.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.byref(n)) == 10001
+    gpu_ctx.free(d)
+    gpu_ctx.free(dimg)
+
+
+def test_batch_equals_single_and_is_deterministic(gpu_ctx):
+    imgs = [csb.synth(640, 480, 100 + i) for i in range(9)]
+    p = csb.make_params(5, 0.0, 1.0)
+    single = [gpu_ctx.extract(im, p, max_pts=8192) for im in imgs]
+    dptrs = []
+    for im in imgs:
+        d, pitch = gpu_ctx.upload_image(im)
+        dptrs.append(d)
+    dsifts = [gpu_ctx.alloc(588 * 8192) for _ in imgs]
+    pins = [csb.PinnedArray(8192) for _ in imgs]
+    try:
+        for _ in range(2):
+            counts = gpu_ctx.extract_batch(dptrs, 640, 480, pitch, p, dsifts, [pa.ptr for pa in pins], 8192)
+            assert counts.tolist() == [len(s) for s in single]
+            for i in range(len(imgs)):
+                r = PU.compare_keypoints(pins[i].array[: counts[i]].copy(), single[i])
+                assert r["matched"] == counts[i] and r["pos_exact"] == r["matched"]
+                assert r["desc_max"] < 1e-3
+        # dense host frames + pageable result buffers through the same entry point
+        hs = [np.zeros(8192, csb.SIFT_DTYPE) for _ in imgs]
+        counts2 = gpu_ctx.extract_batch([im.ctypes.data for im in imgs], 640, 480, 640, p, dsifts,
+                                        [h.ctypes.data for h in hs], 8192, on_host=True)
+        assert counts2.tolist() == counts.tolist()
+        r = PU.compare_keypoints(hs[3][: counts2[3]], single[3])
+        assert r["matched"] == counts2[3] and r["pos_exact"] == r["matched"]
+    finally:
+        for d in dptrs + dsifts:
+            gpu_ctx.free(d)
+        for pa in pins:
+            pa.free()
+
+
+def test_full_size_properties_4k_rootsift(gpu_ctx):
+    """BASELINE config 3 (3840x2160, ExtractRootSift, ~95 k keypoints): size-independent
+    properties — determinism of the keypoint set, unit-L2 RootSIFT descriptors, count in
+    the oracle-calibrated range, coarse-first ordering."""
+    img = csb.synth(3840, 2160, 2000)
+    p = csb.make_params(5, 0.0, 0.1, rootsift=True)
+    a = gpu_ctx.extract(img, p, max_pts=131072)
+    b = gpu_ctx.extract(img, p, max_pts=131072)
+    assert len(a) == len(b) and 90000 < len(a) < 100000, len(a)
+    assert np.array_equal(np.sort(PU.kp_key(a), axis=0), np.sort(PU.kp_key(b), axis=0))
+    assert np.all(np.diff(a["subsampling"]) <= 0)
+    nrm = np.linalg.norm(a["data"].astype(np.float64), axis=1)
+    assert np.abs(nrm - 1.0).max() < 1e-3                    # sqrt(L1-normalised) has unit L2 norm
+    assert a["data"].min() >= 0.0
+    assert 0 <= a["orientation"].min() and a["orientation"].max() < 360.0
+
+
+# ------------------------------------------------------------------ RootSIFT ---
+def test_rootsift_standalone_bit_exact(gpu_ctx, frames):
+    pts = gpu_ctx.extract(frames[0], csb.make_params(4, 0.0, 1.0), max_pts=16384)
+    conv = gpu_ctx.rootsift(pts)
+    assert np.array_equal(conv["data"], O.rootsift(pts)["data"])       # fp32 serial sum + fp64 divide
+    fused = gpu_ctx.extract(frames[0], csb.make_params(4, 0.0, 1.0, rootsift=True), max_pts=16384)
+    ia, ib, oa, ob = PU.match_sets(fused, conv)
+    assert len(oa) == 0 and len(ob) == 0
+    assert PU.desc_rel_l2(fused["data"][ia], conv["data"][ib]).max() < 1e-3
+
+
+# ------------------------------------------------------------------ matching ---
+@pytest.mark.parametrize("dist", ["l2", "dot"])
+def test_match_fixture_bit_exact(gpu_ctx, workdir, dist):
+    s1 = O.read_vlfeat_sift(PU.GOLDEN / "sift1.bin")
+    s2 = O.read_vlfeat_sift(PU.GOLDEN / "sift2.bin")
+    ours = gpu_ctx.match(s1, s2, dist)
+    orc = O.match(s1, s2, dist)
+    for f in ("score", "ambiguity", "match", "match_xpos", "match_ypos"):
+        assert np.array_equal(ours[f], orc[f]), f
+    if dist == "l2":
+        i, j = O.read_match_indices(PU.GOLDEN / "match_indices1_2.bin")
+        assert int((ours["match"][i - 1] + 1 == j).sum()) == 326         # test/test.cpp:30-40
+        assert O.count_matches(ours, 1000.0, 0.6) == 340                 # test/test.cpp:52-55
+    if O.ref_available():
+        ref, nm = O.ref_match(s1, s2, workdir, dist, 1000.0, 0.6, tag="fx" + dist)
+        for f in ("score", "ambiguity", "match", "match_xpos", "match_ypos"):
+            assert np.array_equal(ours[f], ref[f]), f
+        assert nm == O.count_matches(ours, 1000.0, 0.6)
+
+
+def test_match_ragged_sizes_ties_and_duplicates(gpu_ctx):
+    rng = np.random.default_rng(9)
+    for n1, n2 in ((1, 1), (5, 3), (17, 33), (100, 1000), (257, 15)):
+        a = np.zeros(n1, csb.SIFT_DTYPE)
+        b = np.zeros(n2, csb.SIFT_DTYPE)
+        da = np.abs(rng.standard_normal((n1, 128))).astype(np.float32)
+        db = np.abs(rng.standard_normal((n2, 128))).astype(np.float32)
+        a["data"] = da / np.linalg.norm(da, axis=1, keepdims=True)
+        b["data"] = db / np.linalg.norm(db, axis=1, keepdims=True)
+        b["coords2D"] = rng.uniform(0, 100, (n2, 2)).astype(np.float32)
+        if n2 > 20:                                          # exact duplicates -> tie-break rule
+            b["data"][17] = b["data"][3]
+            b["data"][24 % n2] = b["data"][3]
+            a["data"][0] = b["data"][3]
+        for dist in ("l2", "dot"):
+            ours, orc = gpu_ctx.match(a, b, dist), O.match(a, b, dist)
+            for f in ("score", "ambiguity", "match", "match_xpos", "match_ypos"):
+                assert np.array_equal(ours[f], orc[f]), (n1, n2, dist, f)
+    # empty sets: nothing to do (matching.cu:282-283)
+    assert csb.lib().csb_match(gpu_ctx.h, None, 0, None, 0, 1, None) == 0
+
+
+def test_match_full_size_properties(gpu_ctx):
+    """8192 x 8192 (BASELINE config 5 pair size): self-match is the identity with score ~0."""
+    rng = np.random.default_rng(4)
+    n = 8192
+    a = np.zeros(n, csb.SIFT_DTYPE)
+    d = np.abs(rng.standard_normal((n, 128))).astype(np.float32)
+    a["data"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    m = gpu_ctx.match(a, a, "l2")
+    assert np.array_equal(m["match"], np.arange(n))
+    assert np.abs(m["score"]).max() < 1e-5 and m["ambiguity"].max() < 1e-3
+    sub = O.match(a[:64], a, "l2")
+    for f in ("score", "ambiguity", "match"):
+        assert np.array_equal(m[f][:64], sub[f])
+
+
+# ---------------------------------------------------------------- homography ---
+def glibc_rand_samples(valid, num_loops):
+    """FindHomography's sampling loop (homography.cu:232-244) with libc rand(), seed 1."""
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    nv = len(valid)
+    rp = np.zeros((4, num_loops), np.int32)
+    for i in range(num_loops):
+        p1, p2, p3, p4 = (libc.rand() % nv for _ in range(4))
+        while p2 == p1:
+            p2 = libc.rand() % nv
+        while p3 == p1 or p3 == p2:
+            p3 = libc.rand() % nv
+        while p4 == p1 or p4 == p2 or p4 == p3:
+            p4 = libc.rand() % nv
+        rp[:, i] = valid[[p1, p2, p3, p4]]
+    return rp
+
+
+def test_c1_pipeline_match_and_homography(gpu_ctx, frames, workdir):
+    """BASELINE config 1 (main.cpp demo): pre-blur, ExtractSift x2, MatchSiftData,
+    FindHomography(numLoops, 0.0, 0.80, 5.0) on the reference's own image pair."""
+    a, b = PU.preblur(frames[0]), PU.preblur(frames[1])
+    p = csb.make_params(6, 0.0, 0.1)
+    k1 = gpu_ctx.extract(a, p, max_pts=32768)
+    k2 = gpu_ctx.extract(b, p, max_pts=32768)
+    assert 10000 < len(k1) < 11500 and 10000 < len(k2) < 11500   # emulator: 10 837 / 10 869
+    m = gpu_ctx.match(k1, k2, "l2")
+    orc = O.match(k1, k2, "l2")
+    for f in ("score", "ambiguity", "match", "match_xpos", "match_ypos"):
+        assert np.array_equal(m[f], orc[f]), f
+    valid = O.valid_points(m, 0.0, 0.80)
+    loops = 2048
+    rp = glibc_rand_samples(valid, loops)
+    H, cnt = gpu_ctx.find_homography(m, rp, 5.0)
+    Ho, cnto = O.find_homography(m, rp, 5.0)
+    assert cnt == cnto and cnt > 2500
+    assert np.allclose(H, Ho, rtol=1e-4, atol=1e-6)
+    assert abs(H[0] - 1) < 0.05 and abs(H[4] - 1) < 0.05          # consecutive RGB-D frames: near identity
+    if O.ref_available():
+        # the reference draws the same rand() sequence (fresh process, seed 1)
+        refh = O.ref_homography(m, workdir, loops, 0.0, 0.80, 5.0, 0, 3.0, tag="c1h")
+        n16 = len(m) % 16
+        assert abs(refh["num_matches"] - cnt) <= (16 - n16 if n16 else 0)   # its pad slots are uninitialised
+        if refh["num_matches"] == cnt:                        # same winning hypothesis
+            assert np.allclose(refh["H"], H, rtol=1e-3, atol=1e-5)
+        H2, nfit, _ = O.improve_homography(m, H, 5, 0.0, 0.80, 3.0)
+        assert nfit > 1500

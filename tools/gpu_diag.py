@@ -366,5 +366,7 @@ def _():
     return res
 
 
+import shutil  # noqa: E402
+shutil.rmtree(WORK, ignore_errors=True)   # keep gpurun_out small (64 MiB cap)
 print("DIAG DONE")
 (OUT / "diag.json").write_text(json.dumps(REPORT, indent=1, default=str))
