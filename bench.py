@@ -269,7 +269,8 @@ def main():
     ctx.profile(True)
     ctx.profile_reset()
     nprof = min(len(my_frames), 64)
-    ctx.extract_batch(dev_list[:nprof], W, H, pitch, prm, ds_list[:nprof], hs_list[:nprof], MAXPTS)
+    for k in range(nprof):     # one frame in flight: kernels are timed alone, not overlapped with other slots
+        ctx.extract_batch(dev_list[k:k + 1], W, H, pitch, prm, ds_list[k:k + 1], hs_list[k:k + 1], MAXPTS)
     tab = ctx.profile_table()
     ctx.profile(False)
     peak, peak_src = peaks()

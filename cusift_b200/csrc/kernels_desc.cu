@@ -12,9 +12,16 @@
 // clamp, unnormalised coordinates, raw — not +0.5 — coordinates), because the
 // hardware filter's 1.8 fixed-point weights are part of the reference's results.
 // The sample-coordinate and weight arithmetic follows the reference's sm_100a
-// SASS (which products are fused, which are not); the histogram sums are
-// accumulated with shared-memory atomics whose order is unspecified in the
-// reference as well (cuSIFT_D.cu:234-253,343), hence the comparison tolerances.
+// SASS (which products are fused, which are not).  The histogram sums are the one
+// place where the reference is nondeterministic (shared-memory float atomicAdd,
+// cuSIFT_D.cu:234-253,343 — a CAS loop on sm_100a that serialises on every bin
+// collision).  Here they are accumulated WITHOUT atomics and in a fixed order:
+//   orientation: every lane owns a private 32-bin column in shared memory
+//                (hist[bin][lane], bank = lane), reduced by a skewed read;
+//   descriptor : lane = (half, cell_y, cell_x) samples its own 4x4 cell, so at each
+//                of the 8 trilinear vote sites the 16 lanes of a half hit 16
+//                different cells; the two halves own separate 128-bin copies.
+// Results are run-to-run deterministic and within the reference's own spread.
 #include "csb_internal.h"
 
 namespace {
@@ -43,10 +50,15 @@ __device__ __forceinline__ float sumsq_tree(const float (&b)[4], int lane) {
   return __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
 }
 
-__device__ __forceinline__ void vote(float *buf, int idx, float v) {
-  // votes past buffer[128] exist in the reference (cuSIFT_D.cu:243 guard is off by
-  // one; angi can be 8) and land beyond its last shared array: dropped here.
-  if (idx >= 0 && idx < 128) atomicAdd(buf + idx, v);
+constexpr int DCOPY = 128 + 16;   // one descriptor copy: 128 bins + a dummy slot per lane of the half
+
+// Plain read-modify-write vote: the caller guarantees that no two lanes of the warp
+// target the same address in the same call (see the lane->cell mapping below).
+__device__ __forceinline__ void vote(float *copy, int idx, float v, int dummy) {
+  const bool ok = (idx >= 0) && (idx < 128);   // votes past buffer[128] land outside the reference's arrays: dropped
+  float *q = copy + (ok ? idx : dummy);
+  *q = __fadd_rn(*q, ok ? v : 0.0f);
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constant__ OctaveTexSet T,
@@ -54,14 +66,19 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
                                                             const int *__restrict__ d_oct,
                                                             const unsigned int *__restrict__ counter, int max_pts,
                                                             int rootsift) {
-  __shared__ float s_hist[WARPS][64];
+  __shared__ __align__(16) float s_hist[WARPS][32 * 32];   // orientation: [bin][lane] private columns
+  __shared__ float s_sm[WARPS][64];                         // reduced + smoothed orientation histogram
   __shared__ float s_gauss[WARPS][16];
-  __shared__ float s_buf[WARPS][128];
+  __shared__ float s_buf[WARPS][2 * DCOPY];                 // descriptor: one copy per half-warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float *hist = s_hist[warp], *gauss = s_gauss[warp], *buf = s_buf[warp];
+  float *hist = s_hist[warp], *sm = s_sm[warp], *gauss = s_gauss[warp], *buf = s_buf[warp];
   const unsigned int cnt = *counter;
   const int n = (int)min(cnt, (unsigned int)max_pts);
+  // descriptor sampling pattern: lane = half*16 + cell_y*4 + cell_x
+  const int half = lane >> 4, cellx = lane & 3, celly = (lane >> 2) & 3;
+  float *copy = buf + half * DCOPY;
+  const int dummy = 128 + (lane & 15);
 
   for (int k = blockIdx.x * WARPS + warp; k < n; k += gridDim.x * WARPS) {
     csb_sift_point *pt = d_sift + k;
@@ -74,8 +91,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
       const float d = (float)(lane - 5);
       gauss[lane] = expf(__fmul_rn(__fmul_rn(d, i2sigma2), d));
     }
-    hist[lane] = 0.0f;
-    hist[lane + 32] = 0.0f;
+    {
+      float4 *z = reinterpret_cast<float4 *>(hist + lane * 32);
+#pragma unroll
+      for (int j = 0; j < 8; j++) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncwarp();
     const float xp = __fsub_rn(px, 5.0f), yp = __fsub_rn(py, 5.0f);
     for (int s = lane; s < 121; s += 32) {
@@ -86,26 +106,35 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
       int bin = (int)__fadd_rn(__fdiv_rn(__fmul_rn(16.0f, atan2f(dy, dx)), 3.1416f), 16.5f);
       if (bin > 31) bin = 0;
       const float grad = sqrtf(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-      atomicAdd(hist + bin, __fmul_rn(__fmul_rn(grad, gauss[xd]), gauss[yd]));
+      float *q = hist + bin * 32 + lane;          // private column: no other lane touches it
+      *q = __fadd_rn(*q, __fmul_rn(__fmul_rn(grad, gauss[xd]), gauss[yd]));
     }
     __syncwarp();
     {
-      const float h0 = hist[lane];
-      const float h1 = __fadd_rn(hist[(lane + 31) & 31], hist[(lane + 1) & 31]);
-      const float h2 = __fadd_rn(hist[(lane + 30) & 31], hist[(lane + 2) & 31]);
-      hist[32 + lane] = __fadd_rn(__fmaf_rn(h0, 6.0f, __fmul_rn(h1, 4.0f)), h2);
+      // lane b sums bin b over the 32 private columns, skewed so that banks differ
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int l = 0; l < 32; l++) acc = __fadd_rn(acc, hist[lane * 32 + ((l + lane) & 31)]);
+      sm[lane] = acc;
+    }
+    __syncwarp();
+    {
+      const float h0 = sm[lane];
+      const float h1 = __fadd_rn(sm[(lane + 31) & 31], sm[(lane + 1) & 31]);
+      const float h2 = __fadd_rn(sm[(lane + 30) & 31], sm[(lane + 2) & 31]);
+      sm[32 + lane] = __fadd_rn(__fmaf_rn(h0, 6.0f, __fmul_rn(h1, 4.0f)), h2);
     }
     __syncwarp();
     float orient;
     {
-      const float v = hist[32 + lane];
-      const float pk = (v > hist[32 + ((lane + 31) & 31)] && v >= hist[32 + ((lane + 1) & 31)]) ? v : 0.0f;
+      const float v = sm[32 + lane];
+      const float pk = (v > sm[32 + ((lane + 31) & 31)] && v >= sm[32 + ((lane + 1) & 31)]) ? v : 0.0f;
       // serial scan of the reference (strict >, first maximum wins) == lowest lane holding the maximum
       const float maxval1 = warp_max(pk);
       const unsigned int who = __ballot_sync(FULL, pk == maxval1);
       const int i1 = (maxval1 > 0.0f) ? (__ffs(who) - 1) : -1;
-      const float val1 = hist[32 + ((i1 + 1) & 31)];
-      const float val2 = hist[32 + ((i1 + 31) & 31)];
+      const float val1 = sm[32 + ((i1 + 1) & 31)];
+      const float val2 = sm[32 + ((i1 + 31) & 31)];
       const float peak = __fadd_rn(
           (float)i1, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(val1, val2)),
                                __fsub_rn(__fsub_rn(__fadd_rn(maxval1, maxval1), val1), val2)));
@@ -118,15 +147,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
       const float d = __fsub_rn((float)lane, 7.5f);
       gauss[lane] = expf(__fdiv_rn(__fmul_rn(-d, d), 128.0f));
     }
-#pragma unroll
-    for (int j = 0; j < 4; j++) buf[lane + 32 * j] = 0.0f;
+    for (int j = lane; j < 2 * DCOPY; j += 32) buf[j] = 0.0f;
     __syncwarp();
     const float theta = __fmul_rn(2.0f * 3.1415f / 360.0f, orient);
     const float sina = sinf(theta), cosa = cosf(theta);
     const float sc = __fmul_rn(pscale, 0.75f);
     const float ssina = __fmul_rn(sina, sc), scosa = __fmul_rn(cosa, sc);
-    for (int s = lane; s < 256; s += 32) {
-      const int tx = s & 15, y = s >> 4;
+#pragma unroll 1
+    for (int it = 0; it < 8; it++) {
+      const int j = it * 2 + half;                 // sample within the lane's 4x4 cell
+      const int tx = 4 * cellx + (j & 3), y = 4 * celly + (j >> 2);
       const float ftx = __fsub_rn((float)tx, 7.5f), fy = __fsub_rn((float)y, 7.5f);
       const float xpos = __fmaf_rn(-ssina, fy, __fadd_rn(__fmul_rn(ftx, scosa), px));
       const float ypos = __fmaf_rn(scosa, fy, __fadd_rn(__fmul_rn(ftx, ssina), py));
@@ -148,31 +178,30 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
       const float iangf = __fsub_rn(1.0f, angf);
       const int hbase = 8 * (4 * veri + hori);
       const int p1 = angi + hbase, p2 = angp + hbase;
-      if (tx >= 2) {
-        const float grad1 = __fmul_rn(ihorf, grad);
-        if (y >= 2) {
-          const float grad2 = __fmul_rn(iverf, grad1);
-          vote(buf, p1, __fmul_rn(iangf, grad2));
-          vote(buf, p2, __fmul_rn(angf, grad2));
+      // the four spatial shares (guards of cuSIFT_D.cu:230-255; `tx<=14` sic)
+      const bool gl = tx >= 2, gr = tx <= 14, gu = y >= 2, gd = y <= 13;
+      const float gUL = __fmul_rn(iverf, __fmul_rn(ihorf, grad)), gDL = __fmul_rn(verf, __fmul_rn(ihorf, grad));
+      const float gUR = __fmul_rn(iverf, __fmul_rn(horf, grad)), gDR = __fmul_rn(verf, __fmul_rn(horf, grad));
+      // angi == 8 (atan2f >= 3.1415) makes p1 point at bin 0 of the NEXT cell, which another lane may be
+      // voting into at the same site: those (rare) votes are deferred to an atomic pass below.
+      const bool spill = angi >= 8;
+      const int q1 = spill ? -1 : p1;
+      vote(copy, (gl && gu) ? q1 : -1, __fmul_rn(iangf, gUL), dummy);
+      vote(copy, (gl && gu) ? p2 : -1, __fmul_rn(angf, gUL), dummy);
+      vote(copy, (gl && gd) ? q1 + 32 : -1, __fmul_rn(iangf, gDL), dummy);
+      vote(copy, (gl && gd) ? p2 + 32 : -1, __fmul_rn(angf, gDL), dummy);
+      vote(copy, (gr && gu) ? q1 + 8 : -1, __fmul_rn(iangf, gUR), dummy);
+      vote(copy, (gr && gu) ? p2 + 8 : -1, __fmul_rn(angf, gUR), dummy);
+      vote(copy, (gr && gd) ? q1 + 40 : -1, __fmul_rn(iangf, gDR), dummy);
+      vote(copy, (gr && gd) ? p2 + 40 : -1, __fmul_rn(angf, gDR), dummy);
+      if (__any_sync(FULL, spill)) {
+        if (spill) {
+          if (gl && gu && p1 < 128) atomicAdd(copy + p1, __fmul_rn(iangf, gUL));
+          if (gl && gd && p1 + 32 < 128) atomicAdd(copy + p1 + 32, __fmul_rn(iangf, gDL));
+          if (gr && gu && p1 + 8 < 128) atomicAdd(copy + p1 + 8, __fmul_rn(iangf, gUR));
+          if (gr && gd && p1 + 40 < 128) atomicAdd(copy + p1 + 40, __fmul_rn(iangf, gDR));
         }
-        if (y <= 13) {
-          const float grad2 = __fmul_rn(verf, grad1);
-          vote(buf, p1 + 32, __fmul_rn(iangf, grad2));
-          vote(buf, p2 + 32, __fmul_rn(angf, grad2));
-        }
-      }
-      if (tx <= 14) {   // sic: reproduces the reference's guard (cuSIFT_D.cu:243)
-        const float grad1 = __fmul_rn(horf, grad);
-        if (y >= 2) {
-          const float grad2 = __fmul_rn(iverf, grad1);
-          vote(buf, p1 + 8, __fmul_rn(iangf, grad2));
-          vote(buf, p2 + 8, __fmul_rn(angf, grad2));
-        }
-        if (y <= 13) {
-          const float grad2 = __fmul_rn(verf, grad1);
-          vote(buf, p1 + 40, __fmul_rn(iangf, grad2));
-          vote(buf, p2 + 40, __fmul_rn(angf, grad2));
-        }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -180,7 +209,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
     // normalise, clamp at 0.2, normalise (cuSIFT_D.cu:259-291)
     float b[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) b[j] = buf[lane + 32 * j];
+    for (int j = 0; j < 4; j++) b[j] = __fadd_rn(buf[lane + 32 * j], buf[DCOPY + lane + 32 * j]);
     const float r1 = rsqrtf(sumsq_tree(b, lane));
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -194,6 +223,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
     if (rootsift) {
       // ConvertSiftToRootSift_D (cuSIFT_D.cu:299-317): serial fp32 sum over i=0..127,
       // then sqrtf((float)(max(0.0,(double)d) / (double)sum)).
+      __syncwarp();
 #pragma unroll
       for (int j = 0; j < 4; j++) buf[lane + 32 * j] = b[j];
       __syncwarp();
@@ -245,11 +275,16 @@ __global__ void __launch_bounds__(256) k_copy_out(const csb_sift_point *__restri
   const unsigned int cnt = *counter;
   const int n = (int)min(cnt, (unsigned int)max_pts);
   if (h_sift != nullptr) {
-    const size_t words = (size_t)n * (sizeof(csb_sift_point) / 4);
+    // 128-bit stores: a warp emits 512 contiguous bytes per instruction towards PCIe
+    const size_t bytes = (size_t)n * sizeof(csb_sift_point);
+    const size_t vecs = bytes / 16;
+    const uint4 *src4 = reinterpret_cast<const uint4 *>(d_sift);
+    uint4 *dst4 = reinterpret_cast<uint4 *>(h_sift);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vecs; i += stride) dst4[i] = src4[i];
     const uint32_t *src = reinterpret_cast<const uint32_t *>(d_sift);
     uint32_t *dst = reinterpret_cast<uint32_t *>(h_sift);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
-      dst[i] = src[i];
+    for (size_t i = vecs * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes / 4; i += stride) dst[i] = src[i];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     h_count[0] = n;

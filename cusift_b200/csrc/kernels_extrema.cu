@@ -1,134 +1,254 @@
 // DoG extrema detection, sub-pixel refinement, edge rejection and compaction.
 //
 // Replaces FindPointsMulti_D (reference cuSIFT_D.cu:402-523, host side
-// cuSIFT.cu:424-455).  Differences in structure, not in results:
-//   * one pass over the octave (each thread owns a pixel column of the 5 centre
-//     planes) instead of 5 overlapping scale-blocks; a DoG value is fetched once
-//     for the |v|>thresh gate and neighbours are only touched behind that gate;
-//   * no 32-entry block-local list (the reference's wraps, cuSIFT_D.cu:455,465):
-//     keypoints are compacted with warp ballots, one atomicAdd per warp;
+// cuSIFT.cu:424-455).  Same results, different structure:
+//   * ONE pass over the 7 DoG planes of an octave (28 B/pixel, each value fetched
+//     once) instead of 5 overlapping scale-blocks that re-read every plane ~3x.
+//     A warp owns 30 columns (+1 halo lane each side) and streams rows downwards;
+//     per plane a 3-row window lives in registers, horizontal neighbours come
+//     from warp shuffles, and the 26-neighbour test is a separable min/max network
+//     (3-input FMNMX): per plane  hx = max3(left, v, right),
+//     F = max3(hx[y-1], hx[y], hx[y+1]) (full 3x3),  E = max3(hx[y-1], hx[y+1],
+//     max(left,right)) (3x3 without the centre);  v is a strict maximum iff
+//     v > max3(F[plane-1], F[plane+1], E[plane]).  No shared memory, no barriers
+//     in the scan.
+//   * candidates go to a small per-CTA list (never wraps: overflow is refined in
+//     place; the reference's 32-entry list silently wraps, cuSIFT_D.cu:455,465);
+//     after the scan the CTA refines them densely and compacts survivors with
+//     warp ballots, one global atomicAdd per warp.
 //   * the refinement is evaluated in the exact multiply-add order of the
 //     reference's sm_100a SASS, so x, y, scale, sharpness and edgeness are
 //     bit-identical to the reference's for the same DoG input.
+#include <type_traits>
+
 #include "csb_internal.h"
 
 namespace {
 
-__device__ __forceinline__ bool strict_extremum(const float *__restrict__ dog, size_t plane, int pitch, int sc, int x,
-                                                int y, float v, bool isMax) {
-  // 26 neighbours on planes sc, sc+1, sc+2 (cuSIFT_D.cu:430-470); interior pixels only.
-#pragma unroll
-  for (int p = 0; p < 3; p++) {
-    const float *q = dog + (size_t)(sc + p) * plane + (size_t)y * pitch + x;
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++) {
-#pragma unroll
-      for (int dx = -1; dx <= 1; dx++) {
-        if (p == 1 && dy == 0 && dx == 0) continue;
-        const float u = q[dy * pitch + dx];
-        if (isMax ? !(v > u) : !(v < u)) return false;
-      }
-    }
+constexpr int XT_COLS = 30;          // output columns per warp
+constexpr int XT_WARPS = 4;
+constexpr int XT_TW = XT_COLS * XT_WARPS;   // 120 output columns per CTA
+constexpr int XT_ROWS = 36;          // output rows per CTA (multiple of 3)
+constexpr int XT_CAP = 512;          // candidate list entries per CTA
+constexpr int NPL = CSB_NUM_DOG;     // 7 planes
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+struct Refined {
+  float x, y, scale, sharp, edge;
+};
+
+// cuSIFT_D.cu:474-522 in the reference's evaluation order.  Returns false when the
+// edge test rejects the candidate.
+__device__ __forceinline__ bool refine(const float *__restrict__ dog, size_t plane, int pitch,
+                                       const ExtremaParams &P, int x, int y, int sc, Refined &o) {
+  const float *p1 = dog + (size_t)(sc + 1) * plane + (size_t)y * pitch + x;
+  const float *p0 = p1 - plane, *p2 = p1 + plane;
+  const float val = p1[0];
+  const float two = __fadd_rn(val, val);
+  const float dxx = __fsub_rn(__fsub_rn(two, p1[-1]), p1[1]);
+  const float dyy = __fsub_rn(__fsub_rn(two, p1[-pitch]), p1[pitch]);
+  const float dxy =
+      __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(p1[pitch + 1], p1[-pitch - 1]), p1[-pitch + 1]), p1[pitch - 1]));
+  const float tra = __fadd_rn(dxx, dyy);
+  const float det = __fmaf_rn(dxx, dyy, -__fmul_rn(dxy, dxy));
+  const float tra2 = __fmul_rn(tra, tra);
+  if (!(tra2 < __fmul_rn(det, P.edge_limit))) return false;
+  const float edge = __fdividef(tra2, det);
+  const float dx = __fmul_rn(0.5f, __fsub_rn(p1[1], p1[-1]));
+  const float dy = __fmul_rn(0.5f, __fsub_rn(p1[pitch], p1[-pitch]));
+  const float ds = __fmul_rn(0.5f, __fsub_rn(p0[0], p2[0]));
+  const float dss = __fsub_rn(__fsub_rn(two, p2[0]), p0[0]);
+  const float dxs = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(p2[1], p0[-1]), p0[1]), p2[-1]));
+  const float dys = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(p2[pitch], p0[-pitch]), p2[-pitch]), p0[pitch]));
+  const float idxx = __fmaf_rn(dyy, dss, -__fmul_rn(dys, dys));
+  const float idxy = __fmaf_rn(dxs, dys, -__fmul_rn(dxy, dss));
+  const float idxs = __fmaf_rn(dxy, dys, -__fmul_rn(dyy, dxs));
+  const float den = __fmaf_rn(dxs, idxs, __fmaf_rn(dxx, idxx, __fmul_rn(dxy, idxy)));
+  const float idet = __fdividef(1.0f, den);
+  const float idyy = __fmaf_rn(dxx, dss, -__fmul_rn(dxs, dxs));
+  const float idys = __fmaf_rn(dxy, dxs, -__fmul_rn(dxx, dys));
+  const float idss = det;   // dxx*dyy - dxy*dxy: same value (CSE'd in the reference too)
+  float pdx = __fmul_rn(idet, __fmaf_rn(ds, idxs, __fmaf_rn(dx, idxx, __fmul_rn(dy, idxy))));
+  float pdy = __fmul_rn(idet, __fmaf_rn(ds, idys, __fmaf_rn(dy, idyy, __fmul_rn(dx, idxy))));
+  float pds = __fmul_rn(idet, __fmaf_rn(idss, ds, __fmaf_rn(dx, idxs, __fmul_rn(dy, idys))));
+  if (pdx < -0.5f || pdx > 0.5f || pdy < -0.5f || pdy > 0.5f || pds < -0.5f || pds > 0.5f) {
+    pdx = __fdividef(dx, dxx);
+    pdy = __fdividef(dy, dyy);
+    pds = __fdividef(ds, dss);
   }
+  const float dval = __fmaf_rn(ds, pds, __fmaf_rn(dx, pdx, __fmul_rn(dy, pdy)));
+  o.x = __fadd_rn((float)x, pdx);
+  o.y = __fadd_rn((float)y, pdy);
+  o.scale = __fmul_rn(P.scales[sc], exp2f(__fmul_rn(pds, P.factor)));
+  o.sharp = __fmaf_rn(dval, 0.5f, val);
+  o.edge = edge;
   return true;
 }
 
-__global__ void __launch_bounds__(256) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
-                                                     const __grid_constant__ ExtremaParams P,
-                                                     csb_sift_point *__restrict__ d_sift, int *__restrict__ d_oct,
-                                                     unsigned int *__restrict__ counter, int max_pts) {
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * 8 + threadIdx.y;
-  const int lane = threadIdx.x;   // blockDim.x == 32: one warp per tile row
-  // image-border pixels can never be strict extrema (their clamped neighbours
-  // include the pixel itself, cuSIFT_D.cu:416,427-429)
-  const bool inside = (x >= 1 && y >= 1 && x < w - 1 && y < h - 1);
-  const size_t plane = (size_t)pitch * h;
+__device__ __forceinline__ void store_point(csb_sift_point *__restrict__ d_sift, int *__restrict__ d_oct,
+                                            unsigned int idx, const Refined &r, const ExtremaParams &P) {
+  csb_sift_point *o = d_sift + idx;
+  o->coords2D[0] = r.x;
+  o->coords2D[1] = r.y;
+  o->scale = r.scale;
+  o->sharpness = r.sharp;
+  o->edgeness = r.edge;
+  o->orientation = 0.f;
+  o->score = 0.f;
+  o->ambiguity = 0.f;
+  o->match = 0;
+  o->match_xpos = 0.f;
+  o->match_ypos = 0.f;
+  o->match_error = 0.f;
+  o->subsampling = P.subsampling;
+  o->empty[0] = o->empty[1] = o->empty[2] = 0.f;
+  o->coords3D[0] = o->coords3D[1] = o->coords3D[2] = 0.f;
+  d_oct[idx] = P.octave;
+}
 
-#pragma unroll 1
-  for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
+// Warp-ballot compaction of `emit` lanes into the global list (whole warp must call).
+__device__ __forceinline__ void emit_warp(bool emit, const Refined &r, const ExtremaParams &P,
+                                          csb_sift_point *__restrict__ d_sift, int *__restrict__ d_oct,
+                                          unsigned int *__restrict__ counter, int max_pts, int lane) {
+  const unsigned int m = __ballot_sync(FULL, emit);
+  if (!m) return;
+  const int leader = __ffs(m) - 1;
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+  base = __shfl_sync(FULL, base, leader);
+  if (emit) {
+    const unsigned int idx = base + __popc(m & ((1u << lane) - 1u));
+    if (idx < (unsigned int)max_pts) store_point(d_sift, d_oct, idx, r, P);
+  }
+}
+
+// Slow path for a full candidate list: refine and append immediately.
+__device__ __noinline__ void refine_in_place(const float *__restrict__ dog, size_t plane, int pitch,
+                                             const ExtremaParams &P, int x, int y, int sc,
+                                             csb_sift_point *__restrict__ d_sift, int *__restrict__ d_oct,
+                                             unsigned int *__restrict__ counter, int max_pts) {
+  Refined r;
+  if (refine(dog, plane, pitch, P, x, y, sc, r)) {
+    const unsigned int idx = atomicAdd(counter, 1u);
+    if (idx < (unsigned int)max_pts) store_point(d_sift, d_oct, idx, r, P);
+  }
+}
+
+struct Win {
+  float v[NPL][3];    // DoG value at this thread's column, 3-row window
+  float sx[NPL][3];   // max(left, right)
+  float sn[NPL][3];   // min(left, right)
+};
+
+__global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
+                                                               const __grid_constant__ ExtremaParams P,
+                                                               csb_sift_point *__restrict__ d_sift,
+                                                               int *__restrict__ d_oct,
+                                                               unsigned int *__restrict__ counter, int max_pts) {
+  __shared__ unsigned int s_cnt;
+  __shared__ unsigned int s_list[XT_CAP];   // x | y << 14 | scale << 28
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * XT_TW + warp * XT_COLS - 1 + lane;
+  const int cx = clampi(x, 0, w - 1);
+  const int y0 = blockIdx.y * XT_ROWS;
+  const size_t plane = (size_t)pitch * h;
+  // image-border pixels can never be strict extrema (their clamped neighbours include
+  // the pixel itself, cuSIFT_D.cu:416,427-429); lanes 0 and 31 are halo columns
+  const bool colOK = (lane >= 1) && (lane <= XT_COLS) && (x >= 1) && (x <= w - 2);
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+
+  Win W;
+  float nxt[NPL];
+  const float *col = dog + cx;
+
+  auto fetch = [&](int r) {   // issue the 7 loads of source row r (clamped)
+    const float *q = col + (size_t)clampi(r, 0, h - 1) * pitch;
+#pragma unroll
+    for (int p = 0; p < NPL; p++) nxt[p] = q[(size_t)p * plane];
+  };
+  auto place = [&](auto SLOT) {   // window slot <- fetched row, with horizontal neighbours
+    constexpr int S = decltype(SLOT)::value;
+#pragma unroll
+    for (int p = 0; p < NPL; p++) {
+      const float c = nxt[p];
+      const float l = __shfl_up_sync(FULL, c, 1), r = __shfl_down_sync(FULL, c, 1);
+      W.v[p][S] = c;
+      W.sx[p][S] = fmaxf(l, r);
+      W.sn[p][S] = fminf(l, r);
+    }
+  };
+  auto test = [&](auto SA, auto SM, auto SB, int y) {   // output row y = middle slot
+    constexpr int A = decltype(SA)::value, M = decltype(SM)::value, B = decltype(SB)::value;
+    float fx[NPL], fn[NPL];   // full 3x3 max / min per plane
+    float hxa[NPL], hxb[NPL], hna[NPL], hnb[NPL];
+#pragma unroll
+    for (int p = 0; p < NPL; p++) {
+      hxa[p] = fmaxf(W.sx[p][A], W.v[p][A]);
+      hxb[p] = fmaxf(W.sx[p][B], W.v[p][B]);
+      hna[p] = fminf(W.sn[p][A], W.v[p][A]);
+      hnb[p] = fminf(W.sn[p][B], W.v[p][B]);
+      fx[p] = max3(hxa[p], hxb[p], fmaxf(W.sx[p][M], W.v[p][M]));
+      fn[p] = min3(hna[p], hnb[p], fminf(W.sn[p][M], W.v[p][M]));
+    }
+    const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + XT_ROWS);
+#pragma unroll
+    for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
+      const int c = sc + 1;
+      const float val = W.v[c][M];
+      const float mx = max3(fx[c - 1], fx[c + 1], max3(hxa[c], hxb[c], W.sx[c][M]));
+      const float mn = min3(fn[c - 1], fn[c + 1], min3(hna[c], hnb[c], W.sn[c][M]));
+      const bool cand = rowOK && ((val > P.thresh && val > mx) || (val < -P.thresh && val < mn));
+      if (cand) {
+        const unsigned int slot = atomicAdd(&s_cnt, 1u);
+        if (slot < XT_CAP) {
+          s_list[slot] = (unsigned int)x | ((unsigned int)y << 14) | ((unsigned int)sc << 28);
+        } else {   // list full: refine in place (rare, keeps every candidate)
+          refine_in_place(dog, plane, pitch, P, x, y, sc, d_sift, d_oct, counter, max_pts);
+        }
+      }
+    }
+  };
+  using I0 = std::integral_constant<int, 0>;
+  using I1 = std::integral_constant<int, 1>;
+  using I2 = std::integral_constant<int, 2>;
+
+  // prime the window: rows y0-1 -> slot 0, y0 -> slot 1
+  fetch(y0 - 1);
+  place(I0{});
+  fetch(y0);
+  place(I1{});
+  fetch(y0 + 1);
+  const int yEnd = min(y0 + XT_ROWS, h - 1);   // exclusive; rows >= h-1 never qualify
+  for (int y = y0; y < yEnd; y += 3) {
+    place(I2{});          // row y+1
+    fetch(y + 2);
+    test(I0{}, I1{}, I2{}, y);
+    place(I0{});          // row y+2
+    fetch(y + 3);
+    test(I1{}, I2{}, I0{}, y + 1);
+    place(I1{});          // row y+3
+    fetch(y + 4);
+    test(I2{}, I0{}, I1{}, y + 2);
+  }
+  __syncthreads();
+
+  // dense refinement of the CTA's candidates + compaction
+  const unsigned int n = min(s_cnt, (unsigned int)XT_CAP);
+  for (unsigned int base = 0; base < n; base += XT_WARPS * 32) {
+    const unsigned int i = base + threadIdx.x;
     bool emit = false;
-    float ox = 0.f, oy = 0.f, oscale = 0.f, osharp = 0.f, oedge = 0.f;
-    if (inside) {
-      const float *p1 = dog + (size_t)(sc + 1) * plane + (size_t)y * pitch + x;
-      const float val = p1[0];
-      const bool isMax = val > P.thresh, isMin = val < -P.thresh;
-      if ((isMax || isMin) && strict_extremum(dog, plane, pitch, sc, x, y, val, isMax)) {
-        // ---- refinement, cuSIFT_D.cu:474-522 ----
-        const float *p0 = p1 - plane, *p2 = p1 + plane;
-        const float two = __fadd_rn(val, val);
-        const float dxx = __fsub_rn(__fsub_rn(two, p1[-1]), p1[1]);
-        const float dyy = __fsub_rn(__fsub_rn(two, p1[-pitch]), p1[pitch]);
-        const float dxy = __fmul_rn(
-            0.25f, __fsub_rn(__fsub_rn(__fadd_rn(p1[pitch + 1], p1[-pitch - 1]), p1[-pitch + 1]), p1[pitch - 1]));
-        const float tra = __fadd_rn(dxx, dyy);
-        const float det = __fmaf_rn(dxx, dyy, -__fmul_rn(dxy, dxy));
-        const float tra2 = __fmul_rn(tra, tra);
-        if (tra2 < __fmul_rn(det, P.edge_limit)) {
-          const float edge = __fdividef(tra2, det);
-          const float dx = __fmul_rn(0.5f, __fsub_rn(p1[1], p1[-1]));
-          const float dy = __fmul_rn(0.5f, __fsub_rn(p1[pitch], p1[-pitch]));
-          const float ds = __fmul_rn(0.5f, __fsub_rn(p0[0], p2[0]));
-          const float dss = __fsub_rn(__fsub_rn(two, p2[0]), p0[0]);
-          const float dxs = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(p2[1], p0[-1]), p0[1]), p2[-1]));
-          const float dys =
-              __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(p2[pitch], p0[-pitch]), p2[-pitch]), p0[pitch]));
-          const float idxx = __fmaf_rn(dyy, dss, -__fmul_rn(dys, dys));
-          const float idxy = __fmaf_rn(dxs, dys, -__fmul_rn(dxy, dss));
-          const float idxs = __fmaf_rn(dxy, dys, -__fmul_rn(dyy, dxs));
-          const float den = __fmaf_rn(dxs, idxs, __fmaf_rn(dxx, idxx, __fmul_rn(dxy, idxy)));
-          const float idet = __fdividef(1.0f, den);
-          const float idyy = __fmaf_rn(dxx, dss, -__fmul_rn(dxs, dxs));
-          const float idys = __fmaf_rn(dxy, dxs, -__fmul_rn(dxx, dys));
-          const float idss = det;   // dxx*dyy - dxy*dxy, same value (CSE'd in the reference too)
-          float pdx = __fmul_rn(idet, __fmaf_rn(ds, idxs, __fmaf_rn(dx, idxx, __fmul_rn(dy, idxy))));
-          float pdy = __fmul_rn(idet, __fmaf_rn(ds, idys, __fmaf_rn(dy, idyy, __fmul_rn(dx, idxy))));
-          float pds = __fmul_rn(idet, __fmaf_rn(idss, ds, __fmaf_rn(dx, idxs, __fmul_rn(dy, idys))));
-          if (pdx < -0.5f || pdx > 0.5f || pdy < -0.5f || pdy > 0.5f || pds < -0.5f || pds > 0.5f) {
-            pdx = __fdividef(dx, dxx);
-            pdy = __fdividef(dy, dyy);
-            pds = __fdividef(ds, dss);
-          }
-          const float dval = __fmaf_rn(ds, pds, __fmaf_rn(dx, pdx, __fmul_rn(dy, pdy)));
-          ox = __fadd_rn((float)x, pdx);
-          oy = __fadd_rn((float)y, pdy);
-          oscale = __fmul_rn(P.scales[sc], exp2f(__fmul_rn(pds, P.factor)));
-          osharp = __fmaf_rn(dval, 0.5f, val);
-          oedge = edge;
-          emit = true;
-        }
-      }
+    Refined r;
+    if (i < n) {
+      const unsigned int e = s_list[i];
+      emit = refine(dog, plane, pitch, P, (int)(e & 0x3fffu), (int)((e >> 14) & 0x3fffu), (int)(e >> 28), r);
     }
-    // warp-ballot compaction: one atomic per warp, slots in lane order
-    const unsigned int m = __ballot_sync(0xffffffffu, emit);
-    if (m) {
-      const int leader = __ffs(m) - 1;
-      unsigned int base = 0;
-      if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (emit) {
-        const unsigned int idx = base + __popc(m & ((1u << lane) - 1u));
-        if (idx < (unsigned int)max_pts) {
-          csb_sift_point *o = d_sift + idx;
-          o->coords2D[0] = ox;
-          o->coords2D[1] = oy;
-          o->scale = oscale;
-          o->sharpness = osharp;
-          o->edgeness = oedge;
-          o->orientation = 0.f;
-          o->score = 0.f;
-          o->ambiguity = 0.f;
-          o->match = 0;
-          o->match_xpos = 0.f;
-          o->match_ypos = 0.f;
-          o->match_error = 0.f;
-          o->subsampling = P.subsampling;
-          o->empty[0] = o->empty[1] = o->empty[2] = 0.f;
-          o->coords3D[0] = o->coords3D[1] = o->coords3D[2] = 0.f;
-          d_oct[idx] = P.octave;
-        }
-      }
-    }
+    emit_warp(emit, r, P, d_sift, d_oct, counter, max_pts, lane);
   }
 }
 
@@ -136,6 +256,6 @@ __global__ void __launch_bounds__(256) k_find_points(const float *__restrict__ d
 
 void launch_find_points(const float *dog, int w, int h, int pitch, const ExtremaParams &ep, csb_sift_point *d_sift,
                         int *d_oct, unsigned int *d_counter, int max_pts, cudaStream_t st) {
-  dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
-  k_find_points<<<grd, blk, 0, st>>>(dog, w, h, pitch, ep, d_sift, d_oct, d_counter, max_pts);
+  dim3 grd((w + XT_TW - 1) / XT_TW, (h + XT_ROWS - 1) / XT_ROWS);
+  k_find_points<<<grd, XT_WARPS * 32, 0, st>>>(dog, w, h, pitch, ep, d_sift, d_oct, d_counter, max_pts);
 }

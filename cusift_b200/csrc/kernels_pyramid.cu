@@ -17,6 +17,8 @@
 // warp b filters row b horizontally, 4 adjacent outputs per lane from three
 // 128-bit shared loads per level, and stores the 7 DoG rows as 128-bit words.
 // Algorithmic HBM traffic: 4 B read + 28 B (+1 B next octave) written per pixel.
+#include <cstdlib>
+
 #include "csb_internal.h"
 
 namespace {
@@ -173,6 +175,198 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Packed-fp32 version (the one the pipeline uses).  Blackwell issues two fp32
+// multiply-adds per instruction with FFMA2/FADD2/FMUL2 (fma.rn.f32x2): each half is an
+// ordinary IEEE single-precision operation, so results stay bit-identical while the
+// number of floating-point issue slots halves.  A CTA therefore processes TWO adjacent
+// 120-column strips in lock-step: every value is a float2 {strip A, strip B}.
+//
+// Shared-memory layout of the vertically blurred rows: positions are grouped in quads;
+// a quad of 4 float2 (32 B) is followed by 16 B of padding, which makes both the
+// 128-bit reads of the horizontal pass (lane stride one quad: 3 x 16 B, odd) and the
+// 64-bit writes of the vertical pass (lanes permuted so that a half-warp covers quads
+// Q, Q+2, Q+4, Q+6) bank-conflict free.
+constexpr int V2_QUAD = 6;                      // float2 slots per quad (4 data + 2 pad)
+constexpr int V2_ROW = (NT / 4) * V2_QUAD;      // float2 slots per (batch row, level)
+constexpr int ROWS2 = 20;                       // output rows per CTA
+constexpr size_t K1V2_SMEM = sizeof(float2) * (BATCH * NLEV * V2_ROW + BATCH * NT);
+
+struct DogWeights2 {
+  float2 k[NLEV][5];   // each tap duplicated {k, k}
+};
+
+__device__ __forceinline__ float2 tap9x2(const float2 (&k)[5], float2 c, float2 s1, float2 s2, float2 s3, float2 s4) {
+  float2 t = __fmul2_rn(k[3], s1);
+  t = __ffma2_rn(c, k[4], t);
+  t = __ffma2_rn(k[2], s2, t);
+  t = __ffma2_rn(k[1], s3, t);
+  t = __ffma2_rn(k[0], s4, t);
+  return t;
+}
+__device__ __forceinline__ float2 down_h2(float2 c0, float2 c1, float2 c2, float2 c3, float2 c4, float2 k0, float2 k1,
+                                          float2 k2) {
+  float2 t = __fmul2_rn(__fadd2_rn(c1, c3), k1);
+  t = __ffma2_rn(__fadd2_rn(c0, c4), k0, t);
+  t = __ffma2_rn(c2, k2, t);
+  return t;
+}
+__device__ __forceinline__ float2 down_v2(float2 rm1, float2 r0, float2 r1, float2 r2, float2 r3, float2 k0, float2 k1,
+                                          float2 k2) {
+  float2 t = __fmul2_rn(__fadd2_rn(r2, r3), k0);
+  t = __ffma2_rn(r0, k2, t);
+  t = __ffma2_rn(__fadd2_rn(rm1, r1), k1, t);
+  return t;
+}
+
+template <bool kDown>
+__global__ void __launch_bounds__(NT) k_blur_dog2(const float *__restrict__ src, int w, int h, int pitch,
+                                                  float *__restrict__ dog, const __grid_constant__ DogWeights2 W,
+                                                  float *__restrict__ next, int npitch, DownK dk) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *V = reinterpret_cast<float2 *>(smem_raw);          // [BATCH][NLEV][V2_ROW]
+  float2 *Raw = V + BATCH * NLEV * V2_ROW;                    // [BATCH][NT], plain position order
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  // vertical phase: lane -> strip position (permuted inside the warp's 32 positions, see above)
+  const int pos = 32 * warp + 4 * (((lane >> 2) & 3) * 2 + (lane >> 4)) + (lane & 3);
+  const int vslot = (pos >> 2) * V2_QUAD + (pos & 3);         // float2 slot of this position in a V row
+  const int xA = blockIdx.x * (2 * TW), xB = xA + TW;         // first output column of strip A / B
+  const int y0 = blockIdx.y * ROWS2;
+  const int cA = clampi(xA + pos - 4, 0, w - 1), cB = clampi(xB + pos - 4, 0, w - 1);
+  const size_t plane = (size_t)pitch * h;
+
+  float2 win[8 + BATCH];
+#pragma unroll
+  for (int i = 0; i < 8 + BATCH; i++) win[i] = make_float2(0.f, 0.f);
+  float2 hw[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) hw[i] = make_float2(0.f, 0.f);
+  const float2 dk0 = make_float2(dk.k0, dk.k0), dk1 = make_float2(dk.k1, dk.k1), dk2 = make_float2(dk.k2, dk.k2);
+
+  float2 pre[BATCH];
+#pragma unroll
+  for (int b = 0; b < BATCH; b++) {
+    const float *r = src + (size_t)clampi(y0 - 4 + b, 0, h - 1) * pitch;
+    pre[b] = make_float2(r[cA], r[cB]);
+  }
+
+  constexpr int NB = (ROWS2 + 8) / BATCH;
+  for (int nb = 0; nb < NB; nb++) {
+    const int r0 = y0 - 4 + nb * BATCH;      // first source row of this batch
+    // window holds source rows r0-8 .. r0+3 after this: shift by BATCH, append the batch
+#pragma unroll
+    for (int i = 0; i < 8; i++) win[i] = win[i + BATCH];
+#pragma unroll
+    for (int b = 0; b < BATCH; b++) win[8 + b] = pre[b];
+    if (nb + 1 < NB) {
+#pragma unroll
+      for (int b = 0; b < BATCH; b++) {
+        const float *r = src + (size_t)clampi(r0 + BATCH + b, 0, h - 1) * pitch;
+        pre[b] = make_float2(r[cA], r[cB]);
+      }
+    }
+    const bool hasOut = nb >= 2;             // block-uniform: window full
+    if constexpr (kDown) {
+#pragma unroll
+      for (int b = 0; b < BATCH; b++) Raw[b * NT + pos] = win[8 + b];
+    }
+    if (hasOut) {
+#pragma unroll
+      for (int b = 0; b < BATCH; b++) {
+        // output row r0+b-4: window rows b .. b+8, centre b+4
+        const float2 c = win[b + 4];
+        const float2 s1 = __fadd2_rn(win[b + 3], win[b + 5]);
+        const float2 s2 = __fadd2_rn(win[b + 2], win[b + 6]);
+        const float2 s3 = __fadd2_rn(win[b + 1], win[b + 7]);
+        const float2 s4 = __fadd2_rn(win[b], win[b + 8]);
+#pragma unroll
+        for (int s = 0; s < NLEV; s++) V[(b * NLEV + s) * V2_ROW + vslot] = tap9x2(W.k[s], c, s1, s2, s3, s4);
+      }
+    }
+    __syncthreads();
+
+    if (hasOut) {
+      // warp `warp` filters batch row `warp` horizontally; lane q -> outputs 4q..4q+3 of both strips
+      const int y = r0 - 4 + warp;
+      if (lane < TW / 4 && y < h) {
+        const int xoA = xA + 4 * lane, xoB = xB + 4 * lane;
+        const float2 *vrow = V + (size_t)(warp * NLEV) * V2_ROW + lane * V2_QUAD;
+        float2 prev[4];
+#pragma unroll
+        for (int s = 0; s < NLEV; s++) {
+          const float4 *q4 = reinterpret_cast<const float4 *>(vrow + s * V2_ROW);
+          float2 v[12];
+#pragma unroll
+          for (int qd = 0; qd < 3; qd++) {
+            const float4 lo = q4[qd * 3 + 0], hi = q4[qd * 3 + 1];   // quad stride: 3 x 16 B
+            v[4 * qd + 0] = make_float2(lo.x, lo.y);
+            v[4 * qd + 1] = make_float2(lo.z, lo.w);
+            v[4 * qd + 2] = make_float2(hi.x, hi.y);
+            v[4 * qd + 3] = make_float2(hi.z, hi.w);
+          }
+          float2 L[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            L[j] = tap9x2(W.k[s], v[j + 4], __fadd2_rn(v[j + 3], v[j + 5]), __fadd2_rn(v[j + 2], v[j + 6]),
+                          __fadd2_rn(v[j + 1], v[j + 7]), __fadd2_rn(v[j], v[j + 8]));
+          if (s > 0) {
+            const float2 m1 = make_float2(-1.0f, -1.0f);
+            float2 d[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) d[j] = __ffma2_rn(L[j], m1, prev[j]);   // prev - L, exactly rounded
+            float *oA = dog + (size_t)(s - 1) * plane + (size_t)y * pitch + xoA;
+            float *oB = dog + (size_t)(s - 1) * plane + (size_t)y * pitch + xoB;
+            if (xoA + 3 < w) {
+              *reinterpret_cast<float4 *>(oA) = make_float4(d[0].x, d[1].x, d[2].x, d[3].x);
+            } else if (xoA < w) {
+              oA[0] = d[0].x;
+              if (xoA + 1 < w) oA[1] = d[1].x;
+              if (xoA + 2 < w) oA[2] = d[2].x;
+            }
+            if (xoB + 3 < w) {
+              *reinterpret_cast<float4 *>(oB) = make_float4(d[0].y, d[1].y, d[2].y, d[3].y);
+            } else if (xoB < w) {
+              oB[0] = d[0].y;
+              if (xoB + 1 < w) oB[1] = d[1].y;
+              if (xoB + 2 < w) oB[2] = d[2].y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++) prev[j] = L[j];
+        }
+      }
+    }
+
+    if constexpr (kDown) {
+      // threads 0..59: next-octave columns xA/2+t and xB/2+t, fed by source rows r0..r0+3
+      if (t < TW / 2) {
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+          const int r = r0 + b;
+          const float2 *rw = Raw + b * NT + 2 * t;
+          const float2 hv = down_h2(rw[2], rw[3], rw[4], rw[5], rw[6], dk0, dk1, dk2);
+#pragma unroll
+          for (int i = 0; i < 4; i++) hw[i] = hw[i + 1];
+          hw[4] = hv;
+          const int twoj = r - 3;   // window = rows r-4..r = 2j-1..2j+3
+          if (twoj >= y0 && twoj < y0 + ROWS2 && !(twoj & 1)) {
+            const int j = twoj >> 1;
+            if (j < (h >> 1)) {
+              const float2 o = down_v2(hw[0], hw[1], hw[2], hw[3], hw[4], dk0, dk1, dk2);
+              const int iA = (xA >> 1) + t, iB = (xB >> 1) + t;
+              if (iA < (w >> 1)) next[(size_t)j * npitch + iA] = o.x;
+              if (iB < (w >> 1)) next[(size_t)j * npitch + iB] = o.y;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Stand-alone ScaleDown (cuSIFT.h:76): one thread per destination pixel.
 __global__ void k_scale_down(const float *__restrict__ src, int w, int h, int spitch, float *__restrict__ dst,
                              int dpitch, DownK dk) {
@@ -199,15 +393,49 @@ void launch_scale_down(const float *src, int w, int h, int spitch, float *dst, i
   k_scale_down<<<grd, blk, 0, st>>>(src, w, h, spitch, dst, dpitch, dk);
 }
 
+// CSB_K1_SCALAR=1 selects the scalar-fp32 kernels above (debugging aid; same results).
+static bool csb_use_scalar_pyramid() {
+  static const bool v = [] {
+    const char *e = getenv("CSB_K1_SCALAR");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
+namespace {
+DogWeights2 dup_weights(const DogWeights &wts) {
+  DogWeights2 w2;
+  for (int s = 0; s < NLEV; s++)
+    for (int j = 0; j < 5; j++) w2.k[s][j] = make_float2(wts.k[s][j], wts.k[s][j]);
+  return w2;
+}
+template <bool kDown>
+void set_smem_attr_once() {   // > 48 KB of dynamic shared memory needs the opt-in (per device; cheap to repeat)
+  cudaFuncSetAttribute(k_blur_dog2<kDown>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1V2_SMEM);
+}
+}  // namespace
+
 void launch_blur_dog(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, cudaStream_t st) {
-  dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
   DownK dk{0.f, 0.f, 0.f};
-  k_blur_dog<false><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, nullptr, 0, dk);
+  if (csb_use_scalar_pyramid()) {
+    dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
+    k_blur_dog<false><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, nullptr, 0, dk);
+    return;
+  }
+  set_smem_attr_once<false>();
+  dim3 grd((w + 2 * TW - 1) / (2 * TW), (h + ROWS2 - 1) / ROWS2);
+  k_blur_dog2<false><<<grd, NT, K1V2_SMEM, st>>>(base, w, h, pitch, dog, dup_weights(wts), nullptr, 0, dk);
 }
 
 void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next,
                           int npitch, const float k[3], cudaStream_t st) {
-  dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
   DownK dk{k[0], k[1], k[2]};
-  k_blur_dog<true><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, next, npitch, dk);
+  if (csb_use_scalar_pyramid()) {
+    dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
+    k_blur_dog<true><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, next, npitch, dk);
+    return;
+  }
+  set_smem_attr_once<true>();
+  dim3 grd((w + 2 * TW - 1) / (2 * TW), (h + ROWS2 - 1) / ROWS2);
+  k_blur_dog2<true><<<grd, NT, K1V2_SMEM, st>>>(base, w, h, pitch, dog, dup_weights(wts), next, npitch, dk);
 }

@@ -369,4 +369,4 @@ def _():
 import shutil  # noqa: E402
 shutil.rmtree(WORK, ignore_errors=True)   # keep gpurun_out small (64 MiB cap)
 print("DIAG DONE")
-(OUT / "diag.json").write_text(json.dumps(REPORT, indent=1, default=str))
+(OUT / ("diag_quick.json" if QUICK else "diag.json")).write_text(json.dumps(REPORT, indent=1, default=str))
