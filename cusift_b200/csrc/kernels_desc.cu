@@ -50,16 +50,18 @@ __device__ __forceinline__ float sumsq_tree(const float (&b)[4], int lane) {
   return __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
 }
 
-constexpr int DCOPY = 128 + 16;   // one descriptor copy: 128 bins + a dummy slot per lane of the half
+constexpr int DCOPY = 128 + 16 * 8;   // one descriptor copy: 128 bins + an 8-bin dummy cell per lane of the half
 
 // Plain read-modify-write vote: the caller guarantees that no two lanes of the warp
 // target the same address in the same call (see the lane->cell mapping below).
-__device__ __forceinline__ void vote(float *copy, int idx, float v, int dummy) {
-  const bool ok = (idx >= 0) && (idx < 128);   // votes past buffer[128] land outside the reference's arrays: dropped
-  float *q = copy + (ok ? idx : dummy);
-  *q = __fadd_rn(*q, ok ? v : 0.0f);
+__device__ __forceinline__ void vote(float *q, float v) {
+  *q = __fadd_rn(*q, v);
   __syncwarp();
 }
+
+struct Grad {
+  float dx, dy;
+};
 
 __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constant__ OctaveTexSet T,
                                                             csb_sift_point *__restrict__ d_sift,
@@ -78,7 +80,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
   // descriptor sampling pattern: lane = half*16 + cell_y*4 + cell_x
   const int half = lane >> 4, cellx = lane & 3, celly = (lane >> 2) & 3;
   float *copy = buf + half * DCOPY;
-  const int dummy = 128 + (lane & 15);
 
   for (int k = blockIdx.x * WARPS + warp; k < n; k += gridDim.x * WARPS) {
     csb_sift_point *pt = d_sift + k;
@@ -153,17 +154,30 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
     const float sina = sinf(theta), cosa = cosf(theta);
     const float sc = __fmul_rn(pscale, 0.75f);
     const float ssina = __fmul_rn(sina, sc), scosa = __fmul_rn(cosa, sc);
-#pragma unroll 1
-    for (int it = 0; it < 8; it++) {
-      const int j = it * 2 + half;                 // sample within the lane's 4x4 cell
+    // sample `it` of this lane's cell; the four texture fetches of sample it+1 are issued
+    // before sample it is voted, so their latency overlaps the atan2f / vote work
+    auto fetch = [&](int it) -> Grad {
+      const int j = it * 2 + half;
       const int tx = 4 * cellx + (j & 3), y = 4 * celly + (j >> 2);
       const float ftx = __fsub_rn((float)tx, 7.5f), fy = __fsub_rn((float)y, 7.5f);
       const float xpos = __fmaf_rn(-ssina, fy, __fadd_rn(__fmul_rn(ftx, scosa), px));
       const float ypos = __fmaf_rn(scosa, fy, __fadd_rn(__fmul_rn(ftx, ssina), py));
-      const float dx = __fsub_rn(tex2D<float>(tex, __fadd_rn(xpos, cosa), __fadd_rn(ypos, sina)),
-                                 tex2D<float>(tex, __fsub_rn(xpos, cosa), __fsub_rn(ypos, sina)));
-      const float dy = __fsub_rn(tex2D<float>(tex, __fsub_rn(xpos, sina), __fadd_rn(ypos, cosa)),
-                                 tex2D<float>(tex, __fadd_rn(xpos, sina), __fsub_rn(ypos, cosa)));
+      Grad g;
+      g.dx = __fsub_rn(tex2D<float>(tex, __fadd_rn(xpos, cosa), __fadd_rn(ypos, sina)),
+                       tex2D<float>(tex, __fsub_rn(xpos, cosa), __fsub_rn(ypos, sina)));
+      g.dy = __fsub_rn(tex2D<float>(tex, __fsub_rn(xpos, sina), __fadd_rn(ypos, cosa)),
+                       tex2D<float>(tex, __fadd_rn(xpos, sina), __fsub_rn(ypos, cosa)));
+      return g;
+    };
+    float *dummy = copy + 128 + 8 * (lane & 15);   // private 8-bin scratch cell
+    Grad gnext = fetch(0);
+#pragma unroll 1
+    for (int it = 0; it < 8; it++) {
+      const Grad g = gnext;
+      if (it + 1 < 8) gnext = fetch(it + 1);
+      const int j = it * 2 + half;                 // sample within the lane's 4x4 cell
+      const int tx = 4 * cellx + (j & 3), y = 4 * celly + (j >> 2);
+      const float dx = g.dx, dy = g.dy;
       const float grad = __fmul_rn(__fmul_rn(gauss[y], gauss[tx]), sqrtf(__fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
       float angf = __fmaf_rn(atan2f(dy, dx), 4.0f / 3.1415f, 4.0f);
       const int hori = (tx + 2) / 4 - 1;
@@ -177,29 +191,34 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
       angf = __fsub_rn(angf, (float)angi);
       const float iangf = __fsub_rn(1.0f, angf);
       const int hbase = 8 * (4 * veri + hori);
-      const int p1 = angi + hbase, p2 = angp + hbase;
-      // the four spatial shares (guards of cuSIFT_D.cu:230-255; `tx<=14` sic)
+      // the four spatial shares (guards of cuSIFT_D.cu:230-255; `tx<=14` sic).  A share whose cell
+      // lies outside buffer[128] is dropped (in the reference it lands beyond its last shared array);
+      // invalid shares are simply accumulated into the lane's scratch cell.
       const bool gl = tx >= 2, gr = tx <= 14, gu = y >= 2, gd = y <= 13;
       const float gUL = __fmul_rn(iverf, __fmul_rn(ihorf, grad)), gDL = __fmul_rn(verf, __fmul_rn(ihorf, grad));
       const float gUR = __fmul_rn(iverf, __fmul_rn(horf, grad)), gDR = __fmul_rn(verf, __fmul_rn(horf, grad));
-      // angi == 8 (atan2f >= 3.1415) makes p1 point at bin 0 of the NEXT cell, which another lane may be
-      // voting into at the same site: those (rare) votes are deferred to an atomic pass below.
+      const bool vUL = gl && gu, vDL = gl && gd && (hbase + 32 < 128);
+      const bool vUR = gr && gu && (hbase + 8 < 128), vDR = gr && gd && (hbase + 40 < 128);
+      float *cUL = vUL ? copy + hbase : dummy, *cDL = vDL ? copy + hbase + 32 : dummy;
+      float *cUR = vUR ? copy + hbase + 8 : dummy, *cDR = vDR ? copy + hbase + 40 : dummy;
+      // angi == 8 (atan2f >= 3.1415, e.g. dy == +0, dx < 0) makes p1 point at bin 0 of the NEXT cell,
+      // which another lane may be voting into at the same site: those votes go through an atomic pass.
       const bool spill = angi >= 8;
-      const int q1 = spill ? -1 : p1;
-      vote(copy, (gl && gu) ? q1 : -1, __fmul_rn(iangf, gUL), dummy);
-      vote(copy, (gl && gu) ? p2 : -1, __fmul_rn(angf, gUL), dummy);
-      vote(copy, (gl && gd) ? q1 + 32 : -1, __fmul_rn(iangf, gDL), dummy);
-      vote(copy, (gl && gd) ? p2 + 32 : -1, __fmul_rn(angf, gDL), dummy);
-      vote(copy, (gr && gu) ? q1 + 8 : -1, __fmul_rn(iangf, gUR), dummy);
-      vote(copy, (gr && gu) ? p2 + 8 : -1, __fmul_rn(angf, gUR), dummy);
-      vote(copy, (gr && gd) ? q1 + 40 : -1, __fmul_rn(iangf, gDR), dummy);
-      vote(copy, (gr && gd) ? p2 + 40 : -1, __fmul_rn(angf, gDR), dummy);
+      const int a1 = spill ? 0 : angi;
+      vote((spill ? dummy : cUL) + a1, __fmul_rn(iangf, gUL));
+      vote(cUL + angp, __fmul_rn(angf, gUL));
+      vote((spill ? dummy : cDL) + a1, __fmul_rn(iangf, gDL));
+      vote(cDL + angp, __fmul_rn(angf, gDL));
+      vote((spill ? dummy : cUR) + a1, __fmul_rn(iangf, gUR));
+      vote(cUR + angp, __fmul_rn(angf, gUR));
+      vote((spill ? dummy : cDR) + a1, __fmul_rn(iangf, gDR));
+      vote(cDR + angp, __fmul_rn(angf, gDR));
       if (__any_sync(FULL, spill)) {
         if (spill) {
-          if (gl && gu && p1 < 128) atomicAdd(copy + p1, __fmul_rn(iangf, gUL));
-          if (gl && gd && p1 + 32 < 128) atomicAdd(copy + p1 + 32, __fmul_rn(iangf, gDL));
-          if (gr && gu && p1 + 8 < 128) atomicAdd(copy + p1 + 8, __fmul_rn(iangf, gUR));
-          if (gr && gd && p1 + 40 < 128) atomicAdd(copy + p1 + 40, __fmul_rn(iangf, gDR));
+          if (vUL && hbase + 8 < 128) atomicAdd(copy + hbase + 8, __fmul_rn(iangf, gUL));
+          if (vDL && hbase + 40 < 128) atomicAdd(copy + hbase + 40, __fmul_rn(iangf, gDL));
+          if (vUR && hbase + 16 < 128) atomicAdd(copy + hbase + 16, __fmul_rn(iangf, gUR));
+          if (vDR && hbase + 48 < 128) atomicAdd(copy + hbase + 48, __fmul_rn(iangf, gDR));
         }
         __syncwarp();
       }

@@ -144,7 +144,7 @@ struct Win {
   float sn[NPL][3];   // min(left, right)
 };
 
-__global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
+__global__ void __launch_bounds__(XT_WARPS * 32, 3) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
                                                                const __grid_constant__ ExtremaParams P,
                                                                csb_sift_point *__restrict__ d_sift,
                                                                int *__restrict__ d_oct,
@@ -164,19 +164,20 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
   __syncthreads();
 
   Win W;
-  float nxt[NPL];
+  float ring[3][NPL];          // rows in flight: three source rows are prefetched ahead of the window
   const float *col = dog + cx;
 
-  auto fetch = [&](int r) {   // issue the 7 loads of source row r (clamped)
+  auto fetch = [&](int r, auto RS) {   // issue the 7 loads of source row r (clamped) into ring slot RS
+    constexpr int R = decltype(RS)::value;
     const float *q = col + (size_t)clampi(r, 0, h - 1) * pitch;
 #pragma unroll
-    for (int p = 0; p < NPL; p++) nxt[p] = q[(size_t)p * plane];
+    for (int p = 0; p < NPL; p++) ring[R][p] = q[(size_t)p * plane];
   };
-  auto place = [&](auto SLOT) {   // window slot <- fetched row, with horizontal neighbours
-    constexpr int S = decltype(SLOT)::value;
+  auto place = [&](auto SLOT, auto RS) {   // window slot <- ring slot, with horizontal neighbours
+    constexpr int S = decltype(SLOT)::value, R = decltype(RS)::value;
 #pragma unroll
     for (int p = 0; p < NPL; p++) {
-      const float c = nxt[p];
+      const float c = ring[R][p];
       const float l = __shfl_up_sync(FULL, c, 1), r = __shfl_down_sync(FULL, c, 1);
       W.v[p][S] = c;
       W.sx[p][S] = fmaxf(l, r);
@@ -218,22 +219,24 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
   using I1 = std::integral_constant<int, 1>;
   using I2 = std::integral_constant<int, 2>;
 
-  // prime the window: rows y0-1 -> slot 0, y0 -> slot 1
-  fetch(y0 - 1);
-  place(I0{});
-  fetch(y0);
-  place(I1{});
-  fetch(y0 + 1);
+  // prime the window (rows y0-1, y0) and the prefetch ring (rows y0+1 .. y0+3)
+  fetch(y0 - 1, I0{});
+  fetch(y0, I1{});
+  place(I0{}, I0{});
+  place(I1{}, I1{});
+  fetch(y0 + 1, I0{});
+  fetch(y0 + 2, I1{});
+  fetch(y0 + 3, I2{});
   const int yEnd = min(y0 + XT_ROWS, h - 1);   // exclusive; rows >= h-1 never qualify
   for (int y = y0; y < yEnd; y += 3) {
-    place(I2{});          // row y+1
-    fetch(y + 2);
+    place(I2{}, I0{});          // row y+1
+    fetch(y + 4, I0{});
     test(I0{}, I1{}, I2{}, y);
-    place(I0{});          // row y+2
-    fetch(y + 3);
+    place(I0{}, I1{});          // row y+2
+    fetch(y + 5, I1{});
     test(I1{}, I2{}, I0{}, y + 1);
-    place(I1{});          // row y+3
-    fetch(y + 4);
+    place(I1{}, I2{});          // row y+3
+    fetch(y + 6, I2{});
     test(I2{}, I0{}, I1{}, y + 2);
   }
   __syncthreads();

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
 // Q, Q+2, Q+4, Q+6) bank-conflict free.
 constexpr int V2_QUAD = 6;                      // float2 slots per quad (4 data + 2 pad)
 constexpr int V2_ROW = (NT / 4) * V2_QUAD;      // float2 slots per (batch row, level)
-constexpr int ROWS2 = 20;                       // output rows per CTA
+constexpr int ROWS2 = 16;                       // output rows per CTA
 constexpr size_t K1V2_SMEM = sizeof(float2) * (BATCH * NLEV * V2_ROW + BATCH * NT);
 
 struct DogWeights2 {
@@ -220,7 +220,7 @@ __device__ __forceinline__ float2 down_v2(float2 rm1, float2 r0, float2 r1, floa
 }
 
 template <bool kDown>
-__global__ void __launch_bounds__(NT) k_blur_dog2(const float *__restrict__ src, int w, int h, int pitch,
+__global__ void __launch_bounds__(NT, 4) k_blur_dog2(const float *__restrict__ src, int w, int h, int pitch,
                                                   float *__restrict__ dog, const __grid_constant__ DogWeights2 W,
                                                   float *__restrict__ next, int npitch, DownK dk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -245,11 +245,17 @@ __global__ void __launch_bounds__(NT) k_blur_dog2(const float *__restrict__ src,
   for (int i = 0; i < 5; i++) hw[i] = make_float2(0.f, 0.f);
   const float2 dk0 = make_float2(dk.k0, dk.k0), dk1 = make_float2(dk.k1, dk.k1), dk2 = make_float2(dk.k2, dk.k2);
 
-  float2 pre[BATCH];
+  // two batches of source rows are kept in flight ahead of the window (load latency >> batch time)
+  float2 pre[BATCH], pre2[BATCH];
 #pragma unroll
   for (int b = 0; b < BATCH; b++) {
     const float *r = src + (size_t)clampi(y0 - 4 + b, 0, h - 1) * pitch;
     pre[b] = make_float2(r[cA], r[cB]);
+  }
+#pragma unroll
+  for (int b = 0; b < BATCH; b++) {
+    const float *r = src + (size_t)clampi(y0 + b, 0, h - 1) * pitch;
+    pre2[b] = make_float2(r[cA], r[cB]);
   }
 
   constexpr int NB = (ROWS2 + 8) / BATCH;
@@ -259,12 +265,15 @@ __global__ void __launch_bounds__(NT) k_blur_dog2(const float *__restrict__ src,
 #pragma unroll
     for (int i = 0; i < 8; i++) win[i] = win[i + BATCH];
 #pragma unroll
-    for (int b = 0; b < BATCH; b++) win[8 + b] = pre[b];
-    if (nb + 1 < NB) {
+    for (int b = 0; b < BATCH; b++) {
+      win[8 + b] = pre[b];
+      pre[b] = pre2[b];
+    }
+    if (nb + 2 < NB) {
 #pragma unroll
       for (int b = 0; b < BATCH; b++) {
-        const float *r = src + (size_t)clampi(r0 + BATCH + b, 0, h - 1) * pitch;
-        pre[b] = make_float2(r[cA], r[cB]);
+        const float *r = src + (size_t)clampi(r0 + 2 * BATCH + b, 0, h - 1) * pitch;
+        pre2[b] = make_float2(r[cA], r[cB]);
       }
     }
     const bool hasOut = nb >= 2;             // block-uniform: window full
@@ -292,19 +301,26 @@ __global__ void __launch_bounds__(NT) k_blur_dog2(const float *__restrict__ src,
       const int y = r0 - 4 + warp;
       if (lane < TW / 4 && y < h) {
         const int xoA = xA + 4 * lane, xoB = xB + 4 * lane;
-        const float2 *vrow = V + (size_t)(warp * NLEV) * V2_ROW + lane * V2_QUAD;
+        const float4 *q4 = reinterpret_cast<const float4 *>(V + (size_t)(warp * NLEV) * V2_ROW + lane * V2_QUAD);
+        constexpr int LSTRIDE = V2_ROW / 2;                 // float4 units between levels
+        float *oA = dog + (size_t)y * pitch + xoA;          // plane 0; advanced by `plane` per level
+        const bool fullA = xoA + 3 < w, fullB = xoB + 3 < w;
+        const bool fast = __all_sync(__activemask(), fullA && fullB);
+        float4 ld[6];                                       // software-pipelined shared loads (next level)
+#pragma unroll
+        for (int i = 0; i < 6; i++) ld[i] = q4[(i >> 1) * 3 + (i & 1)];
         float2 prev[4];
 #pragma unroll
         for (int s = 0; s < NLEV; s++) {
-          const float4 *q4 = reinterpret_cast<const float4 *>(vrow + s * V2_ROW);
           float2 v[12];
 #pragma unroll
-          for (int qd = 0; qd < 3; qd++) {
-            const float4 lo = q4[qd * 3 + 0], hi = q4[qd * 3 + 1];   // quad stride: 3 x 16 B
-            v[4 * qd + 0] = make_float2(lo.x, lo.y);
-            v[4 * qd + 1] = make_float2(lo.z, lo.w);
-            v[4 * qd + 2] = make_float2(hi.x, hi.y);
-            v[4 * qd + 3] = make_float2(hi.z, hi.w);
+          for (int i = 0; i < 6; i++) {
+            v[2 * i + 0] = make_float2(ld[i].x, ld[i].y);
+            v[2 * i + 1] = make_float2(ld[i].z, ld[i].w);
+          }
+          if (s + 1 < NLEV) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) ld[i] = q4[(s + 1) * LSTRIDE + (i >> 1) * 3 + (i & 1)];
           }
           float2 L[4];
 #pragma unroll
@@ -316,22 +332,27 @@ __global__ void __launch_bounds__(NT) k_blur_dog2(const float *__restrict__ src,
             float2 d[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) d[j] = __ffma2_rn(L[j], m1, prev[j]);   // prev - L, exactly rounded
-            float *oA = dog + (size_t)(s - 1) * plane + (size_t)y * pitch + xoA;
-            float *oB = dog + (size_t)(s - 1) * plane + (size_t)y * pitch + xoB;
-            if (xoA + 3 < w) {
+            float *oB = oA + TW;
+            if (fast) {
               *reinterpret_cast<float4 *>(oA) = make_float4(d[0].x, d[1].x, d[2].x, d[3].x);
-            } else if (xoA < w) {
-              oA[0] = d[0].x;
-              if (xoA + 1 < w) oA[1] = d[1].x;
-              if (xoA + 2 < w) oA[2] = d[2].x;
-            }
-            if (xoB + 3 < w) {
               *reinterpret_cast<float4 *>(oB) = make_float4(d[0].y, d[1].y, d[2].y, d[3].y);
-            } else if (xoB < w) {
-              oB[0] = d[0].y;
-              if (xoB + 1 < w) oB[1] = d[1].y;
-              if (xoB + 2 < w) oB[2] = d[2].y;
+            } else {
+              if (fullA) {
+                *reinterpret_cast<float4 *>(oA) = make_float4(d[0].x, d[1].x, d[2].x, d[3].x);
+              } else if (xoA < w) {
+                oA[0] = d[0].x;
+                if (xoA + 1 < w) oA[1] = d[1].x;
+                if (xoA + 2 < w) oA[2] = d[2].x;
+              }
+              if (fullB) {
+                *reinterpret_cast<float4 *>(oB) = make_float4(d[0].y, d[1].y, d[2].y, d[3].y);
+              } else if (xoB < w) {
+                oB[0] = d[0].y;
+                if (xoB + 1 < w) oB[1] = d[1].y;
+                if (xoB + 2 < w) oB[2] = d[2].y;
+              }
             }
+            oA += plane;
           }
 #pragma unroll
           for (int j = 0; j < 4; j++) prev[j] = L[j];
