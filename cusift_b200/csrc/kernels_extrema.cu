@@ -8,10 +8,12 @@
 //     per plane a 3-row window lives in registers, horizontal neighbours come
 //     from warp shuffles, and the 26-neighbour test is a separable min/max network
 //     (3-input FMNMX): per plane  hx = max3(left, v, right),
-//     F = max3(hx[y-1], hx[y], hx[y+1]) (full 3x3),  E = max3(hx[y-1], hx[y+1],
-//     max(left,right)) (3x3 without the centre);  v is a strict maximum iff
-//     v > max3(F[plane-1], F[plane+1], E[plane]).  No shared memory, no barriers
-//     in the scan.
+//     F = max3(hx[y-1], hx[y], hx[y+1]) (full 3x3); a pixel is a (non-strict)
+//     maximum of its 3x3x3 block iff v == max3(F[plane-1], F[plane], F[plane+1]).
+//     The scan flags those (plus |v| > thresh); the reference's STRICT comparison
+//     against each of the 26 neighbours (cuSIFT_D.cu:450-470) is then applied to the
+//     few flagged pixels in the dense second phase, so exact ties are rejected
+//     exactly as in the reference.  No shared memory, no barriers in the scan.
 //   * candidates go to a small per-CTA list (never wraps: overflow is refined in
 //     place; the reference's 32-entry list silently wraps, cuSIFT_D.cu:455,465);
 //     after the scan the CTA refines them densely and compacts survivors with
@@ -28,7 +30,7 @@ namespace {
 constexpr int XT_COLS = 30;          // output columns per warp
 constexpr int XT_WARPS = 4;
 constexpr int XT_TW = XT_COLS * XT_WARPS;   // 120 output columns per CTA
-constexpr int XT_ROWS = 36;          // output rows per CTA (multiple of 3)
+constexpr int XT_ROWS = 36;          // output rows per CTA (multiple of 6)
 constexpr int XT_CAP = 512;          // candidate list entries per CTA
 constexpr int NPL = CSB_NUM_DOG;     // 7 planes
 constexpr unsigned FULL = 0xffffffffu;
@@ -138,17 +140,52 @@ __device__ __noinline__ void refine_in_place(const float *__restrict__ dog, size
   }
 }
 
-struct Win {
-  float v[NPL][3];    // DoG value at this thread's column, 3-row window
-  float sx[NPL][3];   // max(left, right)
-  float sn[NPL][3];   // min(left, right)
-};
+// Reference candidate rule (cuSIFT_D.cu:450-470): strictly beyond all 26 neighbours.
+__device__ __forceinline__ bool strict_extremum(const float *__restrict__ dog, size_t plane, int pitch, int sc, int x,
+                                                int y, float thresh) {
+  const float *c = dog + (size_t)(sc + 1) * plane + (size_t)y * pitch + x;
+  const float v = c[0];
+  const bool isMax = v > thresh, isMin = v < -thresh;
+  if (!isMax && !isMin) return false;
+  bool ok = true;
+#pragma unroll
+  for (int p = -1; p <= 1; p++) {
+    const float *q = c + (ptrdiff_t)p * (ptrdiff_t)plane;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+#pragma unroll
+      for (int dx = -1; dx <= 1; dx++) {
+        if (p == 0 && dy == 0 && dx == 0) continue;
+        const float u = q[dy * pitch + dx];
+        ok = ok && (isMax ? (v > u) : (v < u));
+      }
+    }
+  }
+  return ok;
+}
 
-__global__ void __launch_bounds__(XT_WARPS * 32, 3) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
-                                                               const __grid_constant__ ExtremaParams P,
-                                                               csb_sift_point *__restrict__ d_sift,
-                                                               int *__restrict__ d_oct,
-                                                               unsigned int *__restrict__ counter, int max_pts) {
+// Appends the flagged scales of pixel (x, y) to the CTA's candidate list; when the list is full
+// (rare) the candidate is verified and refined on the spot so that nothing is ever dropped.
+__device__ __noinline__ void push_candidates(unsigned int cmask, int x, int y, unsigned int *s_cnt, unsigned int *s_list,
+                                             const float *__restrict__ dog, size_t plane, int pitch,
+                                             const ExtremaParams &P, csb_sift_point *__restrict__ d_sift,
+                                             int *__restrict__ d_oct, unsigned int *__restrict__ counter, int max_pts) {
+  for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
+    if (!((cmask >> sc) & 1u)) continue;
+    const unsigned int slot = atomicAdd(s_cnt, 1u);
+    if (slot < XT_CAP) {
+      s_list[slot] = (unsigned int)x | ((unsigned int)y << 14) | ((unsigned int)sc << 28);
+    } else if (strict_extremum(dog, plane, pitch, sc, x, y, P.thresh)) {
+      refine_in_place(dog, plane, pitch, P, x, y, sc, d_sift, d_oct, counter, max_pts);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
+                                                                  const __grid_constant__ ExtremaParams P,
+                                                                  csb_sift_point *__restrict__ d_sift,
+                                                                  int *__restrict__ d_oct,
+                                                                  unsigned int *__restrict__ counter, int max_pts) {
   __shared__ unsigned int s_cnt;
   __shared__ unsigned int s_list[XT_CAP];   // x | y << 14 | scale << 28
 
@@ -163,85 +200,73 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 3) k_find_points(const float *_
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
 
-  Win W;
-  float ring[3][NPL];          // rows in flight: three source rows are prefetched ahead of the window
+  // per plane: horizontal max3 / min3 of three consecutive rows (slots rotate), centre values of the
+  // middle row for the 5 centre planes, and two source rows in flight
+  float hx[NPL][3], hn[NPL][3], vc[CSB_NUM_SCALES][3];
+  float ring[2][NPL];
   const float *col = dog + cx;
 
-  auto fetch = [&](int r, auto RS) {   // issue the 7 loads of source row r (clamped) into ring slot RS
+  auto fetch = [&](int r, auto RS) {
     constexpr int R = decltype(RS)::value;
     const float *q = col + (size_t)clampi(r, 0, h - 1) * pitch;
 #pragma unroll
     for (int p = 0; p < NPL; p++) ring[R][p] = q[(size_t)p * plane];
   };
-  auto place = [&](auto SLOT, auto RS) {   // window slot <- ring slot, with horizontal neighbours
+  auto place = [&](auto SLOT, auto RS) {
     constexpr int S = decltype(SLOT)::value, R = decltype(RS)::value;
 #pragma unroll
     for (int p = 0; p < NPL; p++) {
       const float c = ring[R][p];
       const float l = __shfl_up_sync(FULL, c, 1), r = __shfl_down_sync(FULL, c, 1);
-      W.v[p][S] = c;
-      W.sx[p][S] = fmaxf(l, r);
-      W.sn[p][S] = fminf(l, r);
+      hx[p][S] = max3(l, c, r);
+      hn[p][S] = min3(l, c, r);
+      if (p >= 1 && p <= CSB_NUM_SCALES) vc[p - 1][S] = c;
     }
   };
-  auto test = [&](auto SA, auto SM, auto SB, int y) {   // output row y = middle slot
-    constexpr int A = decltype(SA)::value, M = decltype(SM)::value, B = decltype(SB)::value;
-    float fx[NPL], fn[NPL];   // full 3x3 max / min per plane
-    float hxa[NPL], hxb[NPL], hna[NPL], hnb[NPL];
+  auto test = [&](auto SM, int y) {   // output row y = slot SM; the other two slots are rows y-1 / y+1
+    constexpr int M = decltype(SM)::value;
+    float fx[NPL], fn[NPL];
 #pragma unroll
     for (int p = 0; p < NPL; p++) {
-      hxa[p] = fmaxf(W.sx[p][A], W.v[p][A]);
-      hxb[p] = fmaxf(W.sx[p][B], W.v[p][B]);
-      hna[p] = fminf(W.sn[p][A], W.v[p][A]);
-      hnb[p] = fminf(W.sn[p][B], W.v[p][B]);
-      fx[p] = max3(hxa[p], hxb[p], fmaxf(W.sx[p][M], W.v[p][M]));
-      fn[p] = min3(hna[p], hnb[p], fminf(W.sn[p][M], W.v[p][M]));
+      fx[p] = max3(hx[p][0], hx[p][1], hx[p][2]);
+      fn[p] = min3(hn[p][0], hn[p][1], hn[p][2]);
     }
-    const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + XT_ROWS);
+    unsigned int cmask = 0;
 #pragma unroll
     for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
-      const int c = sc + 1;
-      const float val = W.v[c][M];
-      const float mx = max3(fx[c - 1], fx[c + 1], max3(hxa[c], hxb[c], W.sx[c][M]));
-      const float mn = min3(fn[c - 1], fn[c + 1], min3(hna[c], hnb[c], W.sn[c][M]));
-      const bool cand = rowOK && ((val > P.thresh && val > mx) || (val < -P.thresh && val < mn));
-      if (cand) {
-        const unsigned int slot = atomicAdd(&s_cnt, 1u);
-        if (slot < XT_CAP) {
-          s_list[slot] = (unsigned int)x | ((unsigned int)y << 14) | ((unsigned int)sc << 28);
-        } else {   // list full: refine in place (rare, keeps every candidate)
-          refine_in_place(dog, plane, pitch, P, x, y, sc, d_sift, d_oct, counter, max_pts);
-        }
-      }
+      const float val = vc[sc][M];
+      const float mx = max3(fx[sc], fx[sc + 1], fx[sc + 2]);
+      const float mn = min3(fn[sc], fn[sc + 1], fn[sc + 2]);
+      const bool cand = (val == mx && val > P.thresh) || (val == mn && val < -P.thresh);
+      cmask |= cand ? (1u << sc) : 0u;
     }
+    const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + XT_ROWS);
+    if (rowOK && cmask) push_candidates(cmask, x, y, &s_cnt, s_list, dog, plane, pitch, P, d_sift, d_oct, counter, max_pts);
   };
   using I0 = std::integral_constant<int, 0>;
   using I1 = std::integral_constant<int, 1>;
   using I2 = std::integral_constant<int, 2>;
 
-  // prime the window (rows y0-1, y0) and the prefetch ring (rows y0+1 .. y0+3)
+  // prime: rows y0-1 -> slot 0, y0 -> slot 1; rows y0+1, y0+2 in flight
   fetch(y0 - 1, I0{});
   fetch(y0, I1{});
   place(I0{}, I0{});
   place(I1{}, I1{});
   fetch(y0 + 1, I0{});
   fetch(y0 + 2, I1{});
-  fetch(y0 + 3, I2{});
   const int yEnd = min(y0 + XT_ROWS, h - 1);   // exclusive; rows >= h-1 never qualify
-  for (int y = y0; y < yEnd; y += 3) {
-    place(I2{}, I0{});          // row y+1
-    fetch(y + 4, I0{});
-    test(I0{}, I1{}, I2{}, y);
-    place(I0{}, I1{});          // row y+2
-    fetch(y + 5, I1{});
-    test(I1{}, I2{}, I0{}, y + 1);
-    place(I1{}, I2{});          // row y+3
-    fetch(y + 6, I2{});
-    test(I2{}, I0{}, I1{}, y + 2);
+  for (int y = y0; y < yEnd; y += 6) {
+    // six row steps: window slot = (row - (y0-1)) mod 3, ring slot alternates
+    place(I2{}, I0{}); fetch(y + 3, I0{}); test(I1{}, y);
+    place(I0{}, I1{}); fetch(y + 4, I1{}); test(I2{}, y + 1);
+    place(I1{}, I0{}); fetch(y + 5, I0{}); test(I0{}, y + 2);
+    place(I2{}, I1{}); fetch(y + 6, I1{}); test(I1{}, y + 3);
+    place(I0{}, I0{}); fetch(y + 7, I0{}); test(I2{}, y + 4);
+    place(I1{}, I1{}); fetch(y + 8, I1{}); test(I0{}, y + 5);
   }
   __syncthreads();
 
-  // dense refinement of the CTA's candidates + compaction
+  // dense second phase: strict 26-neighbour test, refinement, compaction
   const unsigned int n = min(s_cnt, (unsigned int)XT_CAP);
   for (unsigned int base = 0; base < n; base += XT_WARPS * 32) {
     const unsigned int i = base + threadIdx.x;
@@ -249,7 +274,8 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 3) k_find_points(const float *_
     Refined r;
     if (i < n) {
       const unsigned int e = s_list[i];
-      emit = refine(dog, plane, pitch, P, (int)(e & 0x3fffu), (int)((e >> 14) & 0x3fffu), (int)(e >> 28), r);
+      const int ex = (int)(e & 0x3fffu), ey = (int)((e >> 14) & 0x3fffu), es = (int)(e >> 28);
+      if (strict_extremum(dog, plane, pitch, es, ex, ey, P.thresh)) emit = refine(dog, plane, pitch, P, ex, ey, es, r);
     }
     emit_warp(emit, r, P, d_sift, d_oct, counter, max_pts, lane);
   }
