@@ -14,9 +14,9 @@
 //     against each of the 26 neighbours (cuSIFT_D.cu:450-470) is then applied to the
 //     few flagged pixels in the dense second phase, so exact ties are rejected
 //     exactly as in the reference.  No shared memory, no barriers in the scan.
-//   * candidates go to a small per-CTA list (never wraps: overflow is refined in
-//     place; the reference's 32-entry list silently wraps, cuSIFT_D.cu:455,465);
-//     after the scan the CTA refines them densely and compacts survivors with
+//   * candidates go to a per-CTA list that is drained before it can overflow (the
+//     reference's 32-entry list silently wraps, cuSIFT_D.cu:455,465); draining =
+//     the whole CTA verifies + refines them densely and compacts survivors with
 //     warp ballots, one global atomicAdd per warp.
 //   * the refinement is evaluated in the exact multiply-add order of the
 //     reference's sm_100a SASS, so x, y, scale, sharpness and edgeness are
@@ -31,7 +31,7 @@ constexpr int XT_COLS = 30;          // output columns per warp
 constexpr int XT_WARPS = 4;
 constexpr int XT_TW = XT_COLS * XT_WARPS;   // 120 output columns per CTA
 constexpr int XT_ROWS = 36;          // output rows per CTA (multiple of 6)
-constexpr int XT_CAP = 512;          // candidate list entries per CTA
+constexpr int XT_CAP = 4096;         // candidate list entries per CTA (drained before it can overflow)
 constexpr int NPL = CSB_NUM_DOG;     // 7 planes
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -128,18 +128,6 @@ __device__ __forceinline__ void emit_warp(bool emit, const Refined &r, const Ext
   }
 }
 
-// Slow path for a full candidate list: refine and append immediately.
-__device__ __noinline__ void refine_in_place(const float *__restrict__ dog, size_t plane, int pitch,
-                                             const ExtremaParams &P, int x, int y, int sc,
-                                             csb_sift_point *__restrict__ d_sift, int *__restrict__ d_oct,
-                                             unsigned int *__restrict__ counter, int max_pts) {
-  Refined r;
-  if (refine(dog, plane, pitch, P, x, y, sc, r)) {
-    const unsigned int idx = atomicAdd(counter, 1u);
-    if (idx < (unsigned int)max_pts) store_point(d_sift, d_oct, idx, r, P);
-  }
-}
-
 // Reference candidate rule (cuSIFT_D.cu:450-470): strictly beyond all 26 neighbours.
 __device__ __forceinline__ bool strict_extremum(const float *__restrict__ dog, size_t plane, int pitch, int sc, int x,
                                                 int y, float thresh) {
@@ -164,23 +152,6 @@ __device__ __forceinline__ bool strict_extremum(const float *__restrict__ dog, s
   return ok;
 }
 
-// Appends the flagged scales of pixel (x, y) to the CTA's candidate list; when the list is full
-// (rare) the candidate is verified and refined on the spot so that nothing is ever dropped.
-__device__ __noinline__ void push_candidates(unsigned int cmask, int x, int y, unsigned int *s_cnt, unsigned int *s_list,
-                                             const float *__restrict__ dog, size_t plane, int pitch,
-                                             const ExtremaParams &P, csb_sift_point *__restrict__ d_sift,
-                                             int *__restrict__ d_oct, unsigned int *__restrict__ counter, int max_pts) {
-  for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
-    if (!((cmask >> sc) & 1u)) continue;
-    const unsigned int slot = atomicAdd(s_cnt, 1u);
-    if (slot < XT_CAP) {
-      s_list[slot] = (unsigned int)x | ((unsigned int)y << 14) | ((unsigned int)sc << 28);
-    } else if (strict_extremum(dog, plane, pitch, sc, x, y, P.thresh)) {
-      refine_in_place(dog, plane, pitch, P, x, y, sc, d_sift, d_oct, counter, max_pts);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
                                                                   const __grid_constant__ ExtremaParams P,
                                                                   csb_sift_point *__restrict__ d_sift,
@@ -200,10 +171,10 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
 
-  // per plane: horizontal max3 / min3 of three consecutive rows (slots rotate), centre values of the
-  // middle row for the 5 centre planes, and two source rows in flight
+  // per plane: horizontal max3 / min3 of three consecutive rows (slots rotate), centre values of
+  // those rows for the 5 centre planes, and three source rows in flight
   float hx[NPL][3], hn[NPL][3], vc[CSB_NUM_SCALES][3];
-  float ring[2][NPL];
+  float ring[3][NPL];
   const float *col = dog + cx;
 
   auto fetch = [&](int r, auto RS) {
@@ -231,54 +202,57 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
       fx[p] = max3(hx[p][0], hx[p][1], hx[p][2]);
       fn[p] = min3(hn[p][0], hn[p][1], hn[p][2]);
     }
-    unsigned int cmask = 0;
+    const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + XT_ROWS);
 #pragma unroll
     for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
       const float val = vc[sc][M];
       const float mx = max3(fx[sc], fx[sc + 1], fx[sc + 2]);
       const float mn = min3(fn[sc], fn[sc + 1], fn[sc + 2]);
-      const bool cand = (val == mx && val > P.thresh) || (val == mn && val < -P.thresh);
-      cmask |= cand ? (1u << sc) : 0u;
+      const bool cand = rowOK && ((val == mx && val > P.thresh) || (val == mn && val < -P.thresh));
+      if (cand) s_list[atomicAdd(&s_cnt, 1u)] = (unsigned int)x | ((unsigned int)y << 14) | ((unsigned int)sc << 28);
     }
-    const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + XT_ROWS);
-    if (rowOK && cmask) push_candidates(cmask, x, y, &s_cnt, s_list, dog, plane, pitch, P, d_sift, d_oct, counter, max_pts);
+  };
+  // dense second phase: strict 26-neighbour test, refinement, compaction (whole CTA)
+  auto drain = [&]() {
+    const unsigned int n = s_cnt;
+    for (unsigned int base = 0; base < n; base += XT_WARPS * 32) {
+      const unsigned int i = base + threadIdx.x;
+      bool emit = false;
+      Refined r;
+      if (i < n) {
+        const unsigned int e = s_list[i];
+        const int ex = (int)(e & 0x3fffu), ey = (int)((e >> 14) & 0x3fffu), es = (int)(e >> 28);
+        if (strict_extremum(dog, plane, pitch, es, ex, ey, P.thresh)) emit = refine(dog, plane, pitch, P, ex, ey, es, r);
+      }
+      emit_warp(emit, r, P, d_sift, d_oct, counter, max_pts, lane);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
   };
   using I0 = std::integral_constant<int, 0>;
   using I1 = std::integral_constant<int, 1>;
   using I2 = std::integral_constant<int, 2>;
 
-  // prime: rows y0-1 -> slot 0, y0 -> slot 1; rows y0+1, y0+2 in flight
+  // prime: rows y0-1 -> slot 0, y0 -> slot 1; rows y0+1 .. y0+3 in flight
   fetch(y0 - 1, I0{});
   fetch(y0, I1{});
   place(I0{}, I0{});
   place(I1{}, I1{});
   fetch(y0 + 1, I0{});
   fetch(y0 + 2, I1{});
+  fetch(y0 + 3, I2{});
   const int yEnd = min(y0 + XT_ROWS, h - 1);   // exclusive; rows >= h-1 never qualify
-  for (int y = y0; y < yEnd; y += 6) {
-    // six row steps: window slot = (row - (y0-1)) mod 3, ring slot alternates
-    place(I2{}, I0{}); fetch(y + 3, I0{}); test(I1{}, y);
-    place(I0{}, I1{}); fetch(y + 4, I1{}); test(I2{}, y + 1);
-    place(I1{}, I0{}); fetch(y + 5, I0{}); test(I0{}, y + 2);
-    place(I2{}, I1{}); fetch(y + 6, I1{}); test(I1{}, y + 3);
-    place(I0{}, I0{}); fetch(y + 7, I0{}); test(I2{}, y + 4);
-    place(I1{}, I1{}); fetch(y + 8, I1{}); test(I0{}, y + 5);
+  for (int y = y0; y < yEnd; y += 3) {
+    place(I2{}, I0{}); fetch(y + 4, I0{}); test(I1{}, y);        // rows y-1, y, y+1
+    place(I0{}, I1{}); fetch(y + 5, I1{}); test(I2{}, y + 1);
+    place(I1{}, I2{}); fetch(y + 6, I2{}); test(I0{}, y + 2);
+    // three rows add at most 3*XT_TW*5 entries: drain early if the next three might not fit
+    __syncthreads();
+    if (s_cnt > XT_CAP - 3 * XT_TW * CSB_NUM_SCALES) drain();
   }
   __syncthreads();
-
-  // dense second phase: strict 26-neighbour test, refinement, compaction
-  const unsigned int n = min(s_cnt, (unsigned int)XT_CAP);
-  for (unsigned int base = 0; base < n; base += XT_WARPS * 32) {
-    const unsigned int i = base + threadIdx.x;
-    bool emit = false;
-    Refined r;
-    if (i < n) {
-      const unsigned int e = s_list[i];
-      const int ex = (int)(e & 0x3fffu), ey = (int)((e >> 14) & 0x3fffu), es = (int)(e >> 28);
-      if (strict_extremum(dog, plane, pitch, es, ex, ey, P.thresh)) emit = refine(dog, plane, pitch, P, ex, ey, es, r);
-    }
-    emit_warp(emit, r, P, d_sift, d_oct, counter, max_pts, lane);
-  }
+  drain();
 }
 
 }  // namespace
