@@ -14,10 +14,10 @@
 //     against each of the 26 neighbours (cuSIFT_D.cu:450-470) is then applied to the
 //     few flagged pixels in the dense second phase, so exact ties are rejected
 //     exactly as in the reference.  No shared memory, no barriers in the scan.
-//   * candidates go to a per-CTA list that is drained before it can overflow (the
-//     reference's 32-entry list silently wraps, cuSIFT_D.cu:455,465); draining =
-//     the whole CTA verifies + refines them densely and compacts survivors with
-//     warp ballots, one global atomicAdd per warp.
+//   * candidates go to a per-CTA list sized for the worst case (16-bit entries; the
+//     reference's 32-entry list silently wraps, cuSIFT_D.cu:455,465); after the
+//     scan the whole CTA verifies + refines them densely and compacts survivors
+//     with warp ballots, one global atomicAdd per warp.
 //   * the refinement is evaluated in the exact multiply-add order of the
 //     reference's sm_100a SASS, so x, y, scale, sharpness and edgeness are
 //     bit-identical to the reference's for the same DoG input.
@@ -31,7 +31,7 @@ constexpr int XT_COLS = 30;          // output columns per warp
 constexpr int XT_WARPS = 4;
 constexpr int XT_TW = XT_COLS * XT_WARPS;   // 120 output columns per CTA
 constexpr int XT_ROWS = 36;          // output rows per CTA (multiple of 6)
-constexpr int XT_CAP = 4096;         // candidate list entries per CTA (drained before it can overflow)
+constexpr int XT_CAP = XT_COLS * XT_WARPS * XT_ROWS * CSB_NUM_SCALES;   // worst case: the list cannot overflow
 constexpr int NPL = CSB_NUM_DOG;     // 7 planes
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
                                                                   int *__restrict__ d_oct,
                                                                   unsigned int *__restrict__ counter, int max_pts) {
   __shared__ unsigned int s_cnt;
-  __shared__ unsigned int s_list[XT_CAP];   // x | y << 14 | scale << 28
+  __shared__ unsigned short s_list[XT_CAP];   // local column | local row << 7 | scale << 13
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = blockIdx.x * XT_TW + warp * XT_COLS - 1 + lane;
@@ -203,13 +203,21 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
       fn[p] = min3(hn[p][0], hn[p][1], hn[p][2]);
     }
     const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + XT_ROWS);
+    unsigned int cmask = 0;
 #pragma unroll
     for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
       const float val = vc[sc][M];
       const float mx = max3(fx[sc], fx[sc + 1], fx[sc + 2]);
       const float mn = min3(fn[sc], fn[sc + 1], fn[sc + 2]);
-      const bool cand = rowOK && ((val == mx && val > P.thresh) || (val == mn && val < -P.thresh));
-      if (cand) s_list[atomicAdd(&s_cnt, 1u)] = (unsigned int)x | ((unsigned int)y << 14) | ((unsigned int)sc << 28);
+      const float m = (val > 0.0f) ? mx : mn;               // the side this value could be an extremum of
+      const bool cand = (val == m) && (fabsf(val) > P.thresh);
+      cmask |= cand ? (1u << sc) : 0u;
+    }
+    if (rowOK && cmask) {                                    // rare
+      const unsigned int loc = (unsigned int)(x - (int)blockIdx.x * XT_TW) | ((unsigned int)(y - y0) << 7);
+#pragma unroll
+      for (int sc = 0; sc < CSB_NUM_SCALES; sc++)
+        if ((cmask >> sc) & 1u) s_list[atomicAdd(&s_cnt, 1u)] = (unsigned short)(loc | ((unsigned int)sc << 13));
     }
   };
   // dense second phase: strict 26-neighbour test, refinement, compaction (whole CTA)
@@ -221,14 +229,11 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
       Refined r;
       if (i < n) {
         const unsigned int e = s_list[i];
-        const int ex = (int)(e & 0x3fffu), ey = (int)((e >> 14) & 0x3fffu), es = (int)(e >> 28);
+        const int ex = (int)blockIdx.x * XT_TW + (int)(e & 0x7fu), ey = y0 + (int)((e >> 7) & 0x3fu), es = (int)(e >> 13);
         if (strict_extremum(dog, plane, pitch, es, ex, ey, P.thresh)) emit = refine(dog, plane, pitch, P, ex, ey, es, r);
       }
       emit_warp(emit, r, P, d_sift, d_oct, counter, max_pts, lane);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
   };
   using I0 = std::integral_constant<int, 0>;
   using I1 = std::integral_constant<int, 1>;
@@ -247,9 +252,6 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
     place(I2{}, I0{}); fetch(y + 4, I0{}); test(I1{}, y);        // rows y-1, y, y+1
     place(I0{}, I1{}); fetch(y + 5, I1{}); test(I2{}, y + 1);
     place(I1{}, I2{}); fetch(y + 6, I2{}); test(I0{}, y + 2);
-    // three rows add at most 3*XT_TW*5 entries: drain early if the next three might not fit
-    __syncthreads();
-    if (s_cnt > XT_CAP - 3 * XT_TW * CSB_NUM_SCALES) drain();
   }
   __syncthreads();
   drain();

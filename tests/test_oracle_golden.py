@@ -89,10 +89,11 @@ def test_detector_golden_cusift1_check():
     coarse = pts[pts["subsampling"] > 1]
     assert len(coarse) == 1555
     assert set(np.nonzero(pts["subsampling"] > 1)[0]) <= set(idx.tolist())
-    # orientation: texture-unit emulation (1.8 fixed-point weights) -> tolerance, not equality
+    # orientation: with the texture filter restated from hardware measurements (oracle.c tex2d) every
+    # golden row agrees within the reference's own run-to-run spread (float atomics, ~6e-5 deg)
     do = PU.ang_diff_deg(pts["orientation"][idx], gold[:, 3])
-    assert np.median(do) < 0.005
-    assert np.mean(do <= PU.ORI_TOL_DEG) > 0.92
+    assert np.median(do) < 1e-4
+    assert do.max() < PU.ORI_TOL_DEG, do.max()
 
 
 def test_scale_down_constants_and_shape():
