@@ -60,6 +60,7 @@ SIGNATURES = {
     "csb_scale_down": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     "csb_rootsift": (_i, [_vp, _vp, _i]),
     "csb_match": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
+    "csb_match_redo_blocks": (C.c_longlong, [_vp]),
     "csb_find_homography": (_i, [_vp, _vp, _i, _ip, _i, C.c_float, _fp, _ip]),
     "csb_debug_octave": (_i, [_vp, _i, _fp, _fp, _ip, _ip]),
     "csb_profile_enable": (_i, [_vp, _i]),

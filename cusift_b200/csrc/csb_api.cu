@@ -81,6 +81,15 @@ struct csb_ctx {
   bool no_fuse = false;
   std::vector<ProfEntry> prof;
   long long launches = 0;
+  // tensor-core matcher scratch
+  bool match_exact = false;          // CSB_MATCH_EXACT=1: always use the fp32 CUDA-core kernel
+  void *tc_pack[2] = {nullptr, nullptr};
+  size_t tc_pack_cap[2] = {0, 0};
+  float *tc_val = nullptr;
+  int *tc_idx = nullptr, *tc_flags = nullptr, *tc_list = nullptr, *tc_count = nullptr;
+  size_t tc_sl_cap = 0, tc_blk_cap = 0;
+  int *h_tc_count = nullptr;
+  long long tc_redo_blocks = 0;      // 16-query blocks redone exactly (diagnostics)
   // homography scratch
   float *d_coord = nullptr, *d_homo = nullptr;
   int *d_rand = nullptr, *d_counts = nullptr;
@@ -459,6 +468,8 @@ int csb_ctx_create(int device, int num_slots, csb_ctx **out) {
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   const char *nf = getenv("CSB_NO_FUSE");
   ctx->no_fuse = nf && nf[0] == '1';
+  const char *me = getenv("CSB_MATCH_EXACT");
+  ctx->match_exact = me && me[0] == '1';
   ctx->n_slots = num_slots;
   ctx->slots = new Slot[num_slots];
   for (int i = 0; i < num_slots; i++) {
@@ -491,6 +502,14 @@ void csb_ctx_destroy(csb_ctx *ctx) {
     if (s->stream) cudaStreamDestroy(s->stream);
   }
   delete[] ctx->slots;
+  for (int i = 0; i < 2; i++)
+    if (ctx->tc_pack[i]) cudaFree(ctx->tc_pack[i]);
+  if (ctx->tc_val) cudaFree(ctx->tc_val);
+  if (ctx->tc_idx) cudaFree(ctx->tc_idx);
+  if (ctx->tc_flags) cudaFree(ctx->tc_flags);
+  if (ctx->tc_list) cudaFree(ctx->tc_list);
+  if (ctx->tc_count) cudaFree(ctx->tc_count);
+  if (ctx->h_tc_count) cudaFreeHost(ctx->h_tc_count);
   if (ctx->d_coord) cudaFree(ctx->d_coord);
   if (ctx->d_homo) cudaFree(ctx->d_homo);
   if (ctx->d_rand) cudaFree(ctx->d_rand);
@@ -657,9 +676,68 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
   if (!d_sift1 || !d_sift2) return fail(ctx, CSB_E_INVALID, "csb_match: null device data");
   CSB_CHECK(ctx, cudaSetDevice(ctx->device));
   Slot *s = &ctx->slots[0];
-  {
+  const bool use_tc = !ctx->match_exact && n1 >= 256 && n2 >= 256;
+  if (!use_tc) {
     LaunchScope ls(ctx, s, "match");
     launch_match((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, distance, s->stream);
+  } else {
+    // tensor-core path: pack -> tcgen05 scan (top-8 short list per query and split) -> exact rescoring
+    const int ns[2] = {n1, n2};
+    const void *sets[2] = {d_sift1, d_sift2};
+    for (int i = 0; i < 2; i++) {
+      const size_t need = tc_packed_bytes(ns[i]);
+      if (ctx->tc_pack_cap[i] < need) {
+        if (ctx->tc_pack[i]) cudaFree(ctx->tc_pack[i]);
+        ctx->tc_pack[i] = nullptr;
+        CSB_CHECK(ctx, cudaMalloc(&ctx->tc_pack[i], need));
+        ctx->tc_pack_cap[i] = need;
+      }
+    }
+    const int splits = tc_splits(n1, n2, ctx->sm_count);
+    const size_t sl_need = (size_t)tc_pad(n1) * 4 * 8;      // up to 4 splits x top-8
+    if (ctx->tc_sl_cap < sl_need) {
+      if (ctx->tc_val) cudaFree(ctx->tc_val);
+      if (ctx->tc_idx) cudaFree(ctx->tc_idx);
+      ctx->tc_val = nullptr; ctx->tc_idx = nullptr;
+      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_val, sizeof(float) * sl_need));
+      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_idx, sizeof(int) * sl_need));
+      ctx->tc_sl_cap = sl_need;
+    }
+    const size_t blk_need = (size_t)(n1 + 15) / 16;
+    if (ctx->tc_blk_cap < blk_need) {
+      if (ctx->tc_flags) cudaFree(ctx->tc_flags);
+      if (ctx->tc_list) cudaFree(ctx->tc_list);
+      ctx->tc_flags = nullptr; ctx->tc_list = nullptr;
+      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_flags, sizeof(int) * blk_need));
+      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_list, sizeof(int) * blk_need));
+      ctx->tc_blk_cap = blk_need;
+    }
+    if (!ctx->tc_count) {
+      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_count, 256));
+      CSB_CHECK(ctx, cudaHostAlloc((void **)&ctx->h_tc_count, 256, cudaHostAllocDefault));
+    }
+    {
+      LaunchScope ls(ctx, s, "match_pack");
+      ctx->launches += 1;
+      launch_pack_f16((const csb_sift_point *)sets[0], ns[0], ctx->tc_pack[0], s->stream);
+      launch_pack_f16((const csb_sift_point *)sets[1], ns[1], ctx->tc_pack[1], s->stream);
+    }
+    {
+      LaunchScope ls(ctx, s, "match_tc");
+      launch_match_tc(ctx->tc_pack[0], n1, ctx->tc_pack[1], n2, splits, ctx->tc_val, ctx->tc_idx, s->stream);
+    }
+    {
+      LaunchScope ls(ctx, s, "match_rescore");
+      ctx->launches += 1;
+      launch_rescore((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, ctx->tc_val, ctx->tc_idx, splits,
+                     distance, ctx->tc_flags, ctx->tc_list, ctx->tc_count, s->stream);
+    }
+    {
+      LaunchScope ls(ctx, s, "match_redo");
+      launch_match_blocks((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, distance, ctx->tc_list,
+                          ctx->tc_count, s->stream);
+    }
+    CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_tc_count, ctx->tc_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   }
   CSB_CHECK(ctx, cudaGetLastError());
   if (h_sift1) {   // the five match fields, strided (matching.cu:352-356)
@@ -669,9 +747,12 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
                                      5 * sizeof(float), n1, cudaMemcpyDeviceToHost, s->stream));
   }
   CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+  if (use_tc) ctx->tc_redo_blocks += ctx->h_tc_count[0];
   if (ctx->profile) prof_collect(ctx, s);
   return 0;
 }
+
+long long csb_match_redo_blocks(const csb_ctx *ctx) { return ctx ? ctx->tc_redo_blocks : 0; }
 
 int csb_find_homography(csb_ctx *ctx, const void *d_sift, int n, const int *h_rand_pts, int num_loops, float thresh,
                         float *H9, int *num_inliers) {

@@ -47,6 +47,17 @@ void launch_copy_out(const csb_sift_point *d_sift, const unsigned int *d_counter
                      int *h_count_mapped, int sm_count, cudaStream_t st);
 void launch_match(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
                   cudaStream_t st);
+void launch_match_blocks(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
+                         const int *block_list, const int *block_count, cudaStream_t st);
+// tensor-core matcher (kernels_match_tc.cu)
+size_t tc_packed_bytes(int n);
+int tc_pad(int n);
+int tc_splits(int n1, int n2, int sm_count);
+void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, cudaStream_t st);
+void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
+                     cudaStream_t st);
+void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,
+                    int n_splits, int distance, int *redo_flags, int *redo_list, int *redo_count, cudaStream_t st);
 void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
                        int *d_counts, int num_loops, float thresh2, cudaStream_t st);
 

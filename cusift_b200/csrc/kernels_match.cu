@@ -24,13 +24,17 @@ __device__ __forceinline__ bool better(float a, float b) {
 
 template <bool kL2>
 __global__ void __launch_bounds__(256) k_match(csb_sift_point *__restrict__ s1, int n1,
-                                               const csb_sift_point *__restrict__ s2, int n2, int chunks) {
+                                               const csb_sift_point *__restrict__ s2, int n2, int chunks,
+                                               const int *__restrict__ block_list, const int *__restrict__ block_count) {
   __shared__ float A[16][128];
   __shared__ float B[16][128];
   const int tx = threadIdx.x, ty = threadIdx.y;
+  // optional indirection: only the listed blocks of 16 queries (redo pass of the tensor-core matcher)
+  if (block_list != nullptr && (int)blockIdx.x >= *block_count) return;
+  const int qb = block_list != nullptr ? block_list[blockIdx.x] : (int)blockIdx.x;
 
   {
-    const float *ptr1 = s1[min(n1 - 1, (int)blockIdx.x * 16 + ty)].data;
+    const float *ptr1 = s1[min(n1 - 1, qb * 16 + ty)].data;
 #pragma unroll
     for (int i = 0; i < 8; i++) A[ty][16 * i + tx] = ptr1[16 * i + tx];
   }
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(256) k_match(csb_sift_point *__restrict__ s1, 
     if (better<kL2>(os, second)) second = os;
   }
 
-  const int p1 = blockIdx.x * 16 + ty;
+  const int p1 = qb * 16 + ty;
   if (tx == 0 && p1 < n1) {
     csb_sift_point *o = s1 + p1;
     o->score = best;
@@ -101,6 +105,16 @@ void launch_match(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2
   if (n1 <= 0 || n2 <= 0) return;
   dim3 blk(16, 16), grd((n1 + 15) / 16);
   const int chunks = (n2 + 15) / 16;
-  if (distance == 1) k_match<true><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks);
-  else k_match<false><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks);
+  if (distance == 1) k_match<true><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, nullptr, nullptr);
+  else k_match<false><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, nullptr, nullptr);
+}
+
+// Exact pass restricted to the 16-query blocks in block_list[0 .. *block_count).
+void launch_match_blocks(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
+                         const int *block_list, const int *block_count, cudaStream_t st) {
+  if (n1 <= 0 || n2 <= 0) return;
+  dim3 blk(16, 16), grd((n1 + 15) / 16);
+  const int chunks = (n2 + 15) / 16;
+  if (distance == 1) k_match<true><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, block_list, block_count);
+  else k_match<false><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, block_list, block_count);
 }

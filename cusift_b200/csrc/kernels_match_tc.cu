@@ -1,0 +1,456 @@
+// Brute-force matching on the 5th-generation tensor cores (tcgen05 / TMEM), with
+// exact fp32 rescoring so that the results equal the reference's.
+//
+// MatchSiftData is the one dense contraction of the hot path: S = D1 * D2^T with
+// K = 128 (reference: ComputeDistance, extras/matching.cu:52-98, a 16x16-tile fp32
+// CUDA-core kernel that writes the n1 x n2 matrix to HBM, then FindMinCorr/FindMaxCorr
+// :116-270 reads it back).  Here:
+//
+//  1. k_pack_f16     descriptors (fp32, 588-byte AoS records) -> fp16, K-major,
+//                    128-byte-swizzled operand tiles in global memory, laid out so that
+//                    any block of rows of one 64-wide K half is ONE contiguous range.
+//  2. k_match_tc     persistent-style CTA per (256 queries, slice of the candidates):
+//                      warp 0   producer: 1-D bulk copies (cp.async.bulk -> UBLKCP) of the
+//                               query tiles (once) and of the 256-candidate tiles (2 stages),
+//                               completion on mbarriers (expect_tx);
+//                      warp 1   one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                               M128 x N256 x K16, 8 per accumulator, operands straight from
+//                               shared memory (smem descriptors, SWIZZLE_128B), fp32
+//                               accumulators in TMEM: two 128x256 accumulators (512 columns),
+//                               one per 128-query half, so every candidate tile is used twice;
+//                               tcgen05.commit releases the smem stage / publishes the accumulator;
+//                      warps 2-9  epilogue: thread = one query row (one TMEM lane); tcgen05.ld
+//                               32 columns at a time, chunk-max filter, sorted top-8 of the
+//                               approximate dot products kept in registers.
+//  3. k_rescore      warp per query: exact fp32 scores of the short-listed candidates in the
+//                    reference's rotated k order (bit-identical to ComputeDistance), then the
+//                    reference's best / second-best rule incl. its tie-breaking
+//                    (FindMinCorr/FindMaxCorr).  A query whose short list cannot be PROVEN to
+//                    contain the exact top two (8th approximate score within 2*eps of the 2nd)
+//                    is flagged and redone by the exact fp32 kernel (kernels_match.cu).
+//
+// fp16 inputs: descriptors are non-negative, <= 1, unit norm; rounding each element to
+// fp16 perturbs a dot product by < 128 * 2 * 2^-12 * (elementwise products) <= 6.1e-4 * dot.
+#include <cuda_fp16.h>
+
+#include "csb_internal.h"
+
+namespace {
+
+constexpr int TC_QT = 256;        // queries per CTA (two 128-row accumulators)
+constexpr int TC_CT = 256;        // candidates per tile (UMMA N)
+constexpr int TC_STAGES = 2;
+constexpr int TC_TOPK = 8;
+constexpr int KHALF_BYTES_PER_ROW = 128;          // 64 fp16
+constexpr uint32_t A_HALF_BYTES = 128 * KHALF_BYTES_PER_ROW;      // one 128-row x 64-K operand block: 16 KB
+constexpr uint32_t B_HALF_BYTES = TC_CT * KHALF_BYTES_PER_ROW;    // 32 KB
+constexpr uint32_t SMEM_A = 2 /*query halves*/ * 2 /*K halves*/ * A_HALF_BYTES;   // 64 KB
+constexpr uint32_t SMEM_B_STAGE = 2 * B_HALF_BYTES;                                 // 64 KB
+constexpr uint32_t SMEM_TC = SMEM_A + TC_STAGES * SMEM_B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 32 * (2 + 8);
+constexpr float TC_EPS = 6.5e-4f;   // bound on |fp16-input dot - exact dot| for unit descriptors
+
+// ---- PTX wrappers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: 8-row x 128-byte atoms
+// (1024 B), consecutive atoms along M/N 1024 B apart (SBO); LBO unused for swizzled K-major.
+__device__ __forceinline__ uint64_t smem_desc_k128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address >> 4, bits [0,14)
+  d |= (uint64_t)0 << 16;                                // leading byte offset >> 4 (ignored)
+  d |= (uint64_t)(1024u >> 4) << 32;                     // stride byte offset >> 4, bits [32,46)
+  d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor, kind::f16: fp16 x fp16 -> fp32, both operands K-major, M=128, N=256.
+constexpr uint32_t IDESC_F16_M128_N256 = (1u << 4)                 // D format = F32
+                                         | (0u << 7) | (0u << 10)   // A, B format = F16
+                                         | (0u << 15) | (0u << 16)  // A, B K-major
+                                         | ((uint32_t)(TC_CT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// ---- 1. pack ----------------------------------------------------------------------
+// Packed layout (per set): two K-halves; half kb is a [n_pad][64] fp16 matrix (128-byte rows) in
+// which the 16-byte chunk c of row r is stored at chunk position c ^ (r & 7) (128B swizzle).
+__global__ void __launch_bounds__(256) k_pack_f16(const csb_sift_point *__restrict__ pts, int n, int n_pad,
+                                                  __half *__restrict__ packed) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 16-byte chunk): 16 chunks/row
+  const int r = gid >> 4, c16 = gid & 15;
+  if (r >= n_pad) return;
+  const int kb = c16 >> 3, c = c16 & 7;
+  __align__(16) __half v[8];
+  if (r < n) {
+    const float *d = pts[r].data + 8 * c16;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __float2half_rn(d[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __float2half_rn(0.0f);
+  }
+  char *dst = reinterpret_cast<char *>(packed) + (size_t)kb * n_pad * KHALF_BYTES_PER_ROW +
+              (size_t)r * KHALF_BYTES_PER_ROW + ((c ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(v);
+}
+
+// ---- 2. tensor-core scan --------------------------------------------------------------
+// Sorted (descending) top-K insert.
+__device__ __forceinline__ void topk_insert(float (&tv)[TC_TOPK], int (&ti)[TC_TOPK], float v, int idx) {
+#pragma unroll
+  for (int k = 0; k < TC_TOPK; k++) {
+    if (v > tv[k]) {
+      const float fv = tv[k];
+      const int fi = ti[k];
+      tv[k] = v;
+      ti[k] = idx;
+      v = fv;
+      idx = fi;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__restrict__ q_packed, int nq_pad,
+                                                            const __half *__restrict__ c_packed, int nc, int nc_pad,
+                                                            int tiles_per_split, float *__restrict__ out_val,
+                                                            int *__restrict__ out_idx, int n_splits) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte alignment for the swizzle atoms
+  unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char *sA = base;                          // [qhalf][khalf][128 rows][128 B]
+  unsigned char *sB = base + SMEM_A;                 // [stage][khalf][256 rows][128 B]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base + SMEM_A + TC_STAGES * SMEM_B_STAGE);
+  uint64_t *a_full = bars + 0;
+  uint64_t *b_full = bars + 1;                       // [TC_STAGES]
+  uint64_t *b_empty = bars + 1 + TC_STAGES;          // [TC_STAGES]
+  uint64_t *acc_full = bars + 1 + 2 * TC_STAGES;     // [2]
+  uint64_t *acc_empty = bars + 3 + 2 * TC_STAGES;    // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 + 2 * TC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qtile = blockIdx.x, split = blockIdx.y;
+  const int n_tiles_total = nc_pad / TC_CT;
+  const int t0 = split * tiles_per_split;
+  const int t1 = min(t0 + tiles_per_split, n_tiles_total);
+  const int n_tiles = max(t1 - t0, 0);
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(a_full, 1);
+    for (int s = 0; s < TC_STAGES; s++) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(acc_full + a, 1);
+      mbar_init(acc_empty + a, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {   // TMEM: all 512 columns (two 128 x 256 fp32 accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      mbar_expect_tx(a_full, SMEM_A);
+      for (int qh = 0; qh < 2; qh++)
+        for (int kb = 0; kb < 2; kb++)
+          bulk_g2s(sA + (qh * 2 + kb) * A_HALF_BYTES,
+                   reinterpret_cast<const char *>(q_packed) + (size_t)kb * nq_pad * KHALF_BYTES_PER_ROW +
+                       (size_t)(qtile * TC_QT + qh * 128) * KHALF_BYTES_PER_ROW,
+                   A_HALF_BYTES, a_full);
+      for (int i = 0; i < n_tiles; i++) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(b_empty + s, ph ^ 1);
+        mbar_expect_tx(b_full + s, SMEM_B_STAGE);
+        for (int kb = 0; kb < 2; kb++)
+          bulk_g2s(sB + s * SMEM_B_STAGE + kb * B_HALF_BYTES,
+                   reinterpret_cast<const char *>(c_packed) + (size_t)kb * nc_pad * KHALF_BYTES_PER_ROW +
+                       (size_t)(t0 + i) * TC_CT * KHALF_BYTES_PER_ROW,
+                   B_HALF_BYTES, b_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+      for (int i = 0; i < n_tiles; i++) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(b_full + s, ph);
+        tc_fence_after();
+        for (int qh = 0; qh < 2; qh++) {
+          // accumulator qh is reused every tile: wait until the epilogue drained the previous one
+          mbar_wait(acc_empty + qh, (i & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(qh * TC_CT);
+#pragma unroll
+          for (int kb = 0; kb < 2; kb++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint64_t ad = smem_desc_k128(smem_u32(sA + (qh * 2 + kb) * A_HALF_BYTES) + k * 32);
+              const uint64_t bd = smem_desc_k128(smem_u32(sB + s * SMEM_B_STAGE + kb * B_HALF_BYTES) + k * 32);
+              tc_mma_f16(d_tmem, ad, bd, IDESC_F16_M128_N256, (kb | k) ? 1u : 0u);
+            }
+          }
+          tc_commit(acc_full + qh);       // accumulator qh complete -> epilogue
+        }
+        tc_commit(b_empty + s);           // both MMAs of this stage done -> producer may refill
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps, thread = one query row =====
+    const int ew = warp - 2;                 // 0..7
+    const int qh = ew >> 2;                  // query half (accumulator)
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int row = qh * 128 + quad * 32 + lane;
+    float tv[TC_TOPK];
+    int ti[TC_TOPK];
+#pragma unroll
+    for (int k = 0; k < TC_TOPK; k++) {
+      tv[k] = -1.0f;
+      ti[k] = -1;
+    }
+    for (int i = 0; i < n_tiles; i++) {
+      mbar_wait(acc_full + qh, i & 1);
+      tc_fence_after();
+      const int col0 = (t0 + i) * TC_CT;
+#pragma unroll 1
+      for (int ch = 0; ch < TC_CT / 32; ch++) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qh * TC_CT + ch * 32), r);
+        float m = __uint_as_float(r[0]);
+#pragma unroll
+        for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(r[j]));
+        if (m > tv[TC_TOPK - 1]) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float v = __uint_as_float(r[j]);
+            const int cidx = col0 + ch * 32 + j;
+            if (v > tv[TC_TOPK - 1] && cidx < nc) topk_insert(tv, ti, v, cidx);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty + qh);           // 128 arrivals free the accumulator
+    }
+    const size_t o = ((size_t)(qtile * TC_QT + row) * n_splits + split) * TC_TOPK;
+#pragma unroll
+    for (int k = 0; k < TC_TOPK; k++) {
+      out_val[o + k] = tv[k];
+      out_idx[o + k] = ti[k];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// ---- 3. exact rescoring -----------------------------------------------------------------
+__device__ __forceinline__ int bitrev4(int x) { return ((x & 1) << 3) | ((x & 2) << 1) | ((x & 4) >> 1) | ((x & 8) >> 3); }
+
+template <bool kL2>
+__global__ void __launch_bounds__(128) k_rescore(csb_sift_point *__restrict__ s1, int n1,
+                                                 const csb_sift_point *__restrict__ s2, int n2,
+                                                 const float *__restrict__ sl_val, const int *__restrict__ sl_idx,
+                                                 int n_splits, int *__restrict__ redo_flags) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n1) return;
+  const int q = warp;
+  const int n_list = n_splits * TC_TOPK;          // <= 32
+  float av = -2.0f;
+  int ci = -1;
+  if (lane < n_list) {
+    av = sl_val[(size_t)q * n_list + lane];
+    ci = sl_idx[(size_t)q * n_list + lane];
+    if (ci < 0) av = -2.0f;
+  }
+  // proof obligation: every candidate NOT in the list has approximate dot <= U = max over splits of
+  // that split's 8th entry; the exact top two are listed if U + 2 eps < (2nd largest approximate dot)
+  float u = (lane < n_list && (lane % TC_TOPK) == TC_TOPK - 1) ? av : -2.0f;
+  float a1 = av;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
+    a1 = fmaxf(a1, __shfl_xor_sync(0xffffffffu, a1, o));
+  }
+  const unsigned int who = __ballot_sync(0xffffffffu, av == a1 && ci >= 0);
+  const int first = __ffs(who) - 1;
+  float a2 = (lane == first) ? -2.0f : av;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a2 = fmaxf(a2, __shfl_xor_sync(0xffffffffu, a2, o));
+  const bool complete = (n2 <= n_list) || (u < -0.5f);   // every candidate is listed
+  const bool proven = complete || (u + 2.0f * TC_EPS < a2);
+
+  // exact score in the reference's rotated k order (matching.cu:84-89), lane = one listed candidate
+  float score = kL2 ? 999.0f : -1.0f;
+  if (ci >= 0) {
+    const float *pa = s1[q].data, *pb = s2[ci].data;
+    const int tx = ci & 15;
+    float sum = 0.0f;
+    for (int i = 0; i < 128; i++) {
+      const int k = (i + tx) & 127;
+      sum = __fmaf_rn(pa[k], pb[k], sum);
+    }
+    score = kL2 ? __fsub_rn(2.0f, __fadd_rn(sum, sum)) : sum;
+  }
+  // best: FindMinCorr's winner = lowest (score, bitrev4(col % 16), col / 16); second = best of the rest
+  // (an equal duplicate lands in `second`, matching.cu:229-235)
+  auto better = [](float sa, int ia, float sb, int ib) {   // is a strictly preferred to b ?
+    if (ib < 0) return ia >= 0;
+    if (ia < 0) return false;
+    if (sa != sb) return kL2 ? (sa < sb) : (sa > sb);
+    const int ra = bitrev4(ia & 15), rb = bitrev4(ib & 15);
+    if (ra != rb) return ra < rb;
+    return ia < ib;
+  };
+  float bs = score;
+  int bi = ci;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(os, oi, bs, bi)) {
+      bs = os;
+      bi = oi;
+    }
+  }
+  float ss = (ci >= 0 && ci != bi) ? score : (kL2 ? 999.0f : -1.0f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, ss, o);
+    ss = kL2 ? fminf(ss, os) : fmaxf(ss, os);
+  }
+  if (lane == 0) {
+    if (!proven) {
+      redo_flags[q >> 4] = 1;              // the exact kernel redoes this block of 16 queries
+    } else {
+      csb_sift_point *o = s1 + q;
+      o->score = bs;
+      if (kL2) o->ambiguity = (float)((double)bs / ((double)ss + 1e-6));
+      else o->ambiguity = (float)((double)__fsub_rn(1.0f, bs) / ((double)__fsub_rn(1.0f, ss) + 1e-6));
+      o->match = bi;
+      if (bi >= 0) {
+        o->match_xpos = s2[bi].coords2D[0];
+        o->match_ypos = s2[bi].coords2D[1];
+      }
+    }
+  }
+}
+
+// Compacts the flagged 16-query blocks into a list for the exact kernel.
+__global__ void k_collect_redo(const int *__restrict__ flags, int n_blocks, int *__restrict__ list, int *__restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_blocks && flags[i]) list[atomicAdd(count, 1)] = i;
+}
+
+}  // namespace
+
+size_t tc_packed_bytes(int n) { return (size_t)((n + TC_QT - 1) / TC_QT * TC_QT) * 256; }
+int tc_pad(int n) { return (n + TC_QT - 1) / TC_QT * TC_QT; }
+int tc_splits(int n1, int n2, int sm_count) {
+  const int qtiles = tc_pad(n1) / TC_QT, ctiles = tc_pad(n2) / TC_CT;
+  int s = sm_count / (qtiles > 0 ? qtiles : 1);
+  if (s < 1) s = 1;
+  if (s > 4) s = 4;                       // the rescoring warp handles at most 4 x 8 listed candidates
+  if (s > ctiles) s = ctiles;
+  return s;
+}
+
+void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, cudaStream_t st) {
+  const int n_pad = tc_pad(n);
+  const int threads = n_pad * 16;
+  k_pack_f16<<<(threads + 255) / 256, 256, 0, st>>>(pts, n, n_pad, reinterpret_cast<__half *>(packed));
+}
+
+void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
+                     cudaStream_t st) {
+  const int nq_pad = tc_pad(n1), nc_pad = tc_pad(n2);
+  const int ctiles = nc_pad / TC_CT;
+  const int tiles_per_split = (ctiles + n_splits - 1) / n_splits;
+  cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC);
+  dim3 grd(nq_pad / TC_QT, n_splits);
+  k_match_tc<<<grd, TC_THREADS, SMEM_TC, st>>>(reinterpret_cast<const __half *>(q_packed), nq_pad,
+                                               reinterpret_cast<const __half *>(c_packed), n2, nc_pad, tiles_per_split,
+                                               sl_val, sl_idx, n_splits);
+}
+
+void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,
+                    int n_splits, int distance, int *redo_flags, int *redo_list, int *redo_count, cudaStream_t st) {
+  const int n_blocks16 = (n1 + 15) / 16;
+  cudaMemsetAsync(redo_flags, 0, sizeof(int) * n_blocks16, st);
+  cudaMemsetAsync(redo_count, 0, sizeof(int), st);
+  const int blocks = (n1 * 32 + 127) / 128;
+  if (distance == 1) k_rescore<true><<<blocks, 128, 0, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, redo_flags);
+  else k_rescore<false><<<blocks, 128, 0, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, redo_flags);
+  k_collect_redo<<<(n_blocks16 + 255) / 256, 256, 0, st>>>(redo_flags, n_blocks16, redo_list, redo_count);
+}

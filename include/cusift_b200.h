@@ -133,6 +133,10 @@ int csb_rootsift(csb_ctx *ctx, void *d_sift, int n);
  * distance: 0 = MatchSiftDistanceDotProduct, 1 = MatchSiftDistanceL2
  * (extras/matching.h:10-13). */
 int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, int distance, void *h_sift1);
+/* Diagnostics of the tensor-core matcher (used for sets of >= 256 points; set CSB_MATCH_EXACT=1
+ * to force the fp32 CUDA-core kernel): number of 16-query blocks whose short list could not be
+ * proven complete and were redone exactly, accumulated since the context was created. */
+long long csb_match_redo_blocks(const csb_ctx *ctx);
 
 /* ---- homography -------------------------------------------------------------
  * FindHomography (extras/homography.h:8, homography.cu:191-278).  Valid points
