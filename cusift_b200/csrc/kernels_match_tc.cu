@@ -19,15 +19,22 @@
 //                               accumulators in TMEM: two 128x256 accumulators (512 columns),
 //                               one per 128-query half, so every candidate tile is used twice;
 //                               tcgen05.commit releases the smem stage / publishes the accumulator;
-//                      warps 2-9  epilogue: thread = one query row (one TMEM lane); tcgen05.ld
-//                               32 columns at a time, chunk-max filter, sorted top-8 of the
-//                               approximate dot products kept in registers.
-//  3. k_rescore      warp per query: exact fp32 scores of the short-listed candidates in the
+//                      warps 2-9  epilogue: thread = one query row (one TMEM lane), tcgen05.ld 32
+//                               columns at a time.  The candidate slice is swept TWICE (the
+//                               tensor pipe has time to spare, the epilogue does not):
+//                               sweep 1 keeps the two largest approximate dot products
+//                               m1 >= m2 per row, branch-free (3 FMNMX per value);
+//                               sweep 2 lists every candidate with approximate dot >= m2 - 2 eps
+//                               (chunk-max filter, so the divergent append path is rare).
+//                               Any candidate left out has exact dot < m2 - eps <= the exact dots
+//                               of at least two listed ones, so the exact best and second best
+//                               are always in the list.
+//  3. k_rescore      warp per query: exact fp32 scores of the listed candidates in the
 //                    reference's rotated k order (bit-identical to ComputeDistance), then the
 //                    reference's best / second-best rule incl. its tie-breaking
-//                    (FindMinCorr/FindMaxCorr).  A query whose short list cannot be PROVEN to
-//                    contain the exact top two (8th approximate score within 2*eps of the 2nd)
-//                    is flagged and redone by the exact fp32 kernel (kernels_match.cu).
+//                    (FindMinCorr/FindMaxCorr).  A query whose list overflowed (> 8 entries per
+//                    split: massive near-ties) is flagged and redone by the exact fp32 kernel
+//                    (kernels_match.cu).
 //
 // fp16 inputs: descriptors are non-negative, <= 1, unit norm; rounding each element to
 // fp16 perturbs a dot product by < 128 * 2 * 2^-12 * (elementwise products) <= 6.1e-4 * dot.
@@ -152,21 +159,6 @@ __global__ void __launch_bounds__(256) k_pack_f16(const csb_sift_point *__restri
 }
 
 // ---- 2. tensor-core scan --------------------------------------------------------------
-// Sorted (descending) top-K insert.
-__device__ __forceinline__ void topk_insert(float (&tv)[TC_TOPK], int (&ti)[TC_TOPK], float v, int idx) {
-#pragma unroll
-  for (int k = 0; k < TC_TOPK; k++) {
-    if (v > tv[k]) {
-      const float fv = tv[k];
-      const int fi = ti[k];
-      tv[k] = v;
-      ti[k] = idx;
-      v = fv;
-      idx = fi;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__restrict__ q_packed, int nq_pad,
                                                             const __half *__restrict__ c_packed, int nc, int nc_pad,
                                                             int tiles_per_split, float *__restrict__ out_val,
@@ -222,15 +214,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
                    reinterpret_cast<const char *>(q_packed) + (size_t)kb * nq_pad * KHALF_BYTES_PER_ROW +
                        (size_t)(qtile * TC_QT + qh * 128) * KHALF_BYTES_PER_ROW,
                    A_HALF_BYTES, a_full);
-      for (int i = 0; i < n_tiles; i++) {
+      for (int i = 0; i < 2 * n_tiles; i++) {      // two sweeps over the candidate slice
         const int s = i % TC_STAGES;
         const uint32_t ph = (i / TC_STAGES) & 1;
+        const int tile = t0 + (i < n_tiles ? i : i - n_tiles);
         mbar_wait(b_empty + s, ph ^ 1);
         mbar_expect_tx(b_full + s, SMEM_B_STAGE);
         for (int kb = 0; kb < 2; kb++)
           bulk_g2s(sB + s * SMEM_B_STAGE + kb * B_HALF_BYTES,
                    reinterpret_cast<const char *>(c_packed) + (size_t)kb * nc_pad * KHALF_BYTES_PER_ROW +
-                       (size_t)(t0 + i) * TC_CT * KHALF_BYTES_PER_ROW,
+                       (size_t)tile * TC_CT * KHALF_BYTES_PER_ROW,
                    B_HALF_BYTES, b_full + s);
       }
     }
@@ -239,7 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
     if (lane == 0) {
       mbar_wait(a_full, 0);
       tc_fence_after();
-      for (int i = 0; i < n_tiles; i++) {
+      for (int i = 0; i < 2 * n_tiles; i++) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (i / TC_STAGES) & 1;
         mbar_wait(b_full + s, ph);
@@ -269,42 +262,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
     const int qh = ew >> 2;                  // query half (accumulator)
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = qh * 128 + quad * 32 + lane;
-    float tv[TC_TOPK];
-    int ti[TC_TOPK];
-#pragma unroll
-    for (int k = 0; k < TC_TOPK; k++) {
-      tv[k] = -1.0f;
-      ti[k] = -1;
-    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qh * TC_CT);
+    // ---- sweep 1: two largest approximate dot products of this row (padding columns hold 0) ----
+    float m1 = -1.0f, m2 = -1.0f;
     for (int i = 0; i < n_tiles; i++) {
       mbar_wait(acc_full + qh, i & 1);
       tc_fence_after();
-      const int col0 = (t0 + i) * TC_CT;
 #pragma unroll 1
       for (int ch = 0; ch < TC_CT / 32; ch++) {
         uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qh * TC_CT + ch * 32), r);
-        float m = __uint_as_float(r[0]);
+        tc_ld32(taddr + (uint32_t)(ch * 32), r);
 #pragma unroll
-        for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(r[j]));
-        if (m > tv[TC_TOPK - 1]) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const float v = __uint_as_float(r[j]);
-            const int cidx = col0 + ch * 32 + j;
-            if (v > tv[TC_TOPK - 1] && cidx < nc) topk_insert(tv, ti, v, cidx);
-          }
+        for (int j = 0; j < 32; j++) {
+          const float v = __uint_as_float(r[j]);
+          const float lo = fminf(m1, v);
+          m1 = fmaxf(m1, v);
+          m2 = fmaxf(m2, lo);
         }
       }
       tc_fence_before();
       mbar_arrive(acc_empty + qh);           // 128 arrivals free the accumulator
     }
+    // ---- sweep 2: list every candidate with approximate dot >= m2 - 2 eps ----
+    const float thr = m2 - 2.0f * TC_EPS;
+    int li[TC_TOPK];
+#pragma unroll
+    for (int k = 0; k < TC_TOPK; k++) li[k] = -1;
+    int cnt = 0;
+    for (int i = 0; i < n_tiles; i++) {
+      mbar_wait(acc_full + qh, (n_tiles + i) & 1);
+      tc_fence_after();
+      const int col0 = (t0 + i) * TC_CT;
+#pragma unroll 1
+      for (int ch = 0; ch < TC_CT / 32; ch++) {
+        uint32_t r[32];
+        tc_ld32(taddr + (uint32_t)(ch * 32), r);
+        float m = __uint_as_float(r[0]);
+#pragma unroll
+        for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(r[j]));
+        if (m >= thr) {                      // rare per lane
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int cidx = col0 + ch * 32 + j;
+            if (__uint_as_float(r[j]) >= thr && cidx < nc) {
+#pragma unroll
+              for (int k = 0; k < TC_TOPK; k++)
+                if (k == cnt) li[k] = cidx;
+              cnt++;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty + qh);
+    }
     const size_t o = ((size_t)(qtile * TC_QT + row) * n_splits + split) * TC_TOPK;
 #pragma unroll
-    for (int k = 0; k < TC_TOPK; k++) {
-      out_val[o + k] = tv[k];
-      out_idx[o + k] = ti[k];
-    }
+    for (int k = 0; k < TC_TOPK; k++) out_idx[o + k] = li[k];
+    out_val[(size_t)(qtile * TC_QT + row) * n_splits + split] = (float)cnt;   // entries found (may exceed TC_TOPK)
   }
 
   tc_fence_before();
@@ -327,29 +342,12 @@ __global__ void __launch_bounds__(128) k_rescore(csb_sift_point *__restrict__ s1
   if (warp >= n1) return;
   const int q = warp;
   const int n_list = n_splits * TC_TOPK;          // <= 32
-  float av = -2.0f;
   int ci = -1;
-  if (lane < n_list) {
-    av = sl_val[(size_t)q * n_list + lane];
-    ci = sl_idx[(size_t)q * n_list + lane];
-    if (ci < 0) av = -2.0f;
-  }
-  // proof obligation: every candidate NOT in the list has approximate dot <= U = max over splits of
-  // that split's 8th entry; the exact top two are listed if U + 2 eps < (2nd largest approximate dot)
-  float u = (lane < n_list && (lane % TC_TOPK) == TC_TOPK - 1) ? av : -2.0f;
-  float a1 = av;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
-    a1 = fmaxf(a1, __shfl_xor_sync(0xffffffffu, a1, o));
-  }
-  const unsigned int who = __ballot_sync(0xffffffffu, av == a1 && ci >= 0);
-  const int first = __ffs(who) - 1;
-  float a2 = (lane == first) ? -2.0f : av;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) a2 = fmaxf(a2, __shfl_xor_sync(0xffffffffu, a2, o));
-  const bool complete = (n2 <= n_list) || (u < -0.5f);   // every candidate is listed
-  const bool proven = complete || (u + 2.0f * TC_EPS < a2);
+  if (lane < n_list) ci = sl_idx[(size_t)q * n_list + lane];
+  // a split that found more candidates above its threshold than fit in its list: redo exactly
+  bool overflow = false;
+  if (lane < n_splits) overflow = sl_val[(size_t)q * n_splits + lane] > (float)TC_TOPK;
+  const bool proven = !__any_sync(0xffffffffu, overflow);
 
   // exact score in the reference's rotated k order (matching.cu:84-89), lane = one listed candidate
   float score = kL2 ? 999.0f : -1.0f;
