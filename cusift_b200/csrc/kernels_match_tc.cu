@@ -115,8 +115,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: 8-row x 128-byte atoms
 // (1024 B), consecutive atoms along M/N 1024 B apart (SBO); LBO unused for swizzled K-major.
@@ -264,24 +264,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
     const int row = qh * 128 + quad * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qh * TC_CT);
     // ---- sweep 1: two largest approximate dot products of this row (padding columns hold 0) ----
-    float m1 = -1.0f, m2 = -1.0f;
+    // four independent (max, second) pairs keep the min/max chains short; merged after the sweep
+    float p1[4], p2[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) p1[k] = p2[k] = -1.0f;
     for (int i = 0; i < n_tiles; i++) {
       mbar_wait(acc_full + qh, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < TC_CT / 32; ch++) {
-        uint32_t r[32];
-        tc_ld32(taddr + (uint32_t)(ch * 32), r);
+      for (int ch = 0; ch < TC_CT / 64; ch++) {
+        uint32_t r[32], q[32];
+        tc_ld32(taddr + (uint32_t)(ch * 64), r);
+        tc_ld32(taddr + (uint32_t)(ch * 64 + 32), q);
+        tc_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j++) {
           const float v = __uint_as_float(r[j]);
-          const float lo = fminf(m1, v);
-          m1 = fmaxf(m1, v);
-          m2 = fmaxf(m2, lo);
+          const float lo = fminf(p1[j & 3], v);
+          p1[j & 3] = fmaxf(p1[j & 3], v);
+          p2[j & 3] = fmaxf(p2[j & 3], lo);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const float v = __uint_as_float(q[j]);
+          const float lo = fminf(p1[j & 3], v);
+          p1[j & 3] = fmaxf(p1[j & 3], v);
+          p2[j & 3] = fmaxf(p2[j & 3], lo);
         }
       }
       tc_fence_before();
       mbar_arrive(acc_empty + qh);           // 128 arrivals free the accumulator
+    }
+    float m1 = p1[0], m2 = p2[0];
+#pragma unroll
+    for (int k = 1; k < 4; k++) {            // merge (m1,m2) with (p1[k],p2[k])
+      const float lo = fminf(m1, p1[k]);
+      m1 = fmaxf(m1, p1[k]);
+      m2 = fmaxf(fmaxf(m2, p2[k]), lo);
     }
     // ---- sweep 2: list every candidate with approximate dot >= m2 - 2 eps ----
     const float thr = m2 - 2.0f * TC_EPS;
@@ -294,17 +313,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
       tc_fence_after();
       const int col0 = (t0 + i) * TC_CT;
 #pragma unroll 1
-      for (int ch = 0; ch < TC_CT / 32; ch++) {
-        uint32_t r[32];
-        tc_ld32(taddr + (uint32_t)(ch * 32), r);
-        float m = __uint_as_float(r[0]);
+      for (int ch = 0; ch < TC_CT / 64; ch++) {
+        uint32_t r[32], q[32];
+        tc_ld32(taddr + (uint32_t)(ch * 64), r);
+        tc_ld32(taddr + (uint32_t)(ch * 64 + 32), q);
+        tc_ld_wait();
+        float ma = fmaxf(__uint_as_float(r[0]), __uint_as_float(q[0])), mb = fmaxf(__uint_as_float(r[1]), __uint_as_float(q[1]));
 #pragma unroll
-        for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(r[j]));
-        if (m >= thr) {                      // rare per lane
+        for (int j = 2; j < 32; j += 2) {
+          ma = fmaxf(fmaxf(ma, __uint_as_float(r[j])), __uint_as_float(q[j]));
+          mb = fmaxf(fmaxf(mb, __uint_as_float(r[j + 1])), __uint_as_float(q[j + 1]));
+        }
+        if (fmaxf(ma, mb) >= thr) {          // rare per lane
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const int cidx = col0 + ch * 32 + j;
-            if (__uint_as_float(r[j]) >= thr && cidx < nc) {
+          for (int j = 0; j < 64; j++) {
+            const int cidx = col0 + ch * 64 + j;
+            const float v = __uint_as_float(j < 32 ? r[j & 31] : q[j & 31]);
+            if (v >= thr && cidx < nc) {
 #pragma unroll
               for (int k = 0; k < TC_TOPK; k++)
                 if (k == cnt) li[k] = cidx;
