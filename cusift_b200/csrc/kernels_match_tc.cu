@@ -263,11 +263,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = qh * 128 + quad * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qh * TC_CT);
-    // ---- sweep 1: two largest approximate dot products of this row (padding columns hold 0) ----
-    // four independent (max, second) pairs keep the min/max chains short; merged after the sweep
-    float p1[4], p2[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) p1[k] = p2[k] = -1.0f;
+    // ---- sweep 1: m1 = largest approximate dot product of this row, m2 = second largest CHUNK maximum
+    // (chunks of 32 columns).  m2 <= the true second largest value, so thr = m2 - 2 eps is still a valid
+    // (slightly more inclusive) listing threshold, and a chunk costs 16 three-input max + 3 ops instead
+    // of 96 (FMNMX runs at half rate: this epilogue is ALU-pipe bound).  Padding columns hold 0.
+    float m1 = -1.0f, m2 = -1.0f;
     for (int i = 0; i < n_tiles; i++) {
       mbar_wait(acc_full + qh, i & 1);
       tc_fence_after();
@@ -277,30 +277,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
         tc_ld32(taddr + (uint32_t)(ch * 64), r);
         tc_ld32(taddr + (uint32_t)(ch * 64 + 32), q);
         tc_ld_wait();
+        float g[8];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const float v = __uint_as_float(r[j]);
-          const float lo = fminf(p1[j & 3], v);
-          p1[j & 3] = fmaxf(p1[j & 3], v);
-          p2[j & 3] = fmaxf(p2[j & 3], lo);
+        for (int k = 0; k < 4; k++) {
+          g[k] = fmaxf(fmaxf(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])), __uint_as_float(r[8 * k + 2]));
+          g[k] = fmaxf(fmaxf(g[k], __uint_as_float(r[8 * k + 3])), __uint_as_float(r[8 * k + 4]));
+          g[k] = fmaxf(fmaxf(g[k], __uint_as_float(r[8 * k + 5])), __uint_as_float(r[8 * k + 6]));
+          g[k] = fmaxf(g[k], __uint_as_float(r[8 * k + 7]));
+          g[4 + k] = fmaxf(fmaxf(__uint_as_float(q[8 * k]), __uint_as_float(q[8 * k + 1])), __uint_as_float(q[8 * k + 2]));
+          g[4 + k] = fmaxf(fmaxf(g[4 + k], __uint_as_float(q[8 * k + 3])), __uint_as_float(q[8 * k + 4]));
+          g[4 + k] = fmaxf(fmaxf(g[4 + k], __uint_as_float(q[8 * k + 5])), __uint_as_float(q[8 * k + 6]));
+          g[4 + k] = fmaxf(g[4 + k], __uint_as_float(q[8 * k + 7]));
         }
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const float v = __uint_as_float(q[j]);
-          const float lo = fminf(p1[j & 3], v);
-          p1[j & 3] = fmaxf(p1[j & 3], v);
-          p2[j & 3] = fmaxf(p2[j & 3], lo);
-        }
+        const float ca = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+        const float cb = fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]));
+        float lo = fminf(m1, ca);
+        m1 = fmaxf(m1, ca);
+        m2 = fmaxf(m2, lo);
+        lo = fminf(m1, cb);
+        m1 = fmaxf(m1, cb);
+        m2 = fmaxf(m2, lo);
       }
       tc_fence_before();
       mbar_arrive(acc_empty + qh);           // 128 arrivals free the accumulator
-    }
-    float m1 = p1[0], m2 = p2[0];
-#pragma unroll
-    for (int k = 1; k < 4; k++) {            // merge (m1,m2) with (p1[k],p2[k])
-      const float lo = fminf(m1, p1[k]);
-      m1 = fmaxf(m1, p1[k]);
-      m2 = fmaxf(fmaxf(m2, p2[k]), lo);
     }
     // ---- sweep 2: list every candidate with approximate dot >= m2 - 2 eps ----
     const float thr = m2 - 2.0f * TC_EPS;
@@ -313,27 +312,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
       tc_fence_after();
       const int col0 = (t0 + i) * TC_CT;
 #pragma unroll 1
-      for (int ch = 0; ch < TC_CT / 64; ch++) {
-        uint32_t r[32], q[32];
-        tc_ld32(taddr + (uint32_t)(ch * 64), r);
-        tc_ld32(taddr + (uint32_t)(ch * 64 + 32), q);
+      for (int ch = 0; ch < TC_CT / 32; ch++) {
+        uint32_t r[32];
+        tc_ld32(taddr + (uint32_t)(ch * 32), r);
         tc_ld_wait();
-        float ma = fmaxf(__uint_as_float(r[0]), __uint_as_float(q[0])), mb = fmaxf(__uint_as_float(r[1]), __uint_as_float(q[1]));
 #pragma unroll
-        for (int j = 2; j < 32; j += 2) {
-          ma = fmaxf(fmaxf(ma, __uint_as_float(r[j])), __uint_as_float(q[j]));
-          mb = fmaxf(fmaxf(mb, __uint_as_float(r[j + 1])), __uint_as_float(q[j + 1]));
-        }
-        if (fmaxf(ma, mb) >= thr) {          // rare per lane
+        for (int k = 0; k < 4; k++) {          // groups of 8 columns: the append path below is rare per group
+          float g = fmaxf(fmaxf(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])), __uint_as_float(r[8 * k + 2]));
+          g = fmaxf(fmaxf(g, __uint_as_float(r[8 * k + 3])), __uint_as_float(r[8 * k + 4]));
+          g = fmaxf(fmaxf(g, __uint_as_float(r[8 * k + 5])), __uint_as_float(r[8 * k + 6]));
+          g = fmaxf(g, __uint_as_float(r[8 * k + 7]));
+          if (g >= thr) {
 #pragma unroll
-          for (int j = 0; j < 64; j++) {
-            const int cidx = col0 + ch * 64 + j;
-            const float v = __uint_as_float(j < 32 ? r[j & 31] : q[j & 31]);
-            if (v >= thr && cidx < nc) {
+            for (int j = 0; j < 8; j++) {
+              const int cidx = col0 + ch * 32 + 8 * k + j;
+              if (__uint_as_float(r[8 * k + j]) >= thr && cidx < nc) {
 #pragma unroll
-              for (int k = 0; k < TC_TOPK; k++)
-                if (k == cnt) li[k] = cidx;
-              cnt++;
+                for (int kk = 0; kk < TC_TOPK; kk++)
+                  if (kk == cnt) li[kk] = cidx;
+                cnt++;
+              }
             }
           }
         }
