@@ -265,6 +265,46 @@ class Context:
         finally:
             self.free(d)
 
+    def allpairs(self, d_sifts, counts, pairs, distance="l2", num_loops=1024, min_score=0.0, max_ambiguity=0.80,
+                 thresh=5.0, seed=1, pair_ids=None):
+        """csb_allpairs_match_ransac over device SiftPoint arrays (raw pointers).  pairs: [(i, j)].
+        Returns (H [n_pairs, 9], inliers [n_pairs], n_valid [n_pairs])."""
+        n_sets, n_pairs = len(d_sifts), len(pairs)
+        ptrs = (C.c_void_p * n_sets)(*d_sifts)
+        cnts = np.ascontiguousarray(counts, np.int32)
+        pi = np.ascontiguousarray([p[0] for p in pairs], np.int32)
+        pj = np.ascontiguousarray([p[1] for p in pairs], np.int32)
+        ids = None if pair_ids is None else np.ascontiguousarray(pair_ids, np.uint32)
+        H = np.zeros((max(n_pairs, 1), 9), np.float32)
+        inl = np.zeros(max(n_pairs, 1), np.int32)
+        nv = np.zeros(max(n_pairs, 1), np.int32)
+        ip = C.POINTER(C.c_int)
+        self._check(self._L.csb_allpairs_match_ransac(
+            self.h, n_sets, ptrs, cnts.ctypes.data_as(ip), n_pairs, pi.ctypes.data_as(ip), pj.ctypes.data_as(ip),
+            None if ids is None else ids.ctypes.data_as(C.POINTER(C.c_uint)), 1 if distance == "l2" else 0, num_loops,
+            min_score, max_ambiguity, thresh, seed, H.ctypes.data_as(C.POINTER(C.c_float)), inl.ctypes.data_as(ip),
+            nv.ctypes.data_as(ip)), "csb_allpairs_match_ransac")
+        return H[:n_pairs], inl[:n_pairs], nv[:n_pairs]
+
+    def sample_points(self, valid: np.ndarray, num_loops: int, seed: int, pair_id: int) -> np.ndarray:
+        """Host restatement of the device sample generator (k_make_samples): int32 [4][num_loops]."""
+        nv = len(valid)
+        rp = np.zeros((4, num_loops), np.int32)
+        if nv < 8:
+            return rp
+        for l in range(num_loops):
+            picks = []
+            for k in range(4):
+                attempt = 0
+                while True:
+                    c = self._L.csb_sample_hash(seed, pair_id, l, k, attempt) % nv
+                    attempt += 1
+                    if c not in picks:
+                        picks.append(c)
+                        break
+            rp[:, l] = valid[picks]
+        return rp
+
     # ---- measurement ------------------------------------------------------
     def profile(self, on: bool):
         self._check(self._L.csb_profile_enable(self.h, int(on)), "csb_profile_enable")

@@ -809,6 +809,110 @@ int csb_find_homography(csb_ctx *ctx, const void *d_sift, int n, const int *h_ra
   return 0;
 }
 
+unsigned int csb_sample_hash(unsigned int seed, unsigned int pair, unsigned int loop, unsigned int k,
+                             unsigned int attempt) {
+  return csb_sample_hash_host(seed, pair, loop, k, attempt);
+}
+
+int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, const int *counts, int n_pairs,
+                              const int *pair_i, const int *pair_j, const unsigned int *pair_ids, int distance,
+                              int num_loops, float min_score, float max_ambiguity, float thresh, unsigned int seed,
+                              float *H_out, int *inliers_out, int *nvalid_out) {
+  if (!ctx || n_sets <= 0 || !d_sifts || !counts || n_pairs < 0 || !pair_i || !pair_j || !H_out || !inliers_out ||
+      !nvalid_out || num_loops <= 0 || (num_loops % 16) != 0 || (distance != 0 && distance != 1))
+    return fail(ctx, CSB_E_INVALID, "csb_allpairs_match_ransac: bad argument");
+  if (n_pairs == 0) return 0;
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  cudaStream_t st = s->stream;
+  int max_n = 0;
+  for (int i = 0; i < n_sets; i++) {
+    if (counts[i] < 0 || (counts[i] > 0 && !d_sifts[i])) return fail(ctx, CSB_E_INVALID, "csb_allpairs: bad set");
+    if (counts[i] > max_n) max_n = counts[i];
+  }
+  for (int k = 0; k < n_pairs; k++)
+    if (pair_i[k] < 0 || pair_i[k] >= n_sets || pair_j[k] < 0 || pair_j[k] >= n_sets)
+      return fail(ctx, CSB_E_INVALID, "csb_allpairs: pair index out of range");
+  // scratch (freed on return; this entry point is coarse-grained)
+  std::vector<void *> packed(n_sets, nullptr);
+  float *sl_val = nullptr, *d_coord = nullptr, *d_homo = nullptr, *d_H = nullptr;
+  int *sl_idx = nullptr, *flags = nullptr, *list = nullptr, *cnt = nullptr, *d_valid = nullptr, *d_nvalid = nullptr,
+      *d_rand = nullptr, *d_counts = nullptr, *d_inl = nullptr, *d_nv = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    for (void *p : packed) if (p) cudaFree(p);
+    cudaFree(sl_val); cudaFree(sl_idx); cudaFree(flags); cudaFree(list); cudaFree(cnt); cudaFree(d_valid);
+    cudaFree(d_nvalid); cudaFree(d_coord); cudaFree(d_rand); cudaFree(d_homo); cudaFree(d_counts); cudaFree(d_H);
+    cudaFree(d_inl); cudaFree(d_nv);
+  };
+#define AP_CHECK(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+      cleanup();                                                                            \
+      return (int)e_;                                                                       \
+    }                                                                                       \
+  } while (0)
+  const bool use_tc = !ctx->match_exact;
+  const int n_up = ((max_n + 15) / 16) * 16;
+  const size_t sl_need = (size_t)tc_pad(max_n > 0 ? max_n : 1) * 4 * 8;
+  AP_CHECK(cudaMalloc((void **)&sl_val, sizeof(float) * sl_need));
+  AP_CHECK(cudaMalloc((void **)&sl_idx, sizeof(int) * sl_need));
+  AP_CHECK(cudaMalloc((void **)&flags, sizeof(int) * ((size_t)max_n / 16 + 2)));
+  AP_CHECK(cudaMalloc((void **)&list, sizeof(int) * ((size_t)max_n / 16 + 2)));
+  AP_CHECK(cudaMalloc((void **)&cnt, 256));
+  AP_CHECK(cudaMalloc((void **)&d_valid, sizeof(int) * (size_t)(max_n + 1)));
+  AP_CHECK(cudaMalloc((void **)&d_nvalid, 256));
+  AP_CHECK(cudaMalloc((void **)&d_coord, sizeof(float) * 4 * (size_t)(n_up + 16)));
+  AP_CHECK(cudaMalloc((void **)&d_rand, sizeof(int) * 4 * (size_t)num_loops));
+  AP_CHECK(cudaMalloc((void **)&d_homo, sizeof(float) * 8 * (size_t)num_loops));
+  AP_CHECK(cudaMalloc((void **)&d_counts, sizeof(int) * (size_t)num_loops));
+  AP_CHECK(cudaMalloc((void **)&d_H, sizeof(float) * 9 * (size_t)n_pairs));
+  AP_CHECK(cudaMalloc((void **)&d_inl, sizeof(int) * (size_t)n_pairs));
+  AP_CHECK(cudaMalloc((void **)&d_nv, sizeof(int) * (size_t)n_pairs));
+  if (use_tc) {
+    for (int i = 0; i < n_sets; i++) {
+      if (counts[i] < 256) continue;
+      AP_CHECK(cudaMalloc(&packed[i], tc_packed_bytes(counts[i])));
+      launch_pack_f16((const csb_sift_point *)d_sifts[i], counts[i], packed[i], st);
+      ctx->launches++;
+    }
+  }
+  for (int k = 0; k < n_pairs; k++) {
+    const int i = pair_i[k], j = pair_j[k];
+    const int n1 = counts[i], n2 = counts[j];
+    csb_sift_point *s1 = (csb_sift_point *)d_sifts[i];
+    const csb_sift_point *s2 = (const csb_sift_point *)d_sifts[j];
+    if (n1 > 0 && n2 > 0) {
+      if (use_tc && n1 >= 256 && n2 >= 256) {
+        const int splits = tc_splits(n1, n2, ctx->sm_count);
+        launch_match_tc(packed[i], n1, packed[j], n2, splits, sl_val, sl_idx, st);
+        launch_rescore(s1, n1, s2, n2, sl_val, sl_idx, splits, distance, flags, list, cnt, st);
+        launch_match_blocks(s1, n1, s2, n2, distance, list, cnt, st);
+        ctx->launches += 4;
+      } else {
+        launch_match(s1, n1, s2, n2, distance, st);
+        ctx->launches += 1;
+      }
+    }
+    const int nu = ((n1 + 15) / 16) * 16;
+    launch_pair_ransac(s1, n1, nu > 0 ? nu : 16, min_score, max_ambiguity, d_valid, d_nvalid, d_coord, d_rand, d_homo,
+                       d_counts, num_loops, thresh * thresh, seed, pair_ids ? pair_ids[k] : (unsigned int)k,
+                       d_H + 9 * (size_t)k, d_inl + k, d_nv + k, st);
+    ctx->launches += 6;
+  }
+  AP_CHECK(cudaGetLastError());
+  AP_CHECK(cudaMemcpyAsync(H_out, d_H, sizeof(float) * 9 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  AP_CHECK(cudaMemcpyAsync(inliers_out, d_inl, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  AP_CHECK(cudaMemcpyAsync(nvalid_out, d_nv, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  AP_CHECK(cudaStreamSynchronize(st));
+#undef AP_CHECK
+  cleanup();
+  (void)rc;
+  return 0;
+}
+
 int csb_debug_octave(csb_ctx *ctx, int oct, float *h_base, float *h_dog, int *w, int *h) {
   if (!ctx) return CSB_E_INVALID;
   Slot *s = &ctx->slots[0];

@@ -61,4 +61,11 @@ void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2
 void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
                        int *d_counts, int num_loops, float thresh2, cudaStream_t st);
 
+void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min_score, float max_amb, int *d_valid,
+                        int *d_nvalid, float *d_coord, int *d_rand, float *d_homo, int *d_counts, int num_loops,
+                        float thresh2, unsigned int seed, unsigned int pair, float *H_out, int *inl_out, int *nvalid_out,
+                        cudaStream_t st);
+unsigned int csb_sample_hash_host(unsigned int seed, unsigned int pair, unsigned int loop, unsigned int k,
+                                  unsigned int attempt);
+
 #endif

@@ -155,7 +155,123 @@ __global__ void __launch_bounds__(256) k_score(const float *__restrict__ coord, 
   if (lane == 0) counts[warp] = cnt;
 }
 
+// ---- batched (all-pairs) RANSAC support: everything stays on the device ----------------------
+// Valid points (score > min_score && ambiguity < max_ambiguity, homography.cu:225-228) in increasing
+// index order, like the reference's validPts.  One CTA, ordered block scan.
+__global__ void __launch_bounds__(1024) k_valid_compact(const csb_sift_point *__restrict__ d_sift, int n, float min_score,
+                                                        float max_amb, int *__restrict__ valid, int *__restrict__ n_valid) {
+  __shared__ int warp_sums[32];
+  __shared__ int base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += 1024) {
+    const int i = start + threadIdx.x;
+    const bool ok = i < n && d_sift[i].score > min_score && d_sift[i].ambiguity < max_amb;
+    const unsigned int m = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) warp_sums[warp] = __popc(m);
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < warp; w++) off += warp_sums[w];
+    if (ok) valid[base + off + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; w++) tot += warp_sums[w];
+      base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_valid = base;
+}
+
+// Counter-based generator for the 4-point samples (the reference draws them with libc rand(),
+// homography.cu:232-244 — unseeded and continuing across calls, so no particular sequence is part
+// of its contract).  csb_sample_hash is restated in Python by the tests.
+__host__ __device__ inline unsigned int csb_hash5(unsigned int seed, unsigned int pair, unsigned int loop,
+                                                        unsigned int k, unsigned int attempt) {
+  unsigned int x = seed ^ (pair * 0x9E3779B9u) ^ (loop * 0x85EBCA6Bu) ^ (k * 0xC2B2AE35u) ^ (attempt * 0x27D4EB2Fu);
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+
+__global__ void k_make_samples(const int *__restrict__ valid, const int *__restrict__ n_valid, int num_loops,
+                               unsigned int seed, unsigned int pair, int *__restrict__ rand_pts) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= num_loops) return;
+  const int nv = *n_valid;
+  int p[4] = {0, 0, 0, 0};
+  if (nv >= 8) {
+    for (int k = 0; k < 4; k++) {
+      unsigned int attempt = 0;
+      for (;;) {
+        const int c = (int)(csb_hash5(seed, pair, (unsigned int)l, (unsigned int)k, attempt++) % (unsigned int)nv);
+        bool dup = false;
+        for (int q = 0; q < k; q++) dup = dup || (p[q] == c);
+        if (!dup) { p[k] = c; break; }
+      }
+    }
+    for (int k = 0; k < 4; k++) rand_pts[k * num_loops + l] = valid[p[k]];
+  } else {
+    for (int k = 0; k < 4; k++) rand_pts[k * num_loops + l] = 0;
+  }
+}
+
+// First-maximum hypothesis (homography.cu:259-264) -> result record {H[9], inliers, n_valid} on the device.
+__global__ void __launch_bounds__(256) k_pick_best(const int *__restrict__ counts, const float *__restrict__ homo,
+                                                   int num_loops, const int *__restrict__ n_valid, int n_pts,
+                                                   float *__restrict__ H_out, int *__restrict__ inl_out,
+                                                   int *__restrict__ nvalid_out) {
+  __shared__ int s_cnt[256], s_idx[256];
+  int best = -1, bidx = 0x7fffffff;
+  for (int i = threadIdx.x; i < num_loops; i += 256) {
+    const int c = counts[i];
+    if (c > best) { best = c; bidx = i; }
+  }
+  s_cnt[threadIdx.x] = best;
+  s_idx[threadIdx.x] = bidx;
+  __syncthreads();
+  for (int len = 128; len > 0; len >>= 1) {
+    if (threadIdx.x < len) {
+      const int oc = s_cnt[threadIdx.x + len], oi = s_idx[threadIdx.x + len];
+      if (oc > s_cnt[threadIdx.x] || (oc == s_cnt[threadIdx.x] && oi < s_idx[threadIdx.x])) {
+        s_cnt[threadIdx.x] = oc;
+        s_idx[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  const int nv = *n_valid;
+  const bool ok = nv >= 8 && n_pts >= 8;       // homography.cu:207,231: otherwise identity, 0 matches
+  if (threadIdx.x < 9) {
+    float v = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.0f : 0.0f;
+    if (ok && threadIdx.x < 8) v = homo[threadIdx.x * num_loops + s_idx[0]];
+    H_out[threadIdx.x] = v;
+  }
+  if (threadIdx.x == 0) {
+    *inl_out = ok ? s_cnt[0] : 0;
+    *nvalid_out = nv;
+  }
+}
+
 }  // namespace
+
+unsigned int csb_sample_hash_host(unsigned int seed, unsigned int pair, unsigned int loop, unsigned int k,
+                                  unsigned int attempt) {
+  return csb_hash5(seed, pair, loop, k, attempt);
+}
+
+void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min_score, float max_amb, int *d_valid,
+                        int *d_nvalid, float *d_coord, int *d_rand, float *d_homo, int *d_counts, int num_loops,
+                        float thresh2, unsigned int seed, unsigned int pair, float *H_out, int *inl_out, int *nvalid_out,
+                        cudaStream_t st) {
+  k_valid_compact<<<1, 1024, 0, st>>>(d_sift, n, min_score, max_amb, d_valid, d_nvalid);
+  k_make_samples<<<(num_loops + 127) / 128, 128, 0, st>>>(d_valid, d_nvalid, num_loops, seed, pair, d_rand);
+  k_gather_coords<<<(n_up + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord);
+  k_hypotheses<<<(num_loops + 63) / 64, 64, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
+  k_score<<<(num_loops * 32 + 255) / 256, 256, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
+  k_pick_best<<<1, 256, 0, st>>>(d_counts, d_homo, num_loops, d_nvalid, n, H_out, inl_out, nvalid_out);
+}
 
 void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
                        int *d_counts, int num_loops, float thresh2, cudaStream_t st) {

@@ -149,6 +149,23 @@ long long csb_match_redo_blocks(const csb_ctx *ctx);
 int csb_find_homography(csb_ctx *ctx, const void *d_sift, int n, const int *h_rand_pts, int num_loops,
                         float thresh, float *H9, int *num_inliers);
 
+/* ---- all-pairs matching + RANSAC (BASELINE config 5) -----------------------------------------
+ * For every listed pair (i, j): MatchSiftData(set_i, set_j, distance) — which, as in the reference,
+ * overwrites set_i's five match fields in place — followed by FindHomography(set_i, num_loops,
+ * min_score, max_ambiguity, thresh).  Everything stays on the device (descriptors are packed for the
+ * tensor cores once per set, samples come from the counter-based generator csb_sample_hash, the
+ * winning hypothesis is picked on the device); one synchronisation at the end.  Outputs, per pair:
+ * H[9], the winner's inlier count, and the number of valid points.  The reference has no batched
+ * entry point: a caller would loop over MatchSiftData + FindHomography (main.cpp:331-334).
+ * pair_ids (optional) are the indices fed to the sample generator (default: position in the list),
+ * so that a pair gets the same samples no matter which rank processes it. */
+int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, const int *counts, int n_pairs,
+                              const int *pair_i, const int *pair_j, const unsigned int *pair_ids, int distance,
+                              int num_loops, float min_score, float max_ambiguity, float thresh, unsigned int seed,
+                              float *H_out, int *inliers_out, int *nvalid_out);
+unsigned int csb_sample_hash(unsigned int seed, unsigned int pair, unsigned int loop, unsigned int k,
+                             unsigned int attempt);
+
 /* ---- debugging / measurement --------------------------------------------------
  * csb_debug_octave: after a csb_extract* call on slot 0, copies octave `oct`'s
  *   base image (dense w x h) and/or its 7 DoG planes (dense [7][h][w]) to host.

@@ -323,6 +323,54 @@ def test_match_ragged_sizes_ties_and_duplicates(gpu_ctx):
     assert csb.lib().csb_match(gpu_ctx.h, None, 0, None, 0, 1, None) == 0
 
 
+def _rand_set(n, seed):
+    r = np.random.default_rng(seed)
+    s = np.zeros(n, csb.SIFT_DTYPE)
+    d = np.abs(r.standard_normal((n, 128))).astype(np.float32)
+    s["data"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    s["coords2D"] = r.uniform(0, 1000, (n, 2)).astype(np.float32)
+    return s
+
+
+@pytest.mark.parametrize("n1,n2", [(256, 256), (300, 700), (1000, 3000), (257, 4097)])
+def test_match_tensor_core_path_bit_exact(gpu_ctx, n1, n2):
+    """Sets of >= 256 points go through the tcgen05 matcher (fp16 tensor-core scan, fp32 rescoring in
+    the reference's k order): still bit-identical to the oracle, incl. exact duplicates / ties."""
+    a, b = _rand_set(n1, n1), _rand_set(n2, n2 + 1)
+    b["data"][17] = b["data"][3]
+    b["data"][24] = b["data"][3]
+    a["data"][0] = b["data"][3]                              # three-way exact tie for query 0
+    b["data"][n2 - 1] = a["data"][7]
+    b["data"][100] = a["data"][7]                            # duplicate pair far apart (different tiles)
+    for dist in ("l2", "dot"):
+        ours, orc = gpu_ctx.match(a, b, dist), O.match(a, b, dist)
+        for f in ("score", "ambiguity", "match", "match_xpos", "match_ypos"):
+            assert np.array_equal(ours[f], orc[f]), (n1, n2, dist, f)
+
+
+def test_match_tensor_core_equals_cuda_core_path(frames):
+    """CSB_MATCH_EXACT=1 forces the fp32 CUDA-core kernel; both paths agree bit for bit on real descriptors."""
+    os.environ["CSB_MATCH_EXACT"] = "1"
+    try:
+        exact_ctx = csb.Context(0, 1)
+    finally:
+        os.environ.pop("CSB_MATCH_EXACT", None)
+    tc_ctx = csb.Context(0, 1)
+    try:
+        p = csb.make_params(5, 0.0, 0.3)
+        k1 = tc_ctx.extract(frames[0], p, max_pts=32768)
+        k2 = tc_ctx.extract(frames[1], p, max_pts=32768)
+        assert len(k1) > 2000 and len(k2) > 2000
+        m_tc, m_ex = tc_ctx.match(k1, k2, "l2"), exact_ctx.match(k1, k2, "l2")
+        for f in ("score", "ambiguity", "match", "match_xpos", "match_ypos"):
+            assert np.array_equal(m_tc[f], m_ex[f]), f
+        redo = csb.lib().csb_match_redo_blocks(tc_ctx.h)
+        assert redo <= (len(k1) + 15) // 16 // 4              # the exact redo path stays the exception
+    finally:
+        exact_ctx.close()
+        tc_ctx.close()
+
+
 def test_match_full_size_properties(gpu_ctx):
     """8192 x 8192 (BASELINE config 5 pair size): self-match is the identity with score ~0."""
     rng = np.random.default_rng(4)
@@ -386,3 +434,41 @@ def test_c1_pipeline_match_and_homography(gpu_ctx, frames, workdir):
             assert np.allclose(refh["H"], H, rtol=1e-3, atol=1e-5)
         H2, nfit, _ = O.improve_homography(m, H, 5, 0.0, 0.80, 3.0)
         assert nfit > 1500
+
+
+def test_allpairs_match_ransac_vs_oracle(gpu_ctx):
+    """BASELINE config 5 in miniature: every unordered pair of 5 keypoint sets, MatchSiftData +
+    FindHomography batched on the device; per pair the result equals the oracle's for the same samples."""
+    imgs = [csb.synth(640, 480, 3000 + i) for i in range(5)]
+    p = csb.make_params(5, 0.0, 0.5)
+    sets = []
+    for im in imgs:
+        k = gpu_ctx.extract(im, p, max_pts=8192)
+        order = np.lexsort((k["scale"], k["coords2D"][:, 1], k["coords2D"][:, 0], k["subsampling"]))   # canonical sort
+        sets.append(np.ascontiguousarray(k[order][:1536]))
+    assert all(len(s) == 1536 for s in sets)
+    dptrs = [gpu_ctx.upload_sift(s) for s in sets]
+    pairs = csb.all_pairs(len(sets))
+    loops, seed = 256, 7
+    try:
+        H, inl, nv = gpu_ctx.allpairs(dptrs, [len(s) for s in sets], pairs, "l2", loops, 0.0, 0.80, 5.0, seed)
+        for k, (i, j) in enumerate(pairs):
+            m = O.match(sets[i], sets[j], "l2")
+            valid = O.valid_points(m, 0.0, 0.80)
+            assert nv[k] == len(valid), (k, nv[k], len(valid))
+            rp = gpu_ctx.sample_points(valid, loops, seed, k)
+            Ho, cnto = O.find_homography(m, rp, 5.0)
+            assert inl[k] == cnto, (k, inl[k], cnto)
+            assert np.allclose(H[k], Ho, rtol=1e-3, atol=1e-5), (k, H[k], Ho)
+        # the last pair processed with query set i leaves its match fields in set i (as in the reference)
+        last = {}
+        for (i, j) in pairs:
+            last[i] = j
+        for i, j in last.items():
+            dev = gpu_ctx.download_sift(dptrs[i], len(sets[i]))
+            ref = O.match(sets[i], sets[j], "l2")
+            for f in ("score", "ambiguity", "match"):
+                assert np.array_equal(dev[f], ref[f]), (i, j, f)
+    finally:
+        for d in dptrs:
+            gpu_ctx.free(d)
