@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -87,6 +88,7 @@ struct csb_ctx {
   size_t tc_pack_cap[2] = {0, 0};
   float *tc_val = nullptr;
   int *tc_idx = nullptr, *tc_flags = nullptr, *tc_list = nullptr, *tc_count = nullptr;
+  void *tc_part = nullptr;
   size_t tc_sl_cap = 0, tc_blk_cap = 0;
   int *h_tc_count = nullptr;
   long long tc_redo_blocks = 0;      // 16-query blocks redone exactly (diagnostics)
@@ -95,6 +97,17 @@ struct csb_ctx {
   int *d_rand = nullptr, *d_counts = nullptr;
   size_t coord_cap = 0, loops_cap = 0;
   int *h_counts = nullptr;
+  // all-pairs scratch (grow-only, csb_allpairs_match_ransac)
+  static constexpr int AP_STREAMS = 4;
+  cudaStream_t ap_stream[AP_STREAMS] = {};
+  cudaEvent_t ap_done[AP_STREAMS] = {};
+  cudaEvent_t ap_packed = nullptr;
+  char *ap_scratch = nullptr;        // AP_STREAMS carve-ups of ap_scratch_stride bytes
+  size_t ap_scratch_cap = 0;
+  char *ap_pack = nullptr;           // fp16 operand tiles of all sets
+  size_t ap_pack_cap = 0;
+  char *ap_result = nullptr;         // per pair: H[9], inliers, n_valid
+  size_t ap_result_cap = 0;
 };
 
 namespace {
@@ -508,6 +521,15 @@ void csb_ctx_destroy(csb_ctx *ctx) {
   if (ctx->tc_idx) cudaFree(ctx->tc_idx);
   if (ctx->tc_flags) cudaFree(ctx->tc_flags);
   if (ctx->tc_list) cudaFree(ctx->tc_list);
+  if (ctx->tc_part) cudaFree(ctx->tc_part);
+  for (int t = 0; t < csb_ctx::AP_STREAMS; t++) {
+    if (ctx->ap_stream[t]) cudaStreamDestroy(ctx->ap_stream[t]);
+    if (ctx->ap_done[t]) cudaEventDestroy(ctx->ap_done[t]);
+  }
+  if (ctx->ap_packed) cudaEventDestroy(ctx->ap_packed);
+  if (ctx->ap_scratch) cudaFree(ctx->ap_scratch);
+  if (ctx->ap_pack) cudaFree(ctx->ap_pack);
+  if (ctx->ap_result) cudaFree(ctx->ap_result);
   if (ctx->tc_count) cudaFree(ctx->tc_count);
   if (ctx->h_tc_count) cudaFreeHost(ctx->h_tc_count);
   if (ctx->d_coord) cudaFree(ctx->d_coord);
@@ -707,7 +729,9 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
     if (ctx->tc_blk_cap < blk_need) {
       if (ctx->tc_flags) cudaFree(ctx->tc_flags);
       if (ctx->tc_list) cudaFree(ctx->tc_list);
-      ctx->tc_flags = nullptr; ctx->tc_list = nullptr;
+      if (ctx->tc_part) cudaFree(ctx->tc_part);
+      ctx->tc_flags = nullptr; ctx->tc_list = nullptr; ctx->tc_part = nullptr;
+      CSB_CHECK(ctx, cudaMalloc(&ctx->tc_part, match_redo_scratch_bytes((int)blk_need)));
       CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_flags, sizeof(int) * blk_need));
       CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_list, sizeof(int) * blk_need));
       ctx->tc_blk_cap = blk_need;
@@ -734,8 +758,9 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
     }
     {
       LaunchScope ls(ctx, s, "match_redo");
+      ctx->launches += 1;
       launch_match_blocks((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, distance, ctx->tc_list,
-                          ctx->tc_count, s->stream);
+                          ctx->tc_count, (int)blk_need, ctx->tc_part, s->stream);
     }
     CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_tc_count, ctx->tc_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   }
@@ -833,83 +858,125 @@ int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, co
   for (int k = 0; k < n_pairs; k++)
     if (pair_i[k] < 0 || pair_i[k] >= n_sets || pair_j[k] < 0 || pair_j[k] >= n_sets)
       return fail(ctx, CSB_E_INVALID, "csb_allpairs: pair index out of range");
-  // scratch (freed on return; this entry point is coarse-grained)
-  std::vector<void *> packed(n_sets, nullptr);
-  float *sl_val = nullptr, *d_coord = nullptr, *d_homo = nullptr, *d_H = nullptr;
-  int *sl_idx = nullptr, *flags = nullptr, *list = nullptr, *cnt = nullptr, *d_valid = nullptr, *d_nvalid = nullptr,
-      *d_rand = nullptr, *d_counts = nullptr, *d_inl = nullptr, *d_nv = nullptr;
-  int rc = 0;
-  auto cleanup = [&]() {
-    for (void *p : packed) if (p) cudaFree(p);
-    cudaFree(sl_val); cudaFree(sl_idx); cudaFree(flags); cudaFree(list); cudaFree(cnt); cudaFree(d_valid);
-    cudaFree(d_nvalid); cudaFree(d_coord); cudaFree(d_rand); cudaFree(d_homo); cudaFree(d_counts); cudaFree(d_H);
-    cudaFree(d_inl); cudaFree(d_nv);
-  };
-#define AP_CHECK(call)                                                                      \
-  do {                                                                                      \
-    cudaError_t e_ = (call);                                                                \
-    if (e_ != cudaSuccess) {                                                                \
-      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
-      cleanup();                                                                            \
-      return (int)e_;                                                                       \
-    }                                                                                       \
-  } while (0)
+  // Pairs run round-robin on AP_STREAMS streams so that the small RANSAC kernels of one pair overlap
+  // the tensor-core scan of the next.  Pairs that share the query set i write the same match fields,
+  // so stream = i % n_streams keeps them in issue order.  Scratch lives in the context and only grows
+  // (cudaMalloc/cudaFree cost more than a whole pair).
+  constexpr int AP_STREAMS = csb_ctx::AP_STREAMS;
+  const bool trace = getenv("CSB_AP_TRACE") != nullptr;
+  auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now_ms();
+  struct Scratch {
+    float *sl_val, *d_coord, *d_homo;
+    int *sl_idx, *flags, *list, *cnt, *d_valid, *d_nvalid, *d_rand, *d_counts;
+    void *part;
+    cudaStream_t st;
+  } sc[AP_STREAMS];
   const bool use_tc = !ctx->match_exact;
   const int n_up = ((max_n + 15) / 16) * 16;
-  const size_t sl_need = (size_t)tc_pad(max_n > 0 ? max_n : 1) * 4 * 8;
-  AP_CHECK(cudaMalloc((void **)&sl_val, sizeof(float) * sl_need));
-  AP_CHECK(cudaMalloc((void **)&sl_idx, sizeof(int) * sl_need));
-  AP_CHECK(cudaMalloc((void **)&flags, sizeof(int) * ((size_t)max_n / 16 + 2)));
-  AP_CHECK(cudaMalloc((void **)&list, sizeof(int) * ((size_t)max_n / 16 + 2)));
-  AP_CHECK(cudaMalloc((void **)&cnt, 256));
-  AP_CHECK(cudaMalloc((void **)&d_valid, sizeof(int) * (size_t)(max_n + 1)));
-  AP_CHECK(cudaMalloc((void **)&d_nvalid, 256));
-  AP_CHECK(cudaMalloc((void **)&d_coord, sizeof(float) * 4 * (size_t)(n_up + 16)));
-  AP_CHECK(cudaMalloc((void **)&d_rand, sizeof(int) * 4 * (size_t)num_loops));
-  AP_CHECK(cudaMalloc((void **)&d_homo, sizeof(float) * 8 * (size_t)num_loops));
-  AP_CHECK(cudaMalloc((void **)&d_counts, sizeof(int) * (size_t)num_loops));
-  AP_CHECK(cudaMalloc((void **)&d_H, sizeof(float) * 9 * (size_t)n_pairs));
-  AP_CHECK(cudaMalloc((void **)&d_inl, sizeof(int) * (size_t)n_pairs));
-  AP_CHECK(cudaMalloc((void **)&d_nv, sizeof(int) * (size_t)n_pairs));
+  int n_streams = AP_STREAMS;
+  if (const char *e = getenv("CSB_AP_STREAMS")) n_streams = atoi(e) < 1 ? 1 : (atoi(e) > AP_STREAMS ? AP_STREAMS : atoi(e));
+  if (n_pairs < n_streams) n_streams = n_pairs;
+  if (!ctx->ap_packed) {
+    for (int t = 0; t < AP_STREAMS; t++) {
+      CSB_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->ap_stream[t], cudaStreamNonBlocking));
+      CSB_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ap_done[t], cudaEventDisableTiming));
+    }
+    CSB_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ap_packed, cudaEventDisableTiming));
+  }
+  {
+    const size_t sl_need = (size_t)tc_pad(max_n > 0 ? max_n : 1) * 4 * 8;
+    const size_t nblk = (size_t)max_n / 16 + 2;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_slv = carve(4 * sl_need), o_sli = carve(4 * sl_need), o_flags = carve(4 * nblk), o_list = carve(4 * nblk),
+                 o_cnt = carve(256), o_part = carve(match_redo_scratch_bytes((int)nblk)), o_valid = carve(4 * (size_t)(max_n + 1)),
+                 o_nvalid = carve(256), o_coord = carve(16 * (size_t)(n_up + 16)), o_rand = carve(16 * (size_t)num_loops),
+                 o_homo = carve(32 * (size_t)num_loops), o_counts = carve(4 * (size_t)num_loops);
+    if (ctx->ap_scratch_cap < off * AP_STREAMS) {
+      if (ctx->ap_scratch) cudaFree(ctx->ap_scratch);
+      ctx->ap_scratch = nullptr; ctx->ap_scratch_cap = 0;
+      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ap_scratch, off * AP_STREAMS));
+      ctx->ap_scratch_cap = off * AP_STREAMS;
+    }
+    for (int t = 0; t < AP_STREAMS; t++) {
+      Scratch &c = sc[t];
+      char *base = ctx->ap_scratch + off * t;
+      c.sl_val = (float *)(base + o_slv); c.sl_idx = (int *)(base + o_sli); c.flags = (int *)(base + o_flags);
+      c.list = (int *)(base + o_list); c.cnt = (int *)(base + o_cnt); c.part = base + o_part;
+      c.d_valid = (int *)(base + o_valid); c.d_nvalid = (int *)(base + o_nvalid); c.d_coord = (float *)(base + o_coord);
+      c.d_rand = (int *)(base + o_rand); c.d_homo = (float *)(base + o_homo); c.d_counts = (int *)(base + o_counts);
+      c.st = ctx->ap_stream[t];
+    }
+  }
+  const size_t res_need = (size_t)n_pairs * 11 * 4;
+  if (ctx->ap_result_cap < res_need) {
+    if (ctx->ap_result) cudaFree(ctx->ap_result);
+    ctx->ap_result = nullptr; ctx->ap_result_cap = 0;
+    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ap_result, res_need));
+    ctx->ap_result_cap = res_need;
+  }
+  float *d_H = (float *)ctx->ap_result;
+  int *d_inl = (int *)(ctx->ap_result + (size_t)n_pairs * 36), *d_nv = d_inl + n_pairs;
+  std::vector<void *> packed(n_sets, nullptr);
   if (use_tc) {
+    size_t need = 0;
+    for (int i = 0; i < n_sets; i++) if (counts[i] >= 256) need += (tc_packed_bytes(counts[i]) + 1023) & ~(size_t)1023;
+    if (ctx->ap_pack_cap < need) {
+      if (ctx->ap_pack) cudaFree(ctx->ap_pack);
+      ctx->ap_pack = nullptr; ctx->ap_pack_cap = 0;
+      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ap_pack, need));
+      ctx->ap_pack_cap = need;
+    }
+    size_t off = 0;
     for (int i = 0; i < n_sets; i++) {
       if (counts[i] < 256) continue;
-      AP_CHECK(cudaMalloc(&packed[i], tc_packed_bytes(counts[i])));
+      packed[i] = ctx->ap_pack + off;
+      off += (tc_packed_bytes(counts[i]) + 1023) & ~(size_t)1023;
       launch_pack_f16((const csb_sift_point *)d_sifts[i], counts[i], packed[i], st);
       ctx->launches++;
     }
   }
+  CSB_CHECK(ctx, cudaEventRecord(ctx->ap_packed, st));
+  for (int t = 0; t < n_streams; t++) CSB_CHECK(ctx, cudaStreamWaitEvent(sc[t].st, ctx->ap_packed, 0));
+  const double t_alloc = now_ms();
   for (int k = 0; k < n_pairs; k++) {
     const int i = pair_i[k], j = pair_j[k];
     const int n1 = counts[i], n2 = counts[j];
+    Scratch &c = sc[i % n_streams];
     csb_sift_point *s1 = (csb_sift_point *)d_sifts[i];
     const csb_sift_point *s2 = (const csb_sift_point *)d_sifts[j];
     if (n1 > 0 && n2 > 0) {
       if (use_tc && n1 >= 256 && n2 >= 256) {
         const int splits = tc_splits(n1, n2, ctx->sm_count);
-        launch_match_tc(packed[i], n1, packed[j], n2, splits, sl_val, sl_idx, st);
-        launch_rescore(s1, n1, s2, n2, sl_val, sl_idx, splits, distance, flags, list, cnt, st);
-        launch_match_blocks(s1, n1, s2, n2, distance, list, cnt, st);
-        ctx->launches += 4;
+        launch_match_tc(packed[i], n1, packed[j], n2, splits, c.sl_val, c.sl_idx, c.st);
+        launch_rescore(s1, n1, s2, n2, c.sl_val, c.sl_idx, splits, distance, c.flags, c.list, c.cnt, c.st);
+        launch_match_blocks(s1, n1, s2, n2, distance, c.list, c.cnt, (n1 + 15) / 16, c.part, c.st);
+        ctx->launches += 5;
       } else {
-        launch_match(s1, n1, s2, n2, distance, st);
+        launch_match(s1, n1, s2, n2, distance, c.st);
         ctx->launches += 1;
       }
     }
     const int nu = ((n1 + 15) / 16) * 16;
-    launch_pair_ransac(s1, n1, nu > 0 ? nu : 16, min_score, max_ambiguity, d_valid, d_nvalid, d_coord, d_rand, d_homo,
-                       d_counts, num_loops, thresh * thresh, seed, pair_ids ? pair_ids[k] : (unsigned int)k,
-                       d_H + 9 * (size_t)k, d_inl + k, d_nv + k, st);
+    launch_pair_ransac(s1, n1, nu > 0 ? nu : 16, min_score, max_ambiguity, c.d_valid, c.d_nvalid, c.d_coord, c.d_rand,
+                       c.d_homo, c.d_counts, num_loops, thresh * thresh, seed, pair_ids ? pair_ids[k] : (unsigned int)k,
+                       d_H + 9 * (size_t)k, d_inl + k, d_nv + k, c.st);
     ctx->launches += 6;
   }
-  AP_CHECK(cudaGetLastError());
-  AP_CHECK(cudaMemcpyAsync(H_out, d_H, sizeof(float) * 9 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
-  AP_CHECK(cudaMemcpyAsync(inliers_out, d_inl, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
-  AP_CHECK(cudaMemcpyAsync(nvalid_out, d_nv, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
-  AP_CHECK(cudaStreamSynchronize(st));
-#undef AP_CHECK
-  cleanup();
-  (void)rc;
+  CSB_CHECK(ctx, cudaGetLastError());
+  for (int t = 0; t < n_streams; t++) {
+    CSB_CHECK(ctx, cudaEventRecord(ctx->ap_done[t], sc[t].st));
+    CSB_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ap_done[t], 0));
+  }
+  CSB_CHECK(ctx, cudaMemcpyAsync(H_out, d_H, sizeof(float) * 9 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  CSB_CHECK(ctx, cudaMemcpyAsync(inliers_out, d_inl, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  CSB_CHECK(ctx, cudaMemcpyAsync(nvalid_out, d_nv, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  const double t_issue = now_ms();
+  CSB_CHECK(ctx, cudaStreamSynchronize(st));
+  if (trace)
+    fprintf(stderr, "[csb allpairs] %d pairs on %d streams: prepare+pack %.2f ms, issue %.2f ms, drain %.2f ms\n", n_pairs,
+            n_streams, t_alloc - t_begin, t_issue - t_alloc, now_ms() - t_issue);
   return 0;
 }
 

@@ -47,8 +47,10 @@ void launch_copy_out(const csb_sift_point *d_sift, const unsigned int *d_counter
                      int *h_count_mapped, int sm_count, cudaStream_t st);
 void launch_match(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
                   cudaStream_t st);
+#define CSB_REDO_SLICES 32
+size_t match_redo_scratch_bytes(int max_blocks);
 void launch_match_blocks(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
-                         const int *block_list, const int *block_count, cudaStream_t st);
+                         const int *block_list, const int *block_count, int max_blocks, void *part, cudaStream_t st);
 // tensor-core matcher (kernels_match_tc.cu)
 size_t tc_packed_bytes(int n);
 int tc_pad(int n);

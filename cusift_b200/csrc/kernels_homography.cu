@@ -14,8 +14,10 @@
 
 namespace {
 
-__global__ void k_gather_coords(const csb_sift_point *__restrict__ d_sift, int n, int n_up, float *__restrict__ coord) {
+__global__ void k_gather_coords(const csb_sift_point *__restrict__ d_sift, int n, int n_up, float *__restrict__ coord,
+                                int *__restrict__ counts, int num_loops) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < num_loops) counts[i] = 0;             // k_score accumulates with atomicAdd
   if (i >= n_up) return;
   float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
   if (i < n) {
@@ -130,17 +132,31 @@ __global__ void __launch_bounds__(64) k_hypotheses(const float *__restrict__ coo
   }
 }
 
-__global__ void __launch_bounds__(256) k_score(const float *__restrict__ coord, const float *__restrict__ homo,
-                                               int *__restrict__ counts, int numPts, int numLoops, float thresh2) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= numLoops) return;
+// TestHomographies (homography.cu:139-192): inliers of every hypothesis over ALL numPts points.
+// Thread = one hypothesis (its 8 coefficients in registers), CTA = 128 hypotheses x a slice of
+// SCORE_PTS points read from shared memory as broadcasts; the integer partial counts are summed
+// with atomicAdd, so the result does not depend on the slicing.
+#define SCORE_HYP 128
+#define SCORE_PTS 256
+__global__ void __launch_bounds__(SCORE_HYP) k_score(const float *__restrict__ coord, const float *__restrict__ homo,
+                                                     int *__restrict__ counts, int numPts, int numLoops, float thresh2) {
+  __shared__ float4 pts[SCORE_PTS];
+  const int p0 = blockIdx.y * SCORE_PTS;
+  const int np = min(SCORE_PTS, numPts - p0);
+  for (int i = threadIdx.x; i < np; i += SCORE_HYP)
+    pts[i] = make_float4(coord[p0 + i + 0 * numPts], coord[p0 + i + 1 * numPts], coord[p0 + i + 2 * numPts],
+                         coord[p0 + i + 3 * numPts]);
+  __syncthreads();
+  const int loop = blockIdx.x * SCORE_HYP + threadIdx.x;
+  if (loop >= numLoops) return;
   float a[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) a[i] = homo[warp + i * numLoops];
+  for (int i = 0; i < 8; i++) a[i] = homo[loop + i * numLoops];
   int cnt = 0;
-  for (int i = lane; i < numPts; i += 32) {
-    const float x1 = coord[i + 0 * numPts], y1 = coord[i + 1 * numPts];
-    const float x2 = coord[i + 2 * numPts], y2 = coord[i + 3 * numPts];
+#pragma unroll 4
+  for (int i = 0; i < np; i++) {
+    const float4 p = pts[i];
+    const float x1 = p.x, y1 = p.y, x2 = p.z, y2 = p.w;
     // homography.cu:165-171, every product rounded toward zero
     const float nomx = __fadd_rn(__fadd_rn(__fmul_rz(a[0], x1), __fmul_rz(a[1], y1)), a[2]);
     const float nomy = __fadd_rn(__fadd_rn(__fmul_rz(a[3], x1), __fmul_rz(a[4], y1)), a[5]);
@@ -150,9 +166,7 @@ __global__ void __launch_bounds__(256) k_score(const float *__restrict__ coord, 
     const float err2 = __fadd_rn(__fmul_rz(errx, errx), __fmul_rz(erry, erry));
     if (err2 < __fmul_rz(thresh2, __fmul_rz(deno, deno))) cnt++;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) counts[warp] = cnt;
+  if (cnt) atomicAdd(counts + loop, cnt);
 }
 
 // ---- batched (all-pairs) RANSAC support: everything stays on the device ----------------------
@@ -161,28 +175,44 @@ __global__ void __launch_bounds__(256) k_score(const float *__restrict__ coord, 
 __global__ void __launch_bounds__(1024) k_valid_compact(const csb_sift_point *__restrict__ d_sift, int n, float min_score,
                                                         float max_amb, int *__restrict__ valid, int *__restrict__ n_valid) {
   __shared__ int warp_sums[32];
-  __shared__ int base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base = 0;
-  __syncthreads();
-  for (int start = 0; start < n; start += 1024) {
-    const int i = start + threadIdx.x;
-    const bool ok = i < n && d_sift[i].score > min_score && d_sift[i].ambiguity < max_amb;
-    const unsigned int m = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) warp_sums[warp] = __popc(m);
-    __syncthreads();
-    int off = 0;
-    for (int w = 0; w < warp; w++) off += warp_sums[w];
-    if (ok) valid[base + off + __popc(m & ((1u << lane) - 1u))] = i;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int w = 0; w < 32; w++) tot += warp_sums[w];
-      base += tot;
+  // thread t owns the contiguous range [t*ipt, (t+1)*ipt): one block-wide exclusive scan orders everything
+  const int ipt = (n + 1023) / 1024;
+  const int i0 = threadIdx.x * ipt, i1 = min(n, i0 + ipt);
+  unsigned int mask = 0;
+  int cnt = 0;
+  for (int i = i0; i < i1; i++) {
+    const bool ok = d_sift[i].score > min_score && d_sift[i].ambiguity < max_amb;
+    if (ok) {
+      if (i - i0 < 32) mask |= 1u << (i - i0);
+      cnt++;
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) *n_valid = base;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    warp_sums[lane] = w;                       // inclusive over warps
+  }
+  __syncthreads();
+  int pos = incl - cnt + (warp > 0 ? warp_sums[warp - 1] : 0);
+  for (int i = i0; i < i1; i++) {
+    const bool ok = (i - i0 < 32) ? ((mask >> (i - i0)) & 1u) != 0
+                                  : (d_sift[i].score > min_score && d_sift[i].ambiguity < max_amb);
+    if (ok) valid[pos++] = i;
+  }
+  if (threadIdx.x == 0) *n_valid = warp_sums[31];
 }
 
 // Counter-based generator for the 4-point samples (the reference draws them with libc rand(),
@@ -267,15 +297,15 @@ void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min
                         cudaStream_t st) {
   k_valid_compact<<<1, 1024, 0, st>>>(d_sift, n, min_score, max_amb, d_valid, d_nvalid);
   k_make_samples<<<(num_loops + 127) / 128, 128, 0, st>>>(d_valid, d_nvalid, num_loops, seed, pair, d_rand);
-  k_gather_coords<<<(n_up + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord);
+  k_gather_coords<<<((n_up > num_loops ? n_up : num_loops) + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord, d_counts, num_loops);
   k_hypotheses<<<(num_loops + 63) / 64, 64, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
-  k_score<<<(num_loops * 32 + 255) / 256, 256, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
+  k_score<<<dim3((num_loops + SCORE_HYP - 1) / SCORE_HYP, (n_up + SCORE_PTS - 1) / SCORE_PTS), SCORE_HYP, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
   k_pick_best<<<1, 256, 0, st>>>(d_counts, d_homo, num_loops, d_nvalid, n, H_out, inl_out, nvalid_out);
 }
 
 void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
                        int *d_counts, int num_loops, float thresh2, cudaStream_t st) {
-  k_gather_coords<<<(n_up + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord);
+  k_gather_coords<<<((n_up > num_loops ? n_up : num_loops) + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord, d_counts, num_loops);
   k_hypotheses<<<(num_loops + 63) / 64, 64, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
-  k_score<<<(num_loops * 32 + 255) / 256, 256, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
+  k_score<<<dim3((num_loops + SCORE_HYP - 1) / SCORE_HYP, (n_up + SCORE_PTS - 1) / SCORE_PTS), SCORE_HYP, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
 }

@@ -22,17 +22,45 @@ __device__ __forceinline__ bool better(float a, float b) {
   return kL2 ? (a < b) : (a > b);
 }
 
+// score / ambiguity / match / match_xpos / match_ypos of one query (matching.cu:236-246, 352-356)
 template <bool kL2>
+__device__ __forceinline__ void write_match(csb_sift_point *o, const csb_sift_point *__restrict__ s2, float best,
+                                            float second, int idx) {
+  o->score = best;
+  if (kL2) o->ambiguity = (float)((double)best / ((double)second + 1e-6));
+  else o->ambiguity = (float)((double)__fsub_rn(1.0f, best) / ((double)__fsub_rn(1.0f, second) + 1e-6));
+  o->match = idx;
+  if (idx >= 0) {
+    o->match_xpos = s2[idx].coords2D[0];
+    o->match_ypos = s2[idx].coords2D[1];
+  }
+}
+
+// kPartial: redo pass of the tensor-core matcher.  CTA (x, y) scores the x-th listed block of 16
+// queries against candidate chunks [y*cps, (y+1)*cps) and stores the slice's (best, second, argbest)
+// in part[]; k_match_finish merges the slices.  FindMinCorr's winner is the minimum of the total order
+// (score, bitrev4(col % 16), col / 16) and its runner-up the best of the remaining scores, so the
+// merge over slices gives the same result as the one long scan.
+struct MatchPart {
+  float best, second;
+  int idx;
+};
+
+template <bool kL2, bool kPartial>
 __global__ void __launch_bounds__(256) k_match(csb_sift_point *__restrict__ s1, int n1,
                                                const csb_sift_point *__restrict__ s2, int n2, int chunks,
-                                               const int *__restrict__ block_list, const int *__restrict__ block_count) {
+                                               const int *__restrict__ block_list, const int *__restrict__ block_count,
+                                               int cps, MatchPart *__restrict__ part) {
   __shared__ float A[16][128];
   __shared__ float B[16][128];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  // optional indirection: only the listed blocks of 16 queries (redo pass of the tensor-core matcher)
-  if (block_list != nullptr && (int)blockIdx.x >= *block_count) return;
-  const int qb = block_list != nullptr ? block_list[blockIdx.x] : (int)blockIdx.x;
+  const int n_blk = kPartial ? *block_count : (int)gridDim.x;
+  for (int bi = blockIdx.x; bi < n_blk; bi += gridDim.x) {
+  const int qb = kPartial ? block_list[bi] : bi;
+  const int c_begin = kPartial ? (int)blockIdx.y * cps : 0;
+  const int c_end = kPartial ? min(chunks, c_begin + cps) : chunks;
 
+  if (kPartial) __syncthreads();   // A is rewritten per listed block
   {
     const float *ptr1 = s1[min(n1 - 1, qb * 16 + ty)].data;
 #pragma unroll
@@ -42,14 +70,22 @@ __global__ void __launch_bounds__(256) k_match(csb_sift_point *__restrict__ s1, 
   float best = init, second = init;
   int idx = -1;
 
-  for (int c = 0; c < chunks; c++) {
-    __syncthreads();
-    {
-      const float *ptr2 = s2[min(n2 - 1, c * 16 + ty)].data;
+  float pre[8];                                   // next chunk of candidates, in flight during the dot products
+  if (c_begin < c_end) {
+    const float *ptr2 = s2[min(n2 - 1, c_begin * 16 + ty)].data;
 #pragma unroll
-      for (int i = 0; i < 8; i++) B[ty][16 * i + tx] = ptr2[16 * i + tx];
-    }
+    for (int i = 0; i < 8; i++) pre[i] = ptr2[16 * i + tx];
+  }
+  for (int c = c_begin; c < c_end; c++) {
     __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; i++) B[ty][16 * i + tx] = pre[i];
+    __syncthreads();
+    if (c + 1 < c_end) {
+      const float *ptr2 = s2[min(n2 - 1, (c + 1) * 16 + ty)].data;
+#pragma unroll
+      for (int i = 0; i < 8; i++) pre[i] = ptr2[16 * i + tx];
+    }
     float sum = 0.0f;
 #pragma unroll 16
     for (int i = 0; i < 128; i++) {
@@ -85,17 +121,50 @@ __global__ void __launch_bounds__(256) k_match(csb_sift_point *__restrict__ s1, 
   }
 
   const int p1 = qb * 16 + ty;
-  if (tx == 0 && p1 < n1) {
-    csb_sift_point *o = s1 + p1;
-    o->score = best;
-    if (kL2) o->ambiguity = (float)((double)best / ((double)second + 1e-6));
-    else o->ambiguity = (float)((double)__fsub_rn(1.0f, best) / ((double)__fsub_rn(1.0f, second) + 1e-6));
-    o->match = idx;
-    if (idx >= 0) {
-      o->match_xpos = s2[idx].coords2D[0];
-      o->match_ypos = s2[idx].coords2D[1];
-    }
+  if (kPartial) {
+    if (tx == 0) part[((size_t)bi * gridDim.y + blockIdx.y) * 16 + ty] = MatchPart{best, second, idx};
+  } else if (tx == 0 && p1 < n1) {
+    write_match<kL2>(s1 + p1, s2, best, second, idx);
   }
+  }
+}
+
+__device__ __forceinline__ int bitrev4(int x) { return ((x & 1) << 3) | ((x & 2) << 1) | ((x & 4) >> 1) | ((x & 8) >> 3); }
+
+// Merges the candidate slices of the redo pass: thread = one query of one listed block.
+template <bool kL2>
+__global__ void k_match_finish(csb_sift_point *__restrict__ s1, int n1, const csb_sift_point *__restrict__ s2,
+                               const int *__restrict__ block_list, const int *__restrict__ block_count, int n_slices,
+                               const MatchPart *__restrict__ part) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = t >> 4, ty = t & 15;
+  if (b >= *block_count) return;
+  const float init = kL2 ? 999.0f : -1.0f;
+  float best = init, second = init;
+  int idx = -1;
+  for (int y = 0; y < n_slices; y++) {
+    const MatchPart p = part[((size_t)b * n_slices + y) * 16 + ty];
+    if (p.idx < 0) continue;                         // empty slice
+    bool take;                                       // is p's winner preferred to the running one ?
+    if (idx < 0) take = true;
+    else if (p.best != best) take = better<kL2>(p.best, best);
+    else {
+      const int ra = bitrev4(p.idx & 15), rb = bitrev4(idx & 15);
+      take = ra != rb ? ra < rb : p.idx < idx;
+    }
+    float loser;
+    if (take) {
+      loser = best;
+      best = p.best;
+      idx = p.idx;
+    } else {
+      loser = p.best;
+    }
+    if (better<kL2>(loser, second)) second = loser;
+    if (better<kL2>(p.second, second)) second = p.second;
+  }
+  const int p1 = block_list[b] * 16 + ty;
+  if (p1 < n1) write_match<kL2>(s1 + p1, s2, best, second, idx);
 }
 
 }  // namespace
@@ -105,16 +174,29 @@ void launch_match(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2
   if (n1 <= 0 || n2 <= 0) return;
   dim3 blk(16, 16), grd((n1 + 15) / 16);
   const int chunks = (n2 + 15) / 16;
-  if (distance == 1) k_match<true><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, nullptr, nullptr);
-  else k_match<false><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, nullptr, nullptr);
+  if (distance == 1) k_match<true, false><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, nullptr, nullptr, 0, nullptr);
+  else k_match<false, false><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, nullptr, nullptr, 0, nullptr);
 }
 
-// Exact pass restricted to the 16-query blocks in block_list[0 .. *block_count).
+// Exact pass restricted to the first min(*block_count, max_blocks) 16-query blocks of block_list,
+// candidates cut into CSB_REDO_SLICES slices so that a handful of blocks does not serialise a whole
+// scan on one SM.  part: match_redo_scratch_bytes(max_blocks) bytes of scratch.
+size_t match_redo_scratch_bytes(int max_blocks) { return (size_t)max_blocks * CSB_REDO_SLICES * 16 * sizeof(MatchPart); }
+
 void launch_match_blocks(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
-                         const int *block_list, const int *block_count, cudaStream_t st) {
-  if (n1 <= 0 || n2 <= 0) return;
-  dim3 blk(16, 16), grd((n1 + 15) / 16);
+                         const int *block_list, const int *block_count, int max_blocks, void *part, cudaStream_t st) {
+  if (n1 <= 0 || n2 <= 0 || max_blocks <= 0) return;
   const int chunks = (n2 + 15) / 16;
-  if (distance == 1) k_match<true><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, block_list, block_count);
-  else k_match<false><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, block_list, block_count);
+  const int cps = (chunks + CSB_REDO_SLICES - 1) / CSB_REDO_SLICES;
+  const int slices = (chunks + cps - 1) / cps;
+  dim3 blk(16, 16), grd(max_blocks < 64 ? max_blocks : 64, slices);
+  MatchPart *mp = (MatchPart *)part;
+  const int fin_blocks = (max_blocks * 16 + 127) / 128;
+  if (distance == 1) {
+    k_match<true, true><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, block_list, block_count, cps, mp);
+    k_match_finish<true><<<fin_blocks, 128, 0, st>>>(d_sift1, n1, d_sift2, block_list, block_count, slices, mp);
+  } else {
+    k_match<false, true><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, block_list, block_count, cps, mp);
+    k_match_finish<false><<<fin_blocks, 128, 0, st>>>(d_sift1, n1, d_sift2, block_list, block_count, slices, mp);
+  }
 }
