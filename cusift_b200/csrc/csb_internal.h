@@ -40,11 +40,9 @@ void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog
                           int npitch, const float k[3], cudaStream_t st);
 void launch_find_points(const float *dog, int w, int h, int pitch, const ExtremaParams &ep, csb_sift_point *d_sift,
                         int *d_oct, unsigned int *d_counter, int max_pts, cudaStream_t st);
-void launch_orient_desc(const OctaveTexSet &texs, csb_sift_point *d_sift, const int *d_oct,
+void launch_orient_desc(const OctaveTexSet &texs, int n_oct, csb_sift_point *d_sift, const int *d_oct,
                         const unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st);
 void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st);
-void launch_copy_out(const csb_sift_point *d_sift, const unsigned int *d_counter, int max_pts, csb_sift_point *h_mapped,
-                     int *h_count_mapped, int sm_count, cudaStream_t st);
 void launch_match(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
                   cudaStream_t st);
 #define CSB_REDO_SLICES 32

@@ -22,6 +22,8 @@
 //                of the 8 trilinear vote sites the 16 lanes of a half hit 16
 //                different cells; the two halves own separate 128-bin copies.
 // Results are run-to-run deterministic and within the reference's own spread.
+#include <cstdlib>
+
 #include "csb_internal.h"
 
 namespace {
@@ -59,11 +61,21 @@ __device__ __forceinline__ void vote(float *q, float v) {
   __syncwarp();
 }
 
+// The two angular shares of one spatial share: q0 != q1 unless both are scratch (a lane's a1 and angp
+// differ, and a spilled a1 goes to the scratch cell), and at one vote site the 16 lanes of a half hit
+// 16 different cells, so both read-modify-writes can be in flight together.
+__device__ __forceinline__ void vote2(float *q0, float v0, float *q1, float v1) {
+  const float o0 = *q0, o1 = *q1;
+  *q0 = __fadd_rn(o0, v0);
+  *q1 = __fadd_rn(o1, v1);
+  __syncwarp();
+}
+
 struct Grad {
   float dx, dy;
 };
 
-__global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constant__ OctaveTexSet T,
+__global__ void __launch_bounds__(WARPS * 32, 6) k_orient_desc(const __grid_constant__ OctaveTexSet T,
                                                             csb_sift_point *__restrict__ d_sift,
                                                             const int *__restrict__ d_oct,
                                                             const unsigned int *__restrict__ counter, int max_pts,
@@ -81,10 +93,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
   const int half = lane >> 4, cellx = lane & 3, celly = (lane >> 2) & 3;
   float *copy = buf + half * DCOPY;
 
-  for (int k = blockIdx.x * WARPS + warp; k < n; k += gridDim.x * WARPS) {
+  // The list holds one contiguous run per octave, coarse to fine (k_find_points leaves the run ends in
+  // counter[1 + o]); blockIdx.y selects the run.  That makes the texture handle a function of a
+  // special register, i.e. provably warp-uniform: a handle looked up through d_oct[k] costs a
+  // divergence ("waterfall") loop around every one of the 48 texture fetches of a keypoint and keeps
+  // ptxas from batching them.
+  const int o = blockIdx.y;
+  unsigned int run_start = 0;
+  for (int c = CSB_MAX_OCTAVES - 1; c > o; c--) run_start = max(run_start, counter[1 + c]);
+  const int start = (int)min(run_start, (unsigned int)n);
+  const int end = (int)min(max(run_start, counter[1 + o]), (unsigned int)n);
+  const cudaTextureObject_t tex = T.tex[o];
+  {
+#pragma unroll 1
+  for (int k = start + blockIdx.x * WARPS + warp; k < end; k += gridDim.x * WARPS) {
     csb_sift_point *pt = d_sift + k;
     const float px = pt->coords2D[0], py = pt->coords2D[1], pscale = pt->scale, psub = pt->subsampling;
-    const cudaTextureObject_t tex = T.tex[d_oct[k]];
 
     // ---------------- orientation (cuSIFT_D.cu:319-396) ----------------
     const float i2sigma2 = __fdiv_rn(-1.0f, __fmul_rn(__fmul_rn(pscale, 4.5f), pscale));
@@ -99,16 +123,30 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
     }
     __syncwarp();
     const float xp = __fsub_rn(px, 5.0f), yp = __fsub_rn(py, 5.0f);
-    for (int s = lane; s < 121; s += 32) {
-      const int yd = s / 11, xd = s - yd * 11;
-      const float xf = __fadd_rn(xp, (float)xd), yf = __fadd_rn(yp, (float)yd);
-      const float dx = __fsub_rn(tex2D<float>(tex, __fadd_rn(xf, 1.0f), yf), tex2D<float>(tex, __fsub_rn(xf, 1.0f), yf));
-      const float dy = __fsub_rn(tex2D<float>(tex, xf, __fadd_rn(yf, 1.0f)), tex2D<float>(tex, xf, __fsub_rn(yf, 1.0f)));
-      int bin = (int)__fadd_rn(__fdiv_rn(__fmul_rn(16.0f, atan2f(dy, dx)), 3.1416f), 16.5f);
-      if (bin > 31) bin = 0;
-      const float grad = sqrtf(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-      float *q = hist + bin * 32 + lane;          // private column: no other lane touches it
-      *q = __fadd_rn(*q, __fmul_rn(__fmul_rn(grad, gauss[xd]), gauss[yd]));
+    // all 16 texture fetches of the lane's (up to) 4 window samples are issued before the first is used
+    float odx[4], ody[4];
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int s = lane + 32 * it;
+      if (s < 121) {
+        const int yd = s / 11, xd = s - yd * 11;
+        const float xf = __fadd_rn(xp, (float)xd), yf = __fadd_rn(yp, (float)yd);
+        odx[it] = __fsub_rn(tex2D<float>(tex, __fadd_rn(xf, 1.0f), yf), tex2D<float>(tex, __fsub_rn(xf, 1.0f), yf));
+        ody[it] = __fsub_rn(tex2D<float>(tex, xf, __fadd_rn(yf, 1.0f)), tex2D<float>(tex, xf, __fsub_rn(yf, 1.0f)));
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int s = lane + 32 * it;
+      if (s < 121) {
+        const int yd = s / 11, xd = s - yd * 11;
+        const float dx = odx[it], dy = ody[it];
+        int bin = (int)__fadd_rn(__fdiv_rn(__fmul_rn(16.0f, atan2f(dy, dx)), 3.1416f), 16.5f);
+        if (bin > 31) bin = 0;
+        const float grad = sqrtf(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        float *q = hist + bin * 32 + lane;          // private column: no other lane touches it
+        *q = __fadd_rn(*q, __fmul_rn(__fmul_rn(grad, gauss[xd]), gauss[yd]));
+      }
     }
     __syncwarp();
     {
@@ -154,8 +192,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
     const float sina = sinf(theta), cosa = cosf(theta);
     const float sc = __fmul_rn(pscale, 0.75f);
     const float ssina = __fmul_rn(sina, sc), scosa = __fmul_rn(cosa, sc);
-    // sample `it` of this lane's cell; the four texture fetches of sample it+1 are issued
-    // before sample it is voted, so their latency overlaps the atan2f / vote work
+    // sample `it` of this lane's cell
     auto fetch = [&](int it) -> Grad {
       const int j = it * 2 + half;
       const int tx = 4 * cellx + (j & 3), y = 4 * celly + (j >> 2);
@@ -170,11 +207,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
       return g;
     };
     float *dummy = copy + 128 + 8 * (lane & 15);   // private 8-bin scratch cell
-    Grad gnext = fetch(0);
-#pragma unroll 1
+    Grad gs[8];                                    // all 32 texture fetches of the lane's 8 samples in flight at once
+#pragma unroll
+    for (int it = 0; it < 8; it++) gs[it] = fetch(it);
+#pragma unroll
     for (int it = 0; it < 8; it++) {
-      const Grad g = gnext;
-      if (it + 1 < 8) gnext = fetch(it + 1);
+      const Grad g = gs[it];
       const int j = it * 2 + half;                 // sample within the lane's 4x4 cell
       const int tx = 4 * cellx + (j & 3), y = 4 * celly + (j >> 2);
       const float dx = g.dx, dy = g.dy;
@@ -205,14 +243,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
       // which another lane may be voting into at the same site: those votes go through an atomic pass.
       const bool spill = angi >= 8;
       const int a1 = spill ? 0 : angi;
-      vote((spill ? dummy : cUL) + a1, __fmul_rn(iangf, gUL));
-      vote(cUL + angp, __fmul_rn(angf, gUL));
-      vote((spill ? dummy : cDL) + a1, __fmul_rn(iangf, gDL));
-      vote(cDL + angp, __fmul_rn(angf, gDL));
-      vote((spill ? dummy : cUR) + a1, __fmul_rn(iangf, gUR));
-      vote(cUR + angp, __fmul_rn(angf, gUR));
-      vote((spill ? dummy : cDR) + a1, __fmul_rn(iangf, gDR));
-      vote(cDR + angp, __fmul_rn(angf, gDR));
+      vote2((spill ? dummy : cUL) + a1, __fmul_rn(iangf, gUL), cUL + angp, __fmul_rn(angf, gUL));
+      vote2((spill ? dummy : cDL) + a1, __fmul_rn(iangf, gDL), cDL + angp, __fmul_rn(angf, gDL));
+      vote2((spill ? dummy : cUR) + a1, __fmul_rn(iangf, gUR), cUR + angp, __fmul_rn(angf, gUR));
+      vote2((spill ? dummy : cDR) + a1, __fmul_rn(iangf, gDR), cDR + angp, __fmul_rn(angf, gDR));
       if (__any_sync(FULL, spill)) {
         if (spill) {
           if (vUL && hbase + 8 < 128) atomicAdd(copy + hbase + 8, __fmul_rn(iangf, gUL));
@@ -261,6 +295,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_orient_desc(const __grid_constan
     }
     __syncwarp();
   }
+  }
 }
 
 // Stand-alone SiftData::ConvertSiftToRootSift (cuSIFT.cu:383-395): one warp per point.
@@ -284,42 +319,16 @@ __global__ void __launch_bounds__(128) k_rootsift(csb_sift_point *__restrict__ d
   }
 }
 
-// Result hand-off: copies the first min(count,max_pts) records (147 words each)
-// and the count into page-locked, device-mapped host memory with coalesced
-// stores, so one stream synchronise is the only host<->device round trip of a
-// frame (the reference: cudaMemcpyFromSymbol + cudaMemcpy, cuSIFT.cu:107-113).
-__global__ void __launch_bounds__(256) k_copy_out(const csb_sift_point *__restrict__ d_sift,
-                                                  const unsigned int *__restrict__ counter, int max_pts,
-                                                  csb_sift_point *__restrict__ h_sift, int *__restrict__ h_count) {
-  const unsigned int cnt = *counter;
-  const int n = (int)min(cnt, (unsigned int)max_pts);
-  if (h_sift != nullptr) {
-    // 128-bit stores: a warp emits 512 contiguous bytes per instruction towards PCIe
-    const size_t bytes = (size_t)n * sizeof(csb_sift_point);
-    const size_t vecs = bytes / 16;
-    const uint4 *src4 = reinterpret_cast<const uint4 *>(d_sift);
-    uint4 *dst4 = reinterpret_cast<uint4 *>(h_sift);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vecs; i += stride) dst4[i] = src4[i];
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(d_sift);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(h_sift);
-    for (size_t i = vecs * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes / 4; i += stride) dst[i] = src[i];
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    h_count[0] = n;
-    h_count[1] = (int)cnt;
-  }
-}
-
 }  // namespace
 
-void launch_orient_desc(const OctaveTexSet &texs, csb_sift_point *d_sift, const int *d_oct,
+void launch_orient_desc(const OctaveTexSet &texs, int n_oct, csb_sift_point *d_sift, const int *d_oct,
                         const unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st) {
-  int blocks = sm_count * 8;
+  int blocks = sm_count * 6;                      // 6 resident CTAs per SM (80 registers, 26 KB shared)
   const int need = (max_pts + WARPS - 1) / WARPS;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  k_orient_desc<<<blocks, WARPS * 32, 0, st>>>(texs, d_sift, d_oct, d_counter, max_pts, rootsift);
+  // grid.y = octave, finest first: its run is by far the longest, the short runs fill the tail
+  k_orient_desc<<<dim3(blocks, n_oct), WARPS * 32, 0, st>>>(texs, d_sift, d_oct, d_counter, max_pts, rootsift);
 }
 
 void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st) {
@@ -327,9 +336,4 @@ void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st) {
   int blocks = (n + 3) / 4;
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_rootsift<<<blocks, 128, 0, st>>>(d_sift, n);
-}
-
-void launch_copy_out(const csb_sift_point *d_sift, const unsigned int *d_counter, int max_pts, csb_sift_point *h_mapped,
-                     int *h_count_mapped, int sm_count, cudaStream_t st) {
-  k_copy_out<<<sm_count * 2, 256, 0, st>>>(d_sift, d_counter, max_pts, h_mapped, h_count_mapped);
 }

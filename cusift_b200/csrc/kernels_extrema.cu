@@ -120,7 +120,12 @@ __device__ __forceinline__ void emit_warp(bool emit, const Refined &r, const Ext
   if (!m) return;
   const int leader = __ffs(m) - 1;
   unsigned int base = 0;
-  if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+  if (lane == leader) {
+    base = atomicAdd(counter, (unsigned int)__popc(m));
+    // counter[1 + octave] = end of this octave's run in the list (octaves are launched one after the
+    // other, so a run is contiguous): lets k_orient_desc pick its texture per run, warp-uniformly
+    atomicMax(counter + 1 + P.octave, base + (unsigned int)__popc(m));
+  }
   base = __shfl_sync(FULL, base, leader);
   if (emit) {
     const unsigned int idx = base + __popc(m & ((1u << lane) - 1u));

@@ -78,7 +78,7 @@ if lf.exists():
         data = rows[start + 1:]
         for r in data:
             wr.writerow([r[ik].split("(")[0], r[ig], r[ib], r[iv]])
-    frame = data[-13:]
+    frame = data[-12:]
     tot = sum(float(r[iv].replace(",", "")) for r in frame)
     lines += ["## launch list (last frame of the capture)", "", "| kernel | grid | ns | share |", "|---|---|---|---|"]
     for r in frame:
