@@ -7,10 +7,11 @@ needs a GPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libcusift_b200.so"
+LIB_PATH = Path(os.environ["CSB_LIB_PATH"]) if os.environ.get("CSB_LIB_PATH") else PKG_DIR / "libcusift_b200.so"   # override: kernel-variant experiments
 HEADER_PATH = PKG_DIR.parent / "include" / "cusift_b200.h"
 
 MAX_OCTAVES = 8

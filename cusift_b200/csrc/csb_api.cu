@@ -424,7 +424,7 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
     ExtremaParams E;
     extrema_params(p, o, subs[o], &E);
     LaunchScope ls(ctx, s, kNameFind[o]);
-    launch_find_points(oct[o].dog, oct[o].w, oct[o].h, oct[o].pitch, E, d_sift, s->d_oct, s->d_counter, max_pts, st);
+    launch_find_points(oct[o].dog, oct[o].w, oct[o].h, oct[o].pitch, E, d_sift, s->d_oct, s->d_counter, max_pts, ctx->sm_count, st);
   }
   {
     OctaveTexSet T;

@@ -39,7 +39,7 @@ void launch_blur_dog(const float *base, int w, int h, int pitch, float *dog, con
 void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next,
                           int npitch, const float k[3], cudaStream_t st);
 void launch_find_points(const float *dog, int w, int h, int pitch, const ExtremaParams &ep, csb_sift_point *d_sift,
-                        int *d_oct, unsigned int *d_counter, int max_pts, cudaStream_t st);
+                        int *d_oct, unsigned int *d_counter, int max_pts, int sm_count, cudaStream_t st);
 void launch_orient_desc(const OctaveTexSet &texs, int n_oct, csb_sift_point *d_sift, const int *d_oct,
                         const unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st);
 void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st);

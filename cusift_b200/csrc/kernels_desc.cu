@@ -29,6 +29,12 @@
 namespace {
 
 constexpr int WARPS = 4;
+#ifndef K3_MINB
+#define K3_MINB 8          // resident CTAs per SM the register budget is sized for
+#endif
+#ifndef K3_BATCH
+#define K3_BATCH 2         // descriptor samples whose texture fetches are in flight together
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -52,7 +58,11 @@ __device__ __forceinline__ float sumsq_tree(const float (&b)[4], int lane) {
   return __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
 }
 
-constexpr int DCOPY = 128 + 16 * 8;   // one descriptor copy: 128 bins + an 8-bin dummy cell per lane of the half
+// Descriptor accumulator of one warp: buf[row][bank], 16 rows x 32 banks.  Rows 0-7 hold angular bin
+// `row` of cell c of half-warp h at bank 16 h + c; rows 8-15 are the scratch bins of lane 16 h + c.
+// At one vote site the 32 lanes address 32 different (half, cell) pairs, hence 32 different banks
+// whatever their angular bins are (the cell-major layout measured 72 % conflict wavefronts).
+constexpr int DBUF = 16 * 32;
 
 // Plain read-modify-write vote: the caller guarantees that no two lanes of the warp
 // target the same address in the same call (see the lane->cell mapping below).
@@ -75,7 +85,7 @@ struct Grad {
   float dx, dy;
 };
 
-__global__ void __launch_bounds__(WARPS * 32, 6) k_orient_desc(const __grid_constant__ OctaveTexSet T,
+__global__ void __launch_bounds__(WARPS * 32, K3_MINB) k_orient_desc(const __grid_constant__ OctaveTexSet T,
                                                             csb_sift_point *__restrict__ d_sift,
                                                             const int *__restrict__ d_oct,
                                                             const unsigned int *__restrict__ counter, int max_pts,
@@ -83,7 +93,7 @@ __global__ void __launch_bounds__(WARPS * 32, 6) k_orient_desc(const __grid_cons
   __shared__ __align__(16) float s_hist[WARPS][32 * 32];   // orientation: [bin][lane] private columns
   __shared__ float s_sm[WARPS][64];                         // reduced + smoothed orientation histogram
   __shared__ float s_gauss[WARPS][16];
-  __shared__ float s_buf[WARPS][2 * DCOPY];                 // descriptor: one copy per half-warp
+  __shared__ float s_buf[WARPS][DBUF];                      // descriptor accumulator, see DBUF
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *hist = s_hist[warp], *sm = s_sm[warp], *gauss = s_gauss[warp], *buf = s_buf[warp];
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(WARPS * 32, 6) k_orient_desc(const __grid_cons
   const int n = (int)min(cnt, (unsigned int)max_pts);
   // descriptor sampling pattern: lane = half*16 + cell_y*4 + cell_x
   const int half = lane >> 4, cellx = lane & 3, celly = (lane >> 2) & 3;
-  float *copy = buf + half * DCOPY;
+  float *copy = buf + half * 16;                            // + cell + 32 * bin
 
   // The list holds one contiguous run per octave, coarse to fine (k_find_points leaves the run ends in
   // counter[1 + o]); blockIdx.y selects the run.  That makes the texture handle a function of a
@@ -117,9 +127,9 @@ __global__ void __launch_bounds__(WARPS * 32, 6) k_orient_desc(const __grid_cons
       gauss[lane] = expf(__fmul_rn(__fmul_rn(d, i2sigma2), d));
     }
     {
-      float4 *z = reinterpret_cast<float4 *>(hist + lane * 32);
+      float4 *z = reinterpret_cast<float4 *>(hist);
 #pragma unroll
-      for (int j = 0; j < 8; j++) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 8; j++) z[j * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
     const float xp = __fsub_rn(px, 5.0f), yp = __fsub_rn(py, 5.0f);
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(WARPS * 32, 6) k_orient_desc(const __grid_cons
       const float d = __fsub_rn((float)lane, 7.5f);
       gauss[lane] = expf(__fdiv_rn(__fmul_rn(-d, d), 128.0f));
     }
-    for (int j = lane; j < 2 * DCOPY; j += 32) buf[j] = 0.0f;
+    for (int j = lane; j < DBUF; j += 32) buf[j] = 0.0f;
     __syncwarp();
     const float theta = __fmul_rn(2.0f * 3.1415f / 360.0f, orient);
     const float sina = sinf(theta), cosa = cosf(theta);
@@ -206,13 +216,16 @@ __global__ void __launch_bounds__(WARPS * 32, 6) k_orient_desc(const __grid_cons
                        tex2D<float>(tex, __fadd_rn(xpos, sina), __fsub_rn(ypos, cosa)));
       return g;
     };
-    float *dummy = copy + 128 + 8 * (lane & 15);   // private 8-bin scratch cell
-    Grad gs[8];                                    // all 32 texture fetches of the lane's 8 samples in flight at once
+    float *dummy = copy + 8 * 32 + (lane & 15);    // private 8-bin scratch cell (rows 8-15)
+#pragma unroll 1
+    for (int it0 = 0; it0 < 8; it0 += K3_BATCH) {
+    Grad gs[K3_BATCH];                             // 4 K3_BATCH texture fetches of the lane in flight at once
 #pragma unroll
-    for (int it = 0; it < 8; it++) gs[it] = fetch(it);
+    for (int i = 0; i < K3_BATCH; i++) gs[i] = fetch(it0 + i);
 #pragma unroll
-    for (int it = 0; it < 8; it++) {
-      const Grad g = gs[it];
+    for (int i = 0; i < K3_BATCH; i++) {
+      const int it = it0 + i;
+      const Grad g = gs[i];
       const int j = it * 2 + half;                 // sample within the lane's 4x4 cell
       const int tx = 4 * cellx + (j & 3), y = 4 * celly + (j >> 2);
       const float dx = g.dx, dy = g.dy;
@@ -228,41 +241,45 @@ __global__ void __launch_bounds__(WARPS * 32, 6) k_orient_desc(const __grid_cons
       const int angp = (angi < 7 ? angi + 1 : 0);
       angf = __fsub_rn(angf, (float)angi);
       const float iangf = __fsub_rn(1.0f, angf);
-      const int hbase = 8 * (4 * veri + hori);
+      const int cell = 4 * veri + hori;              // the UL cell; DL = +4, UR = +1, DR = +5 (may be -5 .. 20)
       // the four spatial shares (guards of cuSIFT_D.cu:230-255; `tx<=14` sic).  A share whose cell
       // lies outside buffer[128] is dropped (in the reference it lands beyond its last shared array);
       // invalid shares are simply accumulated into the lane's scratch cell.
       const bool gl = tx >= 2, gr = tx <= 14, gu = y >= 2, gd = y <= 13;
       const float gUL = __fmul_rn(iverf, __fmul_rn(ihorf, grad)), gDL = __fmul_rn(verf, __fmul_rn(ihorf, grad));
       const float gUR = __fmul_rn(iverf, __fmul_rn(horf, grad)), gDR = __fmul_rn(verf, __fmul_rn(horf, grad));
-      const bool vUL = gl && gu, vDL = gl && gd && (hbase + 32 < 128);
-      const bool vUR = gr && gu && (hbase + 8 < 128), vDR = gr && gd && (hbase + 40 < 128);
-      float *cUL = vUL ? copy + hbase : dummy, *cDL = vDL ? copy + hbase + 32 : dummy;
-      float *cUR = vUR ? copy + hbase + 8 : dummy, *cDR = vDR ? copy + hbase + 40 : dummy;
+      const bool vUL = gl && gu, vDL = gl && gd && (cell + 4 < 16);
+      const bool vUR = gr && gu && (cell + 1 < 16), vDR = gr && gd && (cell + 5 < 16);
+      float *cUL = vUL ? copy + cell : dummy, *cDL = vDL ? copy + cell + 4 : dummy;
+      float *cUR = vUR ? copy + cell + 1 : dummy, *cDR = vDR ? copy + cell + 5 : dummy;
       // angi == 8 (atan2f >= 3.1415, e.g. dy == +0, dx < 0) makes p1 point at bin 0 of the NEXT cell,
       // which another lane may be voting into at the same site: those votes go through an atomic pass.
       const bool spill = angi >= 8;
-      const int a1 = spill ? 0 : angi;
-      vote2((spill ? dummy : cUL) + a1, __fmul_rn(iangf, gUL), cUL + angp, __fmul_rn(angf, gUL));
-      vote2((spill ? dummy : cDL) + a1, __fmul_rn(iangf, gDL), cDL + angp, __fmul_rn(angf, gDL));
-      vote2((spill ? dummy : cUR) + a1, __fmul_rn(iangf, gUR), cUR + angp, __fmul_rn(angf, gUR));
-      vote2((spill ? dummy : cDR) + a1, __fmul_rn(iangf, gDR), cDR + angp, __fmul_rn(angf, gDR));
+      const int a1 = spill ? 0 : 32 * angi, a2 = 32 * angp;
+      vote2((spill ? dummy : cUL) + a1, __fmul_rn(iangf, gUL), cUL + a2, __fmul_rn(angf, gUL));
+      vote2((spill ? dummy : cDL) + a1, __fmul_rn(iangf, gDL), cDL + a2, __fmul_rn(angf, gDL));
+      vote2((spill ? dummy : cUR) + a1, __fmul_rn(iangf, gUR), cUR + a2, __fmul_rn(angf, gUR));
+      vote2((spill ? dummy : cDR) + a1, __fmul_rn(iangf, gDR), cDR + a2, __fmul_rn(angf, gDR));
       if (__any_sync(FULL, spill)) {
         if (spill) {
-          if (vUL && hbase + 8 < 128) atomicAdd(copy + hbase + 8, __fmul_rn(iangf, gUL));
-          if (vDL && hbase + 40 < 128) atomicAdd(copy + hbase + 40, __fmul_rn(iangf, gDL));
-          if (vUR && hbase + 16 < 128) atomicAdd(copy + hbase + 16, __fmul_rn(iangf, gUR));
-          if (vDR && hbase + 48 < 128) atomicAdd(copy + hbase + 48, __fmul_rn(iangf, gDR));
+          if (vUL && cell + 1 < 16) atomicAdd(copy + cell + 1, __fmul_rn(iangf, gUL));
+          if (vDL && cell + 5 < 16) atomicAdd(copy + cell + 5, __fmul_rn(iangf, gDL));
+          if (vUR && cell + 2 < 16) atomicAdd(copy + cell + 2, __fmul_rn(iangf, gUR));
+          if (vDR && cell + 6 < 16) atomicAdd(copy + cell + 6, __fmul_rn(iangf, gDR));
         }
         __syncwarp();
       }
+    }
     }
     __syncwarp();
 
     // normalise, clamp at 0.2, normalise (cuSIFT_D.cu:259-291)
     float b[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) b[j] = __fadd_rn(buf[lane + 32 * j], buf[DCOPY + lane + 32 * j]);
+    for (int j = 0; j < 4; j++) {                    // element lane + 32 j = cell 4 j + lane / 8, bin lane % 8
+      const float *e = buf + (lane & 7) * 32 + 4 * j + (lane >> 3);
+      b[j] = __fadd_rn(e[0], e[16]);
+    }
     const float r1 = rsqrtf(sumsq_tree(b, lane));
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -323,7 +340,7 @@ __global__ void __launch_bounds__(128) k_rootsift(csb_sift_point *__restrict__ d
 
 void launch_orient_desc(const OctaveTexSet &texs, int n_oct, csb_sift_point *d_sift, const int *d_oct,
                         const unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st) {
-  int blocks = sm_count * 6;                      // 6 resident CTAs per SM (80 registers, 26 KB shared)
+  int blocks = sm_count * K3_MINB;                // resident CTAs per SM (register budget, 26 KB shared each)
   const int need = (max_pts + WARPS - 1) / WARPS;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;

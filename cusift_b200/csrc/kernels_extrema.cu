@@ -5,22 +5,28 @@
 //   * ONE pass over the 7 DoG planes of an octave (28 B/pixel, each value fetched
 //     once) instead of 5 overlapping scale-blocks that re-read every plane ~3x.
 //     A warp owns 30 columns (+1 halo lane each side) and streams rows downwards;
-//     per plane a 3-row window lives in registers, horizontal neighbours come
-//     from warp shuffles, and the 26-neighbour test is a separable min/max network
-//     (3-input FMNMX): per plane  hx = max3(left, v, right),
-//     F = max3(hx[y-1], hx[y], hx[y+1]) (full 3x3); a pixel is a (non-strict)
-//     maximum of its 3x3x3 block iff v == max3(F[plane-1], F[plane], F[plane+1]).
-//     The scan flags those (plus |v| > thresh); the reference's STRICT comparison
-//     against each of the 26 neighbours (cuSIFT_D.cu:450-470) is then applied to the
-//     few flagged pixels in the dense second phase, so exact ties are rejected
-//     exactly as in the reference.  No shared memory, no barriers in the scan.
-//   * candidates go to a per-CTA list sized for the worst case (16-bit entries; the
-//     reference's 32-entry list silently wraps, cuSIFT_D.cu:455,465); after the
-//     scan the whole CTA verifies + refines them densely and compacts survivors
-//     with warp ballots, one global atomicAdd per warp.
+//     per plane a 3-row window lives in registers and horizontal neighbours come
+//     from warp shuffles.
+//   * the scan is a conservative PREFILTER in packed fp16: every value travels as the
+//     half2 (rn(v), rn(-v)), so ONE 3-input packed max (VHMNMX) advances the maximum
+//     and the minimum network together (min/max issue at half rate on sm_100a and were
+//     the bound of the fp32 scan): per plane hx = max3(left, c, right), F = max3 over
+//     the three rows, M = max3(F[plane-1], F[plane], F[plane+1]).  Rounding is monotone,
+//     so a true fp32 extremum above the threshold always satisfies rn(v) == M and
+//     rn(|v|) >= rn(thresh); the scan flags those pixels (plus fp16 ties).
+//   * flagged pixels go to a per-CTA list; after the scan the whole CTA applies the
+//     reference's STRICT fp32 comparison against each of the 26 neighbours
+//     (cuSIFT_D.cu:450-470) and its |v| > thresh test, refines the survivors and compacts
+//     them with warp ballots, one global atomicAdd per warp.  (The reference's 32-entry
+//     list silently wraps, cuSIFT_D.cu:455,465; here a pixel that finds the list full is
+//     verified and emitted on the spot by its own lane.)
 //   * the refinement is evaluated in the exact multiply-add order of the
 //     reference's sm_100a SASS, so x, y, scale, sharpness and edgeness are
 //     bit-identical to the reference's for the same DoG input.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
 #include <type_traits>
 
 #include "csb_internal.h"
@@ -30,14 +36,28 @@ namespace {
 constexpr int XT_COLS = 30;          // output columns per warp
 constexpr int XT_WARPS = 4;
 constexpr int XT_TW = XT_COLS * XT_WARPS;   // 120 output columns per CTA
-constexpr int XT_ROWS = 36;          // output rows per CTA (multiple of 6)
-constexpr int XT_CAP = XT_COLS * XT_WARPS * XT_ROWS * CSB_NUM_SCALES;   // worst case: the list cannot overflow
+constexpr int XT_MAX_ROWS = 36;      // output rows per CTA: a launch parameter, multiple of 3, <= 63
+constexpr int XT_CAP = 2048;         // flagged pixels per CTA held for the dense second phase
 constexpr int NPL = CSB_NUM_DOG;     // 7 planes
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// packed fp16 helpers: p = (rn(v), rn(-v)); ptxas fuses the two max.f16x2 into one 3-input VHMNMX
+__device__ __forceinline__ unsigned int pack_pm(float v) {
+  const __half2 p = __floats2half2_rn(v, -v);
+  return *reinterpret_cast<const unsigned int *>(&p);
+}
+__device__ __forceinline__ unsigned int hmax3(unsigned int a, unsigned int b, unsigned int c) {
+  unsigned int t, d;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(b));
+  asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(t), "r"(c));
+  return d;
+}
+// 0xffff in each half where p == m and p >= t
+__device__ __forceinline__ unsigned int flag_pm(unsigned int p, unsigned int m, unsigned int t) {
+  const __half2 hp = *reinterpret_cast<const __half2 *>(&p);
+  return __heq2_mask(hp, *reinterpret_cast<const __half2 *>(&m)) & __hge2_mask(hp, *reinterpret_cast<const __half2 *>(&t));
+}
 
 struct Refined {
   float x, y, scale, sharp, edge;
@@ -157,18 +177,19 @@ __device__ __forceinline__ bool strict_extremum(const float *__restrict__ dog, s
   return ok;
 }
 
-__global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
+__global__ void __launch_bounds__(XT_WARPS * 32, 6) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
                                                                   const __grid_constant__ ExtremaParams P,
                                                                   csb_sift_point *__restrict__ d_sift,
                                                                   int *__restrict__ d_oct,
-                                                                  unsigned int *__restrict__ counter, int max_pts) {
+                                                                  unsigned int *__restrict__ counter, int max_pts,
+                                                                  int rows, int cap) {
   __shared__ unsigned int s_cnt;
   __shared__ unsigned short s_list[XT_CAP];   // local column | local row << 7 | scale << 13
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = blockIdx.x * XT_TW + warp * XT_COLS - 1 + lane;
   const int cx = clampi(x, 0, w - 1);
-  const int y0 = blockIdx.y * XT_ROWS;
+  const int y0 = blockIdx.y * rows;
   const size_t plane = (size_t)pitch * h;
   // image-border pixels can never be strict extrema (their clamped neighbours include
   // the pixel itself, cuSIFT_D.cu:416,427-429); lanes 0 and 31 are halo columns
@@ -176,11 +197,12 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
 
-  // per plane: horizontal max3 / min3 of three consecutive rows (slots rotate), centre values of
-  // those rows for the 5 centre planes, and three source rows in flight
-  float hx[NPL][3], hn[NPL][3], vc[CSB_NUM_SCALES][3];
+  // per plane: packed horizontal max3 of three consecutive rows (slots rotate), packed centre values
+  // of those rows for the 5 centre planes, and three source rows in flight
+  unsigned int hx[NPL][3], vc[CSB_NUM_SCALES][3];
   float ring[3][NPL];
   const float *col = dog + cx;
+  const unsigned int tpk = pack_pm(P.thresh) & 0xffffu, tp = tpk | (tpk << 16);   // (rn(t), rn(t))
 
   auto fetch = [&](int r, auto RS) {
     constexpr int R = decltype(RS)::value;
@@ -192,50 +214,58 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
     constexpr int S = decltype(SLOT)::value, R = decltype(RS)::value;
 #pragma unroll
     for (int p = 0; p < NPL; p++) {
-      const float c = ring[R][p];
-      const float l = __shfl_up_sync(FULL, c, 1), r = __shfl_down_sync(FULL, c, 1);
-      hx[p][S] = max3(l, c, r);
-      hn[p][S] = min3(l, c, r);
+      const unsigned int c = pack_pm(ring[R][p]);
+      const unsigned int l = __shfl_up_sync(FULL, c, 1), r = __shfl_down_sync(FULL, c, 1);
+      hx[p][S] = hmax3(l, c, r);
       if (p >= 1 && p <= CSB_NUM_SCALES) vc[p - 1][S] = c;
     }
   };
   auto test = [&](auto SM, int y) {   // output row y = slot SM; the other two slots are rows y-1 / y+1
     constexpr int M = decltype(SM)::value;
-    float fx[NPL], fn[NPL];
+    unsigned int fx[NPL];
 #pragma unroll
-    for (int p = 0; p < NPL; p++) {
-      fx[p] = max3(hx[p][0], hx[p][1], hx[p][2]);
-      fn[p] = min3(hn[p][0], hn[p][1], hn[p][2]);
-    }
-    const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + XT_ROWS);
-    unsigned int cmask = 0;
+    for (int p = 0; p < NPL; p++) fx[p] = hmax3(hx[p][0], hx[p][1], hx[p][2]);
+    unsigned int e[CSB_NUM_SCALES], any = 0;
 #pragma unroll
     for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
-      const float val = vc[sc][M];
-      const float mx = max3(fx[sc], fx[sc + 1], fx[sc + 2]);
-      const float mn = min3(fn[sc], fn[sc + 1], fn[sc + 2]);
-      const float m = (val > 0.0f) ? mx : mn;               // the side this value could be an extremum of
-      const bool cand = (val == m) && (fabsf(val) > P.thresh);
-      cmask |= cand ? (1u << sc) : 0u;
+      e[sc] = flag_pm(vc[sc][M], hmax3(fx[sc], fx[sc + 1], fx[sc + 2]), tp);
+      any |= e[sc];
     }
-    if (rowOK && cmask) {                                    // rare
+    const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + rows);
+    if (rowOK && any) {                                      // rare
       const unsigned int loc = (unsigned int)(x - (int)blockIdx.x * XT_TW) | ((unsigned int)(y - y0) << 7);
 #pragma unroll
       for (int sc = 0; sc < CSB_NUM_SCALES; sc++)
-        if ((cmask >> sc) & 1u) s_list[atomicAdd(&s_cnt, 1u)] = (unsigned short)(loc | ((unsigned int)sc << 13));
+        if (e[sc]) {
+          const unsigned int slot = atomicAdd(&s_cnt, 1u);
+          if (slot < (unsigned int)cap) s_list[slot] = (unsigned short)(loc | ((unsigned int)sc << 13));
+        }
     }
   };
   // dense second phase: strict 26-neighbour test, refinement, compaction (whole CTA)
   auto drain = [&]() {
-    const unsigned int n = s_cnt;
+    const unsigned int flagged = s_cnt;
+    // more flagged pixels than the list holds (pathological input): forget the list and put every
+    // pixel of the tile through the strict test instead
+    const bool dense = flagged > (unsigned int)cap;
+    const int tile_w = min(XT_TW, w - (int)blockIdx.x * XT_TW), tile_h = min(rows, h - y0);
+    const unsigned int n = dense ? (unsigned int)(tile_w * tile_h * CSB_NUM_SCALES) : flagged;
     for (unsigned int base = 0; base < n; base += XT_WARPS * 32) {
       const unsigned int i = base + threadIdx.x;
       bool emit = false;
       Refined r;
       if (i < n) {
-        const unsigned int e = s_list[i];
-        const int ex = (int)blockIdx.x * XT_TW + (int)(e & 0x7fu), ey = y0 + (int)((e >> 7) & 0x3fu), es = (int)(e >> 13);
-        if (strict_extremum(dog, plane, pitch, es, ex, ey, P.thresh)) emit = refine(dog, plane, pitch, P, ex, ey, es, r);
+        int ex, ey, es;
+        if (dense) {
+          es = (int)(i % CSB_NUM_SCALES);
+          ex = (int)blockIdx.x * XT_TW + (int)((i / CSB_NUM_SCALES) % (unsigned int)tile_w);
+          ey = y0 + (int)((i / CSB_NUM_SCALES) / (unsigned int)tile_w);
+        } else {
+          const unsigned int en = s_list[i];
+          ex = (int)blockIdx.x * XT_TW + (int)(en & 0x7fu), ey = y0 + (int)((en >> 7) & 0x3fu), es = (int)(en >> 13);
+        }
+        const bool inner = ex >= 1 && ex <= w - 2 && ey >= 1 && ey <= h - 2;
+        if (inner && strict_extremum(dog, plane, pitch, es, ex, ey, P.thresh)) emit = refine(dog, plane, pitch, P, ex, ey, es, r);
       }
       emit_warp(emit, r, P, d_sift, d_oct, counter, max_pts, lane);
     }
@@ -252,7 +282,7 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
   fetch(y0 + 1, I0{});
   fetch(y0 + 2, I1{});
   fetch(y0 + 3, I2{});
-  const int yEnd = min(y0 + XT_ROWS, h - 1);   // exclusive; rows >= h-1 never qualify
+  const int yEnd = min(y0 + rows, h - 1);   // exclusive; rows >= h-1 never qualify
   for (int y = y0; y < yEnd; y += 3) {
     place(I2{}, I0{}); fetch(y + 4, I0{}); test(I1{}, y);        // rows y-1, y, y+1
     place(I0{}, I1{}); fetch(y + 5, I1{}); test(I2{}, y + 1);
@@ -265,7 +295,20 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 4) k_find_points(const float *_
 }  // namespace
 
 void launch_find_points(const float *dog, int w, int h, int pitch, const ExtremaParams &ep, csb_sift_point *d_sift,
-                        int *d_oct, unsigned int *d_counter, int max_pts, cudaStream_t st) {
-  dim3 grd((w + XT_TW - 1) / XT_TW, (h + XT_ROWS - 1) / XT_ROWS);
-  k_find_points<<<grd, XT_WARPS * 32, 0, st>>>(dog, w, h, pitch, ep, d_sift, d_oct, d_counter, max_pts);
+                        int *d_oct, unsigned int *d_counter, int max_pts, int sm_count, cudaStream_t st) {
+  const int tiles_x = (w + XT_TW - 1) / XT_TW;
+  // rows per CTA: about one full wave of CTAs (6 resident per SM), so that the serial row loop of a
+  // CTA is as short as the image allows; multiple of 3 (the register window rotates in threes)
+  int rows = (int)(((long long)h * tiles_x + (long long)sm_count * 6 - 1) / ((long long)sm_count * 6));
+  rows = ((rows + 2) / 3) * 3;
+  if (rows < 6) rows = 6;
+  if (rows > XT_MAX_ROWS) rows = XT_MAX_ROWS;
+  dim3 grd(tiles_x, (h + rows - 1) / rows);
+  static int cap = 0;                                  // CSB_XT_CAP: shrink the per-CTA list (tests of the dense fallback)
+  if (!cap) {
+    const char *e = getenv("CSB_XT_CAP");
+    cap = e ? atoi(e) : XT_CAP;
+    if (cap < 1 || cap > XT_CAP) cap = XT_CAP;
+  }
+  k_find_points<<<grd, XT_WARPS * 32, 0, st>>>(dog, w, h, pitch, ep, d_sift, d_oct, d_counter, max_pts, rows, cap);
 }

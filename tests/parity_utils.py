@@ -104,6 +104,12 @@ def compare_keypoints(ours: np.ndarray, ref: np.ndarray, tol: float = POS_TOL) -
     return out
 
 
+def canonical_sort(pts: np.ndarray) -> np.ndarray:
+    """Keypoints in (subsampling, x, y, scale) order — the list order itself is nondeterministic (atomics)."""
+    order = np.lexsort((pts["scale"], pts["coords2D"][:, 1], pts["coords2D"][:, 0], pts["subsampling"]))
+    return np.ascontiguousarray(pts[order])
+
+
 def per_octave_counts(pts: np.ndarray) -> dict:
     sub = pts["subsampling"]
     return {str(float(k)): int((sub == k).sum()) for k in np.unique(sub)}

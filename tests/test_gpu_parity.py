@@ -492,3 +492,29 @@ def test_allpairs_match_ransac_vs_oracle(gpu_ctx):
     finally:
         for d in dptrs:
             gpu_ctx.free(d)
+
+
+def test_extrema_dense_fallback_matches_list_path(frames, tmp_path):
+    """A tile whose flagged pixels exceed the per-CTA list is re-examined pixel by pixel; with the list
+    shrunk to 4 entries (CSB_XT_CAP) practically every tile takes that path and the keypoints stay the same."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import cusift_b200 as csb, parity_utils as PU\n"
+        "g1, _ = PU.golden_frames(); ctx = csb.Context(0, 1)\n"
+        "k = ctx.extract(PU.preblur(g1), csb.make_params(5, 0.0, 0.5), max_pts=32768)\n"
+        "np.save(sys.argv[1], PU.canonical_sort(k))\n" % (str(PU.ROOT), str(PU.ROOT / "tests")))
+    outs = []
+    for cap in ("", "4"):
+        env = dict(os.environ)
+        env.pop("CSB_XT_CAP", None)
+        if cap:
+            env["CSB_XT_CAP"] = cap
+        out = tmp_path / f"k{cap or 'dflt'}.npy"
+        subprocess.run([sys.executable, "-c", code, str(out)], check=True, env=env, timeout=300)
+        outs.append(np.load(out))
+    a, b = outs
+    assert len(a) == len(b) and len(a) > 1000
+    for f in ("coords2D", "scale", "sharpness", "edgeness", "orientation", "subsampling"):
+        assert np.array_equal(a[f], b[f]), f
