@@ -36,6 +36,12 @@ namespace {
 constexpr int XT_COLS = 30;          // output columns per warp
 constexpr int XT_WARPS = 4;
 constexpr int XT_TW = XT_COLS * XT_WARPS;   // 120 output columns per CTA
+#ifndef K2_MINB
+#define K2_MINB 6           // resident CTAs per SM the register budget is sized for
+#endif
+#ifndef K2_WAVES
+#define K2_WAVES 1          // CTAs launched per resident slot
+#endif
 constexpr int XT_MAX_ROWS = 36;      // output rows per CTA: a launch parameter, multiple of 3, <= 63
 constexpr int XT_CAP = 2048;         // flagged pixels per CTA held for the dense second phase
 constexpr int NPL = CSB_NUM_DOG;     // 7 planes
@@ -52,6 +58,12 @@ __device__ __forceinline__ unsigned int hmax3(unsigned int a, unsigned int b, un
   asm("max.f16x2 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(b));
   asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(t), "r"(c));
   return d;
+}
+__device__ __forceinline__ unsigned int eq_pm(unsigned int p, unsigned int m) {
+  return __heq2_mask(*reinterpret_cast<const __half2 *>(&p), *reinterpret_cast<const __half2 *>(&m));
+}
+__device__ __forceinline__ unsigned int ge_pm(unsigned int p, unsigned int t) {
+  return __hge2_mask(*reinterpret_cast<const __half2 *>(&p), *reinterpret_cast<const __half2 *>(&t));
 }
 // 0xffff in each half where p == m and p >= t
 __device__ __forceinline__ unsigned int flag_pm(unsigned int p, unsigned int m, unsigned int t) {
@@ -177,7 +189,7 @@ __device__ __forceinline__ bool strict_extremum(const float *__restrict__ dog, s
   return ok;
 }
 
-__global__ void __launch_bounds__(XT_WARPS * 32, 6) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
+__global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
                                                                   const __grid_constant__ ExtremaParams P,
                                                                   csb_sift_point *__restrict__ d_sift,
                                                                   int *__restrict__ d_oct,
@@ -204,11 +216,16 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 6) k_find_points(const float *_
   const float *col = dog + cx;
   const unsigned int tpk = pack_pm(P.thresh) & 0xffffu, tp = tpk | (tpk << 16);   // (rn(t), rn(t))
 
+  // one 64-bit base per plane, so that a row address is a single IMAD.WIDE (FMA pipe) per load: the
+  // scan is bound by the half-rate ALU pipe, where 64-bit adds would compete with the max network
+  const float *pbase[NPL];
+#pragma unroll
+  for (int p = 0; p < NPL; p++) pbase[p] = col + (size_t)p * plane;
   auto fetch = [&](int r, auto RS) {
     constexpr int R = decltype(RS)::value;
-    const float *q = col + (size_t)clampi(r, 0, h - 1) * pitch;
+    const unsigned int off = (unsigned int)clampi(r, 0, h - 1) * (unsigned int)pitch;
 #pragma unroll
-    for (int p = 0; p < NPL; p++) ring[R][p] = q[(size_t)p * plane];
+    for (int p = 0; p < NPL; p++) ring[R][p] = pbase[p][off];
   };
   auto place = [&](auto SLOT, auto RS) {
     constexpr int S = decltype(SLOT)::value, R = decltype(RS)::value;
@@ -225,18 +242,20 @@ __global__ void __launch_bounds__(XT_WARPS * 32, 6) k_find_points(const float *_
     unsigned int fx[NPL];
 #pragma unroll
     for (int p = 0; p < NPL; p++) fx[p] = hmax3(hx[p][0], hx[p][1], hx[p][2]);
-    unsigned int e[CSB_NUM_SCALES], any = 0;
+    // flagged: packed value equals the 27-neighbourhood maximum at some scale AND some scale of this
+    // pixel reaches the threshold (a superset of "at the same scale", refined in the rare path below)
+    unsigned int mx[CSB_NUM_SCALES];
 #pragma unroll
-    for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
-      e[sc] = flag_pm(vc[sc][M], hmax3(fx[sc], fx[sc + 1], fx[sc + 2]), tp);
-      any |= e[sc];
-    }
+    for (int sc = 0; sc < CSB_NUM_SCALES; sc++) mx[sc] = hmax3(fx[sc], fx[sc + 1], fx[sc + 2]);
+    const unsigned int eq = (eq_pm(vc[0][M], mx[0]) | eq_pm(vc[1][M], mx[1]) | eq_pm(vc[2][M], mx[2])) |
+                            (eq_pm(vc[3][M], mx[3]) | eq_pm(vc[4][M], mx[4]));
+    const unsigned int big = hmax3(hmax3(vc[0][M], vc[1][M], vc[2][M]), vc[3][M], vc[4][M]);
     const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + rows);
-    if (rowOK && any) {                                      // rare
+    if (rowOK && (eq & ge_pm(big, tp))) {                    // rare
       const unsigned int loc = (unsigned int)(x - (int)blockIdx.x * XT_TW) | ((unsigned int)(y - y0) << 7);
 #pragma unroll
       for (int sc = 0; sc < CSB_NUM_SCALES; sc++)
-        if (e[sc]) {
+        if (flag_pm(vc[sc][M], mx[sc], tp)) {
           const unsigned int slot = atomicAdd(&s_cnt, 1u);
           if (slot < (unsigned int)cap) s_list[slot] = (unsigned short)(loc | ((unsigned int)sc << 13));
         }
@@ -299,7 +318,8 @@ void launch_find_points(const float *dog, int w, int h, int pitch, const Extrema
   const int tiles_x = (w + XT_TW - 1) / XT_TW;
   // rows per CTA: about one full wave of CTAs (6 resident per SM), so that the serial row loop of a
   // CTA is as short as the image allows; multiple of 3 (the register window rotates in threes)
-  int rows = (int)(((long long)h * tiles_x + (long long)sm_count * 6 - 1) / ((long long)sm_count * 6));
+  const long long slots = (long long)sm_count * K2_MINB * K2_WAVES;
+  int rows = (int)(((long long)h * tiles_x + slots - 1) / slots);
   rows = ((rows + 2) / 3) * 3;
   if (rows < 6) rows = 6;
   if (rows > XT_MAX_ROWS) rows = XT_MAX_ROWS;
