@@ -150,6 +150,20 @@ def reference_arm(args, rank: int, world: int):
     print(json.dumps(line))
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full
+    capture (profiles/*_traffic.json, written by tools/summarize_ncu.py); None if there is no capture."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob("*_traffic.json")):
+        try:
+            d = json.loads(f.read_text())
+        except (OSError, ValueError):
+            continue
+        if kernel in d:
+            best = d[kernel].get("dram_bytes")
+    return best
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,7 +172,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=512)
     ap.add_argument("--pool", type=int, default=32)
-    ap.add_argument("--slots", type=int, default=4)
+    ap.add_argument("--slots", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -298,7 +312,7 @@ def main():
     if dom:
         d = hbm_kernels[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": d["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": d["frac"], "traffic": ncu_traffic(dom), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": d["alg_bytes"], "avg_launch_us": d["avg_us"]}
 
     cpu_baseline = None
@@ -344,7 +358,7 @@ def main():
             "keypoints_per_frame": float(np.mean(counts)),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e / args.steps},
-            "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e),
+            "gpu_launches": int(launches) * world, "gpu_launches_e2e": int(launches_e) * world,
             "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))

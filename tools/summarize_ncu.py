@@ -2,7 +2,7 @@
 """Turns ncu captures brought back in gpurun_out/ into the tracked summaries under profiles/.
 
   python tools/summarize_ncu.py r01
-reads gpurun_out/prof_*.ncu-rep (ncu --set full, one launch each) and gpurun_out/launches_<tag>.csv
+reads gpurun_out/prof_<tag>_*.ncu-rep (ncu --set full, one launch each) and gpurun_out/launches_<tag>.csv
 (ncu --metrics gpu__time_duration.sum) and writes profiles/<tag>_<kernel>.csv (selected raw metrics),
 profiles/<tag>_launches.csv (per-launch device times) and profiles/<tag>_summary.md.
 """
@@ -29,19 +29,28 @@ KEYS = [
 ]
 STALLS = "smsp__average_warps_issue_stalled_"
 
+def to_bytes(val, unit):
+    v = float(val.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+# bench.py kernel name of each capture (bench.py reads <tag>_traffic.json for roofline.traffic)
+BENCH_NAME = {"blur_dog_o0": "blur_dog_down_o0", "find_points_o0": "find_points_o0", "orient_desc": "orient_desc",
+              "match_tc": "match_tc"}
+traffic = {}
 PROF.mkdir(exist_ok=True)
 lines = [f"# ncu summaries, tag {tag}", "",
          "Captured on a B200 with `ncu --set full --clock-control none --import-source on` (one launch per kernel,",
          "octave 0 of a 1080p frame of the bench workload; cold caches, serialised) and",
          "`ncu --metrics gpu__time_duration.sum --clock-control none` (launch list).  Numbers taken under a profiler are",
          "not bench values; they explain them.", ""]
-for rep in sorted(OUT.glob("prof_*.ncu-rep")):
+for rep in sorted(OUT.glob(f"prof_{tag}_*.ncu-rep")):
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     if len(rows) < 3:
         continue
     hdr, units, vals = rows[0], rows[1], rows[2]
-    name = rep.stem.replace("prof_", "")
+    name = rep.stem.replace(f"prof_{tag}_", "")
     kname = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else name
     sel = [(k, vals[hdr.index(k)], units[hdr.index(k)]) for k in KEYS if k in hdr]
     stalls = sorted(((float(vals[i]), h[len(STALLS):].replace("_per_issue_active.ratio", "")) for i, h in enumerate(hdr)
@@ -52,13 +61,22 @@ for rep in sorted(OUT.glob("prof_*.ncu-rep")):
         wr.writerows(sel)
         wr.writerows((STALLS + s + "_per_issue_active.ratio", f"{v:.4f}", "") for v, s in stalls)
     d = {k: v for k, v, _ in sel}
+    ud = {k: u for k, _, u in sel}
+    if "dram__bytes_read.sum" in d:
+        traffic[BENCH_NAME.get(name, name)] = {
+            "dram_bytes": to_bytes(d["dram__bytes_read.sum"], ud["dram__bytes_read.sum"]) +
+                          to_bytes(d["dram__bytes_write.sum"], ud["dram__bytes_write.sum"]),
+            "dram_bytes_read": to_bytes(d["dram__bytes_read.sum"], ud["dram__bytes_read.sum"]),
+            "dram_bytes_write": to_bytes(d["dram__bytes_write.sum"], ud["dram__bytes_write.sum"]),
+            "capture": rep.name, "note": "one launch under ncu --set full (cache control: flush before the launch)"}
     dur_us = float(d.get("gpu__time_duration.sum", "nan").replace(",", ""))
     unit = dict((k, u) for k, _, u in sel).get("gpu__time_duration.sum", "")
     if unit == "ns":
         dur_us /= 1000.0
     rd, wrb = d.get("dram__bytes_read.sum", "?"), d.get("dram__bytes_write.sum", "?")
     lines += [f"## {name}", "", f"`{kname[:110]}`", "",
-              f"* duration {dur_us:.2f} us; DRAM read {rd} / write {wrb} ({dict((k,u) for k,_,u in sel).get('dram__bytes_read.sum','')}); "
+              f"* duration {dur_us:.2f} us; DRAM read {traffic[BENCH_NAME.get(name, name)]['dram_bytes_read'] / 1e6:.2f} MB / "
+              f"write {traffic[BENCH_NAME.get(name, name)]['dram_bytes_write'] / 1e6:.2f} MB; "
               f"registers {d.get('launch__registers_per_thread')}, grid {d.get('launch__grid_size')} x {d.get('launch__block_size')}",
               f"* issue active {d.get('smsp__issue_active.avg.pct_of_peak_sustained_active')} %, FMA pipe "
               f"{d.get('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active')} %, ALU pipe "
@@ -78,12 +96,14 @@ if lf.exists():
         data = rows[start + 1:]
         for r in data:
             wr.writerow([r[ik].split("(")[0], r[ig], r[ib], r[iv]])
-    frame = data[-12:]
+    frame = data[-11:]    # 5 blur_dog + 5 find_points + orient_desc (the result download is a copy-engine transfer)
     tot = sum(float(r[iv].replace(",", "")) for r in frame)
     lines += ["## launch list (last frame of the capture)", "", "| kernel | grid | ns | share |", "|---|---|---|---|"]
     for r in frame:
         ns = float(r[iv].replace(",", ""))
         lines.append(f"| {r[ik].split('(')[0]} | {r[ig]} | {ns:.0f} | {100*ns/tot:.1f} % |")
     lines += ["", f"sum {tot/1000:.1f} us per 1080p frame (serialised, cold cache)", ""]
+import json
+(PROF / f"{tag}_traffic.json").write_text(json.dumps(traffic, indent=1))
 (PROF / f"{tag}_summary.md").write_text("\n".join(lines))
 print("\n".join(lines))
