@@ -36,3 +36,23 @@ def test_main_cpp_style_pipeline(workdir):
     assert r["head_pts"] == orc_n
     assert abs(r["desc_norm2"] - 1.0) < 1e-3 and abs(r["rootsift_norm2"] - 1.0) < 1e-3
     assert abs(r["half00"] - float(O.scale_down(a)[0, 0])) < 1e-6
+
+
+REFTESTS = ROOT / "build" / "csb_ref_tests"
+
+
+@pytest.mark.skipif(not REFTESTS.exists(), reason="build/csb_ref_tests not built (make demo)")
+def test_reference_test_suite_restated_in_cpp(workdir):
+    """test/test.cpp (Matching.*) and test/detector.cpp (Detector.DetectorCUSIFTTest) of the reference,
+    restated in C++ on the drop-in headers + extras/debug.h readers, against the reference's goldens."""
+    g1, _ = PU.golden_frames()
+    raw = workdir / "gray1.f32"
+    g1.astype(np.float32).tofile(raw)
+    out = subprocess.run([str(REFTESTS), str(PU.GOLDEN), str(raw)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.stdout[-500:], out.stderr[-3000:])
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["nn_checked"] == 326 and r["nn_equal"] == 326      # test.cpp:37-40
+    assert r["ratio_matches"] == 340                            # test.cpp:55
+    assert r["det_pts"] == 4096 and r["det_rows"] == 4096       # detector.cpp:68
+    assert r["det_found"] == 4096 and r["det_found_abs"] == 4096
+    assert r["failed"] == 0
