@@ -58,6 +58,9 @@ SIGNATURES = {
     "csb_extract_host": (_i, [_vp, _vp, _i, _i, C.POINTER(CsbParams), _vp, _i, _vp, _ip]),
     "csb_extract_batch": (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i, _i, C.POINTER(CsbParams), C.POINTER(_vp),
                                 C.POINTER(_vp), _i, _ip]),
+    "csb_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),
+    "csb_extract_batch_u8": (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i, _i, C.POINTER(CsbParams), C.POINTER(_vp),
+                                   C.POINTER(_vp), _i, _ip]),
     "csb_scale_down": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     "csb_rootsift": (_i, [_vp, _vp, _i]),
     "csb_match": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),

@@ -203,6 +203,31 @@ class Context:
                     "csb_extract_batch")
         return counts
 
+    def extract_batch_u8(self, h_imgs, w: int, h: int, stride: int, preblur: bool, params: CsbParams, d_sifts, h_sifts,
+                         max_pts: int) -> np.ndarray:
+        """csb_extract_batch_u8 over lists of raw host pointers to 8-bit frames. Returns the per-frame counts."""
+        n = len(h_imgs)
+        imgs_arr = (C.c_void_p * n)(*h_imgs)
+        ds_arr = (C.c_void_p * n)(*d_sifts)
+        hs_arr = (C.c_void_p * n)(*h_sifts) if h_sifts is not None else None
+        counts = np.zeros(n, np.int32)
+        self._check(self._L.csb_extract_batch_u8(self.h, n, imgs_arr, w, h, stride, int(preblur), C.byref(params), ds_arr,
+                                                 hs_arr, max_pts, counts.ctypes.data_as(C.POINTER(C.c_int))),
+                    "csb_extract_batch_u8")
+        return counts
+
+    def ingest_u8(self, img: np.ndarray, preblur: bool) -> np.ndarray:
+        """csb_ingest_u8 of a host uint8 frame; returns the fp32 device image downloaded again."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        pitch = align_up(w, 128)
+        d_dst = self.alloc(4 * pitch * h)
+        try:
+            self._check(self._L.csb_ingest_u8(self.h, img.ctypes.data, 1, w, h, w, int(preblur), d_dst, pitch), "csb_ingest_u8")
+            return self.download_image(d_dst, pitch, w, h)
+        finally:
+            self.free(d_dst)
+
     def scale_down(self, img: np.ndarray) -> np.ndarray:
         img = np.ascontiguousarray(img, np.float32)
         h, w = img.shape

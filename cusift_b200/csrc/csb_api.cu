@@ -47,6 +47,8 @@ struct Slot {
   float *arena = nullptr;
   size_t arena_bytes = 0;
   float *img0 = nullptr;   // upload target for host frames
+  unsigned char *u8 = nullptr;            // device staging for 8-bit frames (csb_extract_batch_u8)
+  size_t u8_cap = 0;
   Octave oct[CSB_MAX_OCTAVES];
   std::vector<TexCacheEntry> tex_cache;   // textures over caller-owned octave-0 frames
   unsigned int *d_counter = nullptr;
@@ -272,6 +274,15 @@ int slot_tex0(csb_ctx *ctx, Slot *s, const float *ptr, int w, int h, int pitch, 
   s->tex_cache.push_back(e);
   *out = e.tex;
   return 0;
+}
+
+// cv::getGaussianKernel(3, 0.5, CV_32F): exp in double, float taps, float taps scaled by 1/sum (double)
+void preblur_kernel(float *k0, float *k1) {
+  const double sigma = 0.5, scale2x = -0.5 / (sigma * sigma);
+  const float c = (float)exp(scale2x * 0.0), sd = (float)exp(scale2x * 1.0);
+  const double inv = 1.0 / ((double)sd + (double)c + (double)sd);
+  *k0 = (float)((double)c * inv);
+  *k1 = (float)((double)sd * inv);
 }
 
 // ---- host-side constants, restated verbatim from the reference -----------------
@@ -553,6 +564,7 @@ void csb_ctx_destroy(csb_ctx *ctx) {
     for (ProfRec &r : s->prof_free) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (s->d_counter) cudaFree(s->d_counter);
     if (s->d_oct) cudaFree(s->d_oct);
+    if (s->u8) cudaFree(s->u8);
     if (s->h_count) cudaFreeHost(s->h_count);
     if (s->ev_count) cudaEventDestroy(s->ev_count);
     if (s->h_stage) cudaFreeHost(s->h_stage);
@@ -702,6 +714,79 @@ int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int 
       return rc;
     // two-stage pipeline: the frame queued n_slots/2 iterations ago moves on to its download while the
     // younger frames keep the SMs busy
+    const int lag = ctx->n_slots / 2;
+    if (f >= lag && ctx->slots[(f - lag) % ctx->n_slots].user_h && (rc = start_copy(ctx, &ctx->slots[(f - lag) % ctx->n_slots])))
+      return rc;
+  }
+  for (int i = 0; i < ctx->n_slots; i++)
+    if ((rc = finalize_frame(ctx, &ctx->slots[i]))) return rc;
+  return 0;
+}
+
+int csb_ingest_u8(csb_ctx *ctx, const unsigned char *src, int src_on_host, int w, int h, int stride, int preblur,
+                  float *d_dst, int dst_pitch_floats) {
+  if (!ctx || !src || !d_dst || w < 1 || h < 1 || stride < w || dst_pitch_floats < w)
+    return fail(ctx, CSB_E_INVALID, "csb_ingest_u8: bad argument");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  int rc = finalize_frame(ctx, s);
+  if (rc) return rc;
+  const unsigned char *d_src = src;
+  int d_stride = stride;
+  if (src_on_host) {
+    const size_t need = (size_t)w * h;
+    if (s->u8_cap < need) {
+      if (s->u8) cudaFree(s->u8);
+      s->u8 = nullptr; s->u8_cap = 0;
+      CSB_CHECK(ctx, cudaMalloc((void **)&s->u8, need));
+      s->u8_cap = need;
+    }
+    CSB_CHECK(ctx, cudaMemcpy2DAsync(s->u8, w, src, stride, w, h, cudaMemcpyHostToDevice, s->stream));
+    d_src = s->u8;
+    d_stride = w;
+  }
+  float k0, k1;
+  preblur_kernel(&k0, &k1);
+  {
+    LaunchScope ls(ctx, s, "ingest_u8");
+    launch_ingest_u8(d_src, d_stride, w, h, d_dst, dst_pitch_floats, preblur, k0, k1, s->stream);
+  }
+  CSB_CHECK(ctx, cudaGetLastError());
+  CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+  if (ctx->profile) prof_collect(ctx, s);
+  return 0;
+}
+
+int csb_extract_batch_u8(csb_ctx *ctx, int n_frames, const unsigned char *const *h_imgs, int w, int h, int stride,
+                         int preblur, const csb_params *p, void *const *d_sifts, void *const *h_sifts, int max_pts,
+                         int *num_pts) {
+  int rc = check_params(ctx, w, h, p, max_pts);
+  if (rc) return rc;
+  if (n_frames < 0 || !h_imgs || !d_sifts || !num_pts || stride < w)
+    return fail(ctx, CSB_E_INVALID, "csb_extract_batch_u8: bad argument");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  float k0, k1;
+  preblur_kernel(&k0, &k1);
+  for (int f = 0; f < n_frames; f++) {
+    Slot *s = &ctx->slots[f % ctx->n_slots];
+    if ((rc = finalize_frame(ctx, s))) return rc;
+    if ((rc = slot_prepare(ctx, s, w, h, p->num_octaves))) return rc;
+    const size_t need = (size_t)w * h;
+    if (s->u8_cap < need) {
+      if (s->u8) cudaFree(s->u8);
+      s->u8 = nullptr; s->u8_cap = 0;
+      CSB_CHECK(ctx, cudaMalloc((void **)&s->u8, need));
+      s->u8_cap = need;
+    }
+    const int pitch = s->oct[0].pitch;
+    CSB_CHECK(ctx, cudaMemcpy2DAsync(s->u8, w, h_imgs[f], stride, w, h, cudaMemcpyHostToDevice, s->stream));
+    {
+      LaunchScope ls(ctx, s, "ingest_u8");
+      launch_ingest_u8(s->u8, w, w, h, s->img0, pitch, preblur, k0, k1, s->stream);
+    }
+    void *hs = h_sifts ? h_sifts[f] : nullptr;
+    if ((rc = enqueue_frame(ctx, s, s->img0, w, h, pitch, p, (csb_sift_point *)d_sifts[f], max_pts, hs, &num_pts[f])))
+      return rc;
     const int lag = ctx->n_slots / 2;
     if (f >= lag && ctx->slots[(f - lag) % ctx->n_slots].user_h && (rc = start_copy(ctx, &ctx->slots[(f - lag) % ctx->n_slots])))
       return rc;

@@ -42,6 +42,8 @@ void launch_find_points(const float *dog, int w, int h, int pitch, const Extrema
                         int *d_oct, unsigned int *d_counter, int max_pts, int sm_count, cudaStream_t st);
 void launch_orient_desc(const OctaveTexSet &texs, int n_oct, csb_sift_point *d_sift, const int *d_oct,
                         const unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st);
+void launch_ingest_u8(const unsigned char *d_src, int stride, int w, int h, float *d_dst, int pitch, int preblur, float k0,
+                      float k1, cudaStream_t st);
 void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st);
 void launch_match(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
                   cudaStream_t st);

@@ -118,6 +118,19 @@ int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int 
                       int pitch_floats, const csb_params *p, void *const *d_sifts, void *const *h_sifts,
                       int max_pts, int *num_pts);
 
+/* Frame ingest (reference: the host-side preparation in main.cpp:301-318).
+ * csb_ingest_u8: 8-bit grey frame (host or device memory, `stride` bytes per row) -> pitched fp32
+ * device image; preblur != 0 applies cv::GaussianBlur(Size(3,3), 0.5) (main.cpp:308-309), bit-identical
+ * to OpenCV 4's CV_32F result where OpenCV runs its SIMD loop body (within 1 ulp on its scalar row tails).  Synchronous. */
+int csb_ingest_u8(csb_ctx *ctx, const unsigned char *src, int src_on_host, int w, int h, int stride, int preblur,
+                  float *d_dst, int dst_pitch_floats);
+/* csb_extract_batch over 8-bit HOST frames: per frame one w*h-byte upload (4x less PCIe traffic than
+ * the fp32 frame), conversion (+ optional pre-blur) on the device into the slot's octave-0 image, then
+ * the same pipeline and result delivery as csb_extract_batch. */
+int csb_extract_batch_u8(csb_ctx *ctx, int n_frames, const unsigned char *const *h_imgs, int w, int h, int stride,
+                         int preblur, const csb_params *p, void *const *d_sifts, void *const *h_sifts, int max_pts,
+                         int *num_pts);
+
 /* ScaleDown(cuImage &res, cuImage &src, 0.5f) (cuSIFT.h:76, cuSIFT.cu:313-353):
  * dst is (w/2) x (h/2).  Stores are guarded (the reference's are not). */
 int csb_scale_down(csb_ctx *ctx, const float *d_src, int w, int h, int src_pitch, float *d_dst, int dst_pitch);

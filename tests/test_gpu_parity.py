@@ -518,3 +518,39 @@ def test_extrema_dense_fallback_matches_list_path(frames, tmp_path):
     assert len(a) == len(b) and len(a) > 1000
     for f in ("coords2D", "scale", "sharpness", "edgeness", "orientation", "subsampling"):
         assert np.array_equal(a[f], b[f]), f
+
+
+# ------------------------------------------------------------------- ingest ---
+@pytest.mark.parametrize("shape", [(480, 640), (67, 121), (1, 5), (3, 1)])
+def test_ingest_u8_matches_opencv_bit_for_bit(gpu_ctx, shape):
+    """main.cpp:301-309: imread(.,0).convertTo(CV_32FC1) then GaussianBlur(Size(3,3), 0.5), done on the device."""
+    import cv2
+    u8 = np.random.default_rng(5).integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(gpu_ctx.ingest_u8(u8, False), u8.astype(np.float32))
+    want = cv2.GaussianBlur(u8.astype(np.float32), (3, 3), 0.5)
+    got = gpu_ctx.ingest_u8(u8, True)
+    if shape[1] % 16 == 0:
+        assert np.array_equal(got, want.reshape(shape))        # OpenCV's SIMD body: fma(c,k0,(l+r)k1) / fma(u+d,k1,c k0)
+    else:                                                       # its scalar row tails round differently (not fused)
+        np.testing.assert_allclose(got, want.reshape(shape), rtol=2.5e-7, atol=0)
+
+
+def test_extract_batch_u8_equals_float_path(gpu_ctx, frames):
+    """8-bit upload + device pre-blur gives the same keypoints as the reference flow (host convertTo +
+    GaussianBlur + float upload), bit for bit."""
+    g1, g2 = PU.golden_frames()
+    p = csb.make_params(5, 0.0, 0.5)
+    imgs = [np.ascontiguousarray(g, np.uint8) for g in (g1, g2, g1)]
+    pins = [csb.PinnedArray(8192) for _ in imgs]
+    ds = [gpu_ctx.alloc(588 * 8192) for _ in imgs]
+    try:
+        cnt = gpu_ctx.extract_batch_u8([im.ctypes.data for im in imgs], 640, 480, 640, True, p, ds, [q.ptr for q in pins], 8192)
+        for k, im in enumerate(imgs):
+            want = PU.canonical_sort(gpu_ctx.extract(PU.preblur(im), p, max_pts=8192))
+            got = PU.canonical_sort(pins[k].array[: cnt[k]].copy())
+            assert len(got) == len(want) > 1000
+            for f in ("coords2D", "scale", "sharpness", "edgeness", "orientation", "data"):
+                assert np.array_equal(got[f], want[f]), (k, f)
+    finally:
+        for d in ds:
+            gpu_ctx.free(d)
