@@ -75,29 +75,53 @@ struct Refined {
   float x, y, scale, sharp, edge;
 };
 
-// cuSIFT_D.cu:474-522 in the reference's evaluation order.  Returns false when the
-// edge test rejects the candidate.
-__device__ __forceinline__ bool refine(const float *__restrict__ dog, size_t plane, int pitch,
-                                       const ExtremaParams &P, int x, int y, int sc, Refined &o) {
-  const float *p1 = dog + (size_t)(sc + 1) * plane + (size_t)y * pitch + x;
-  const float *p0 = p1 - plane, *p2 = p1 + plane;
-  const float val = p1[0];
+// Strict 26-neighbour test (cuSIFT_D.cu:450-470) + refinement (cuSIFT_D.cu:474-522) of one flagged pixel.
+// All 27 values are loaded up front as independent loads (ONE memory latency; a short-circuit chain of
+// compare-then-load cost up to 26 dependent L2 round trips and was 30 % of the kernel's stall samples),
+// then both steps run from registers in the reference's evaluation order.
+__device__ __forceinline__ bool verify_refine(const float *__restrict__ dog, size_t plane, int pitch,
+                                              const ExtremaParams &P, int x, int y, int sc, Refined &o) {
+  const float *c = dog + (size_t)(sc + 1) * plane + (size_t)y * pitch + x;
+  float n[3][3][3];   // [plane - sc][dy + 1][dx + 1]
+#pragma unroll
+  for (int p = 0; p < 3; p++)
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++) n[p][dy][dx] = c[(ptrdiff_t)(p - 1) * (ptrdiff_t)plane + (dy - 1) * pitch + (dx - 1)];
+  const float val = n[1][1][1];
+  const bool isMax = val > P.thresh, isMin = val < -P.thresh;
+  bool ok = isMax || isMin;
+#pragma unroll
+  for (int p = 0; p < 3; p++)
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++)
+        if (!(p == 1 && dy == 1 && dx == 1)) ok &= isMax ? (val > n[p][dy][dx]) : (val < n[p][dy][dx]);
+  if (!ok) return false;
+  // names as in refine(): p0 = plane below (sc), p1 = centre plane, p2 = plane above
+#define N0(dy, dx) n[0][(dy) + 1][(dx) + 1]
+#define N1(dy, dx) n[1][(dy) + 1][(dx) + 1]
+#define N2(dy, dx) n[2][(dy) + 1][(dx) + 1]
   const float two = __fadd_rn(val, val);
-  const float dxx = __fsub_rn(__fsub_rn(two, p1[-1]), p1[1]);
-  const float dyy = __fsub_rn(__fsub_rn(two, p1[-pitch]), p1[pitch]);
-  const float dxy =
-      __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(p1[pitch + 1], p1[-pitch - 1]), p1[-pitch + 1]), p1[pitch - 1]));
+  const float dxx = __fsub_rn(__fsub_rn(two, N1(0, -1)), N1(0, 1));
+  const float dyy = __fsub_rn(__fsub_rn(two, N1(-1, 0)), N1(1, 0));
+  const float dxy = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(N1(1, 1), N1(-1, -1)), N1(-1, 1)), N1(1, -1)));
   const float tra = __fadd_rn(dxx, dyy);
   const float det = __fmaf_rn(dxx, dyy, -__fmul_rn(dxy, dxy));
   const float tra2 = __fmul_rn(tra, tra);
   if (!(tra2 < __fmul_rn(det, P.edge_limit))) return false;
   const float edge = __fdividef(tra2, det);
-  const float dx = __fmul_rn(0.5f, __fsub_rn(p1[1], p1[-1]));
-  const float dy = __fmul_rn(0.5f, __fsub_rn(p1[pitch], p1[-pitch]));
-  const float ds = __fmul_rn(0.5f, __fsub_rn(p0[0], p2[0]));
-  const float dss = __fsub_rn(__fsub_rn(two, p2[0]), p0[0]);
-  const float dxs = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(p2[1], p0[-1]), p0[1]), p2[-1]));
-  const float dys = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(p2[pitch], p0[-pitch]), p2[-pitch]), p0[pitch]));
+  const float dx = __fmul_rn(0.5f, __fsub_rn(N1(0, 1), N1(0, -1)));
+  const float dy = __fmul_rn(0.5f, __fsub_rn(N1(1, 0), N1(-1, 0)));
+  const float ds = __fmul_rn(0.5f, __fsub_rn(N0(0, 0), N2(0, 0)));
+  const float dss = __fsub_rn(__fsub_rn(two, N2(0, 0)), N0(0, 0));
+  const float dxs = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(N2(0, 1), N0(0, -1)), N0(0, 1)), N2(0, -1)));
+  const float dys = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(N2(1, 0), N0(-1, 0)), N2(-1, 0)), N0(1, 0)));
+#undef N0
+#undef N1
+#undef N2
   const float idxx = __fmaf_rn(dyy, dss, -__fmul_rn(dys, dys));
   const float idxy = __fmaf_rn(dxs, dys, -__fmul_rn(dxy, dss));
   const float idxs = __fmaf_rn(dxy, dys, -__fmul_rn(dyy, dxs));
@@ -163,30 +187,6 @@ __device__ __forceinline__ void emit_warp(bool emit, const Refined &r, const Ext
     const unsigned int idx = base + __popc(m & ((1u << lane) - 1u));
     if (idx < (unsigned int)max_pts) store_point(d_sift, d_oct, idx, r, P);
   }
-}
-
-// Reference candidate rule (cuSIFT_D.cu:450-470): strictly beyond all 26 neighbours.
-__device__ __forceinline__ bool strict_extremum(const float *__restrict__ dog, size_t plane, int pitch, int sc, int x,
-                                                int y, float thresh) {
-  const float *c = dog + (size_t)(sc + 1) * plane + (size_t)y * pitch + x;
-  const float v = c[0];
-  const bool isMax = v > thresh, isMin = v < -thresh;
-  if (!isMax && !isMin) return false;
-  bool ok = true;
-#pragma unroll
-  for (int p = -1; p <= 1; p++) {
-    const float *q = c + (ptrdiff_t)p * (ptrdiff_t)plane;
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++) {
-#pragma unroll
-      for (int dx = -1; dx <= 1; dx++) {
-        if (p == 0 && dy == 0 && dx == 0) continue;
-        const float u = q[dy * pitch + dx];
-        ok = ok && (isMax ? (v > u) : (v < u));
-      }
-    }
-  }
-  return ok;
 }
 
 __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const fl
           ex = (int)blockIdx.x * XT_TW + (int)(en & 0x7fu), ey = y0 + (int)((en >> 7) & 0x3fu), es = (int)(en >> 13);
         }
         const bool inner = ex >= 1 && ex <= w - 2 && ey >= 1 && ey <= h - 2;
-        if (inner && strict_extremum(dog, plane, pitch, es, ex, ey, P.thresh)) emit = refine(dog, plane, pitch, P, ex, ey, es, r);
+        if (inner) emit = verify_refine(dog, plane, pitch, P, ex, ey, es, r);
       }
       emit_warp(emit, r, P, d_sift, d_oct, counter, max_pts, lane);
     }
