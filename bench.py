@@ -330,8 +330,8 @@ def main():
         if name.startswith("blur_dog") and name[-1].isdigit():
             o = int(name[-1])
             alg = OCT_PX[o] * (BYTES_PYR if name.startswith("blur_dog_down") else BYTES_PYR_LAST)
-        elif name.startswith("find_points") and name[-1].isdigit():
-            alg = OCT_PX[int(name[-1])] * BYTES_EXT
+        elif name == "find_points":       # one launch covers every octave
+            alg = sum(OCT_PX) * BYTES_EXT
         if alg:
             ent["alg_bytes"] = alg
             ent["achieved_gbs"] = round(alg / (avg_ms * 1e-3) / 1e9, 1)

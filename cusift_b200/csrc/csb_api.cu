@@ -52,8 +52,8 @@ struct Slot {
   Octave oct[CSB_MAX_OCTAVES];
   std::vector<TexCacheEntry> tex_cache;   // textures over caller-owned octave-0 frames
   unsigned int *d_counter = nullptr;
-  int *d_oct = nullptr;
-  int oct_cap = 0;
+  KpStage *d_stage = nullptr;             // per-octave keypoint lists between k_find_points and k_orient_desc
+  size_t stage_pts = 0;                   // capacity: octaves * max_pts entries
   int *h_count = nullptr;                 // pinned: keypoints found by the frame in flight
   csb_sift_point *h_stage = nullptr;      // pinned + mapped staging for pageable destinations
   size_t stage_cap = 0;
@@ -316,7 +316,7 @@ void laplace_weights(float initBlur, DogWeights *W) {   // cuSIFT.cu:239-240,399
     for (int j = 0; j < 5; j++) W->k[i][j] = kernel[16 * i + j];
 }
 
-void extrema_params(const csb_params *p, int octave, float subsampling, ExtremaParams *E) {   // cuSIFT.cu:239-247,424-444
+void extrema_params(const csb_params *p, ExtremaParams *E) {   // cuSIFT.cu:239-247,424-444 (the same for every octave)
   const float baseBlur = pow(2.0f, -1.0f / CSB_NUM_SCALES);
   const float diffScaleL = pow(2.0f, 1.0f / CSB_NUM_SCALES);
   const double sigma = baseBlur * diffScaleL;
@@ -330,8 +330,7 @@ void extrema_params(const csb_params *p, int octave, float subsampling, ExtremaP
   E->thresh = p->peak_thresh;
   E->edge_limit = p->edge_thresh;
   E->factor = factor;
-  E->subsampling = subsampling;
-  E->octave = octave;
+  E->n_oct = 0;
 }
 
 // Enqueues one frame on a slot.  d_img0/pitch0: octave-0 image on the device.
@@ -341,11 +340,11 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
   cudaStream_t st = s->stream;
   const double t_enq = ctx->trace ? host_now_ms() : 0.0;
 
-  if (s->oct_cap < max_pts) {
-    if (s->d_oct) cudaFree(s->d_oct);
-    s->d_oct = nullptr;
-    CSB_CHECK(ctx, cudaMalloc((void **)&s->d_oct, sizeof(int) * (size_t)max_pts));
-    s->oct_cap = max_pts;
+  if (s->stage_pts < (size_t)n_oct * max_pts) {
+    if (s->d_stage) cudaFree(s->d_stage);
+    s->d_stage = nullptr; s->stage_pts = 0;
+    CSB_CHECK(ctx, cudaMalloc((void **)&s->d_stage, sizeof(KpStage) * (size_t)n_oct * max_pts));
+    s->stage_pts = (size_t)n_oct * max_pts;
   }
 
   // result destination: directly into the caller's buffer when it is page-locked, else via pinned staging
@@ -407,9 +406,6 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
                                                     "blur_dog_down_o6", "blur_dog_down_o7"};
   static const char *kNameBlur[CSB_MAX_OCTAVES] = {"blur_dog_o0", "blur_dog_o1", "blur_dog_o2", "blur_dog_o3",
                                                    "blur_dog_o4", "blur_dog_o5", "blur_dog_o6", "blur_dog_o7"};
-  static const char *kNameFind[CSB_MAX_OCTAVES] = {"find_points_o0", "find_points_o1", "find_points_o2",
-                                                   "find_points_o3", "find_points_o4", "find_points_o5",
-                                                   "find_points_o6", "find_points_o7"};
   for (int o = 0; o < n_oct; o++) {
     const bool need_down = (o + 1 < n_oct);
     DogWeights W;
@@ -429,19 +425,25 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
       }
     }
   }
-  // extrema: coarse -> fine, the reference's output order (cuSIFT.cu:181-196)
-  for (int o = n_oct - 1; o >= 0; o--) {
-    if (!active[o]) continue;
+  // extrema of all active octaves in ONE launch (octave 0 first: it owns most CTAs); every octave fills
+  // its own list, k_orient_desc lays them out coarse -> fine, the reference's order (cuSIFT.cu:181-196)
+  {
     ExtremaParams E;
-    extrema_params(p, o, subs[o], &E);
-    LaunchScope ls(ctx, s, kNameFind[o]);
-    launch_find_points(oct[o].dog, oct[o].w, oct[o].h, oct[o].pitch, E, d_sift, s->d_oct, s->d_counter, max_pts, ctx->sm_count, st);
+    extrema_params(p, &E);
+    for (int o = 0; o < n_oct; o++) {
+      if (!active[o]) continue;
+      ExtremaOctave &X = E.oct[E.n_oct++];
+      X.dog = oct[o].dog; X.w = oct[o].w; X.h = oct[o].h; X.pitch = oct[o].pitch; X.octave = o;
+    }
+    const int n_ctas = plan_find_points(&E, ctx->sm_count);
+    LaunchScope ls(ctx, s, "find_points");
+    launch_find_points(E, n_ctas, s->d_stage, s->d_counter, max_pts, st);
   }
   {
     OctaveTexSet T;
     for (int o = 0; o < CSB_MAX_OCTAVES; o++) T.tex[o] = (o < n_oct) ? oct[o].tex : 0;
     LaunchScope ls(ctx, s, "orient_desc");
-    launch_orient_desc(T, n_oct, d_sift, s->d_oct, s->d_counter, max_pts, p->rootsift, ctx->sm_count, st);
+    launch_orient_desc(T, n_oct, subs, s->d_stage, d_sift, s->d_counter, max_pts, p->rootsift, ctx->sm_count, st);
   }
   // The count comes back first; the SiftPoint array follows as ONE exact-size copy-engine transfer
   // once the host knows it (start_copy).  A kernel storing into mapped host memory would save that
@@ -563,7 +565,7 @@ void csb_ctx_destroy(csb_ctx *ctx) {
     for (ProfRec &r : s->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (ProfRec &r : s->prof_free) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (s->d_counter) cudaFree(s->d_counter);
-    if (s->d_oct) cudaFree(s->d_oct);
+    if (s->d_stage) cudaFree(s->d_stage);
     if (s->u8) cudaFree(s->u8);
     if (s->h_count) cudaFreeHost(s->h_count);
     if (s->ev_count) cudaEventDestroy(s->ev_count);

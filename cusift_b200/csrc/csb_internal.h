@@ -16,15 +16,31 @@ struct DogWeights {
   float k[CSB_NUM_LEVELS][5];
 };
 
-// Parameters of the extrema kernel (d_Threshold/d_EdgeLimit/d_Scales/d_Factor in
-// the reference, cuSIFT_D.cu:13-15, pushed per launch at cuSIFT.cu:441-444).
+// Keypoint as k_find_points leaves it: octave-pixel coordinates, before orientation / descriptor.
+// One list per octave (max_pts entries each) in slot-owned memory; k_orient_desc turns it into the
+// caller's SiftPoint array, coarse octaves first (the reference's order, cuSIFT.cu:181-196).
+struct KpStage {
+  float x, y, scale, sharp, edge;
+};
+
+// Parameters of the extrema kernel (d_Threshold/d_EdgeLimit/d_Scales/d_Factor in the reference,
+// cuSIFT_D.cu:13-15, pushed per launch at cuSIFT.cu:441-444).  ALL octaves of a frame go through
+// ONE launch: a CTA finds its octave from cta_begin.
+struct ExtremaOctave {
+  const float *dog;                // 7 DoG planes, plane stride pitch*h
+  int w, h, pitch;
+  int tiles_x;                     // CTAs per row band
+  int cta_begin;                   // first linear CTA index of this octave (octave 0 first: longest work first)
+  int octave;
+};
 struct ExtremaParams {
   float thresh;                    // peakThresh
   float edge_limit;                // edgeThresh
   float scales[CSB_NUM_SCALES];    // sigma * 2^(i/5)
   float factor;                    // 1/NUM_SCALES
-  float subsampling;               // of this octave
-  int octave;
+  int rows;                        // output rows per CTA (multiple of 3)
+  int n_oct;                       // entries used in oct[]
+  ExtremaOctave oct[CSB_MAX_OCTAVES];
 };
 
 // Per-octave view handed to the orientation/descriptor kernel.
@@ -38,10 +54,13 @@ void launch_scale_down(const float *src, int w, int h, int spitch, float *dst, i
 void launch_blur_dog(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, cudaStream_t st);
 void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next,
                           int npitch, const float k[3], cudaStream_t st);
-void launch_find_points(const float *dog, int w, int h, int pitch, const ExtremaParams &ep, csb_sift_point *d_sift,
-                        int *d_oct, unsigned int *d_counter, int max_pts, int sm_count, cudaStream_t st);
-void launch_orient_desc(const OctaveTexSet &texs, int n_oct, csb_sift_point *d_sift, const int *d_oct,
-                        const unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st);
+// fills ep.rows / tiles_x / cta_begin from the octave geometry already in ep.oct[]; returns the grid size
+int plan_find_points(ExtremaParams *ep, int sm_count);
+void launch_find_points(const ExtremaParams &ep, int n_ctas, KpStage *d_stage, unsigned int *d_counter, int max_pts,
+                        cudaStream_t st);
+// subs[o] = subsampling of octave o (multiplies coords2D / scale in the final record)
+void launch_orient_desc(const OctaveTexSet &texs, int n_oct, const float *subs, const KpStage *d_stage, csb_sift_point *d_sift,
+                        unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st);
 void launch_ingest_u8(const unsigned char *d_src, int stride, int w, int h, float *d_dst, int pitch, int preblur, float k0,
                       float k1, cudaStream_t st);
 void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st);

@@ -85,10 +85,15 @@ struct Grad {
   float dx, dy;
 };
 
+struct OctaveSubs {
+  float v[CSB_MAX_OCTAVES];
+};
+
 __global__ void __launch_bounds__(WARPS * 32, K3_MINB) k_orient_desc(const __grid_constant__ OctaveTexSet T,
+                                                            const __grid_constant__ OctaveSubs S,
+                                                            const KpStage *__restrict__ d_stage,
                                                             csb_sift_point *__restrict__ d_sift,
-                                                            const int *__restrict__ d_oct,
-                                                            const unsigned int *__restrict__ counter, int max_pts,
+                                                            unsigned int *__restrict__ counter, int max_pts,
                                                             int rootsift) {
   __shared__ __align__(16) float s_hist[WARPS][32 * 32];   // orientation: [bin][lane] private columns
   __shared__ float s_sm[WARPS][64];                         // reduced + smoothed orientation histogram
@@ -97,28 +102,36 @@ __global__ void __launch_bounds__(WARPS * 32, K3_MINB) k_orient_desc(const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *hist = s_hist[warp], *sm = s_sm[warp], *gauss = s_gauss[warp], *buf = s_buf[warp];
-  const unsigned int cnt = *counter;
-  const int n = (int)min(cnt, (unsigned int)max_pts);
   // descriptor sampling pattern: lane = half*16 + cell_y*4 + cell_x
   const int half = lane >> 4, cellx = lane & 3, celly = (lane >> 2) & 3;
   float *copy = buf + half * 16;                            // + cell + 32 * bin
 
-  // The list holds one contiguous run per octave, coarse to fine (k_find_points leaves the run ends in
-  // counter[1 + o]); blockIdx.y selects the run.  That makes the texture handle a function of a
-  // special register, i.e. provably warp-uniform: a handle looked up through d_oct[k] costs a
-  // divergence ("waterfall") loop around every one of the 48 texture fetches of a keypoint and keeps
-  // ptxas from batching them.
+  // k_find_points leaves one list per octave (counter[1 + o] entries, capped at max_pts); blockIdx.y
+  // selects the octave.  That makes the texture handle a function of a special register, i.e.
+  // provably warp-uniform: a handle looked up per keypoint costs a divergence ("waterfall") loop
+  // around every one of the 48 texture fetches of a keypoint and keeps ptxas from batching them.
+  // Output slot of entry i of octave o = (entries of all coarser octaves) + i: the reference's order,
+  // coarse octaves first (cuSIFT.cu:181-196), and the order in which max_pts truncates.
   const int o = blockIdx.y;
-  unsigned int run_start = 0;
-  for (int c = CSB_MAX_OCTAVES - 1; c > o; c--) run_start = max(run_start, counter[1 + c]);
-  const int start = (int)min(run_start, (unsigned int)n);
-  const int end = (int)min(max(run_start, counter[1 + o]), (unsigned int)n);
+  unsigned int before = 0, total = 0;
+  for (int c = CSB_MAX_OCTAVES - 1; c >= 0; c--) {
+    const unsigned int nc = min(counter[1 + c], (unsigned int)max_pts);
+    if (c > o) before += nc;
+    total += nc;
+  }
+  if (blockIdx.x == 0 && o == 0 && threadIdx.x == 0) counter[0] = total;   // keypoints found (host caps at max_pts)
+  const int n_o = (int)min(counter[1 + o], (unsigned int)max_pts);
+  const KpStage *__restrict__ stage = d_stage + (size_t)o * max_pts;
+  const float psub = S.v[o];
   const cudaTextureObject_t tex = T.tex[o];
   {
 #pragma unroll 1
-  for (int k = start + blockIdx.x * WARPS + warp; k < end; k += gridDim.x * WARPS) {
+  for (int i = blockIdx.x * WARPS + warp; i < n_o; i += gridDim.x * WARPS) {
+    const unsigned int k = before + (unsigned int)i;
+    if (k >= (unsigned int)max_pts) break;                  // later entries of this warp are beyond the cap too
     csb_sift_point *pt = d_sift + k;
-    const float px = pt->coords2D[0], py = pt->coords2D[1], pscale = pt->scale, psub = pt->subsampling;
+    const KpStage kp = stage[i];
+    const float px = kp.x, py = kp.y, pscale = kp.scale;
 
     // ---------------- orientation (cuSIFT_D.cu:319-396) ----------------
     const float i2sigma2 = __fdiv_rn(-1.0f, __fmul_rn(__fmul_rn(pscale, 4.5f), pscale));
@@ -304,11 +317,17 @@ __global__ void __launch_bounds__(WARPS * 32, K3_MINB) k_orient_desc(const __gri
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) pt->data[lane + 32 * j] = b[j];
-    if (lane == 0) {
-      pt->orientation = orient;
-      pt->coords2D[0] = __fmul_rn(px, psub);
-      pt->coords2D[1] = __fmul_rn(py, psub);
-      pt->scale = __fmul_rn(pscale, psub);
+    if (lane < 16) {   // the 76 header + 12 trailer bytes of the record, one word per lane
+      float v = 0.0f;                                        // score, ambiguity, match (int 0), match_*, empty[], coords3D[]
+      if (lane == 0) v = __fmul_rn(px, psub);                // coords2D, scale: octave -> frame pixels (cuSIFT_D.cu:292-296)
+      else if (lane == 1) v = __fmul_rn(py, psub);
+      else if (lane == 2) v = __fmul_rn(pscale, psub);
+      else if (lane == 3) v = kp.sharp;
+      else if (lane == 4) v = kp.edge;
+      else if (lane == 5) v = orient;
+      else if (lane == 12) v = psub;
+      reinterpret_cast<float *>(pt)[lane] = v;               // words 0..15 = fields up to empty[2]
+      if (lane < 3) pt->coords3D[lane] = 0.0f;
     }
     __syncwarp();
   }
@@ -338,14 +357,16 @@ __global__ void __launch_bounds__(128) k_rootsift(csb_sift_point *__restrict__ d
 
 }  // namespace
 
-void launch_orient_desc(const OctaveTexSet &texs, int n_oct, csb_sift_point *d_sift, const int *d_oct,
-                        const unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st) {
+void launch_orient_desc(const OctaveTexSet &texs, int n_oct, const float *subs, const KpStage *d_stage, csb_sift_point *d_sift,
+                        unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st) {
   int blocks = sm_count * K3_MINB;                // resident CTAs per SM (register budget, 26 KB shared each)
   const int need = (max_pts + WARPS - 1) / WARPS;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  // grid.y = octave, finest first: its run is by far the longest, the short runs fill the tail
-  k_orient_desc<<<dim3(blocks, n_oct), WARPS * 32, 0, st>>>(texs, d_sift, d_oct, d_counter, max_pts, rootsift);
+  OctaveSubs S;
+  for (int o = 0; o < CSB_MAX_OCTAVES; o++) S.v[o] = o < n_oct ? subs[o] : 0.0f;
+  // grid.y = octave, finest first: its list is by far the longest, the short ones fill the tail
+  k_orient_desc<<<dim3(blocks, n_oct), WARPS * 32, 0, st>>>(texs, S, d_stage, d_sift, d_counter, max_pts, rootsift);
 }
 
 void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st) {

@@ -147,61 +147,46 @@ __device__ __forceinline__ bool verify_refine(const float *__restrict__ dog, siz
   return true;
 }
 
-__device__ __forceinline__ void store_point(csb_sift_point *__restrict__ d_sift, int *__restrict__ d_oct,
-                                            unsigned int idx, const Refined &r, const ExtremaParams &P) {
-  csb_sift_point *o = d_sift + idx;
-  o->coords2D[0] = r.x;
-  o->coords2D[1] = r.y;
-  o->scale = r.scale;
-  o->sharpness = r.sharp;
-  o->edgeness = r.edge;
-  o->orientation = 0.f;
-  o->score = 0.f;
-  o->ambiguity = 0.f;
-  o->match = 0;
-  o->match_xpos = 0.f;
-  o->match_ypos = 0.f;
-  o->match_error = 0.f;
-  o->subsampling = P.subsampling;
-  o->empty[0] = o->empty[1] = o->empty[2] = 0.f;
-  o->coords3D[0] = o->coords3D[1] = o->coords3D[2] = 0.f;
-  d_oct[idx] = P.octave;
-}
-
-// Warp-ballot compaction of `emit` lanes into the global list (whole warp must call).
-__device__ __forceinline__ void emit_warp(bool emit, const Refined &r, const ExtremaParams &P,
-                                          csb_sift_point *__restrict__ d_sift, int *__restrict__ d_oct,
-                                          unsigned int *__restrict__ counter, int max_pts, int lane) {
+// Warp-ballot compaction of `emit` lanes into the octave's list (whole warp must call):
+// one global atomicAdd per warp on the octave's counter.
+__device__ __forceinline__ void emit_warp(bool emit, const Refined &r, KpStage *__restrict__ stage,
+                                          unsigned int *__restrict__ oct_counter, int max_pts, int lane) {
   const unsigned int m = __ballot_sync(FULL, emit);
   if (!m) return;
   const int leader = __ffs(m) - 1;
   unsigned int base = 0;
-  if (lane == leader) {
-    base = atomicAdd(counter, (unsigned int)__popc(m));
-    // counter[1 + octave] = end of this octave's run in the list (octaves are launched one after the
-    // other, so a run is contiguous): lets k_orient_desc pick its texture per run, warp-uniformly
-    atomicMax(counter + 1 + P.octave, base + (unsigned int)__popc(m));
-  }
+  if (lane == leader) base = atomicAdd(oct_counter, (unsigned int)__popc(m));
   base = __shfl_sync(FULL, base, leader);
   if (emit) {
     const unsigned int idx = base + __popc(m & ((1u << lane) - 1u));
-    if (idx < (unsigned int)max_pts) store_point(d_sift, d_oct, idx, r, P);
+    if (idx < (unsigned int)max_pts) stage[idx] = KpStage{r.x, r.y, r.scale, r.sharp, r.edge};
   }
 }
 
-__global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const float *__restrict__ dog, int w, int h, int pitch,
-                                                                  const __grid_constant__ ExtremaParams P,
-                                                                  csb_sift_point *__restrict__ d_sift,
-                                                                  int *__restrict__ d_oct,
-                                                                  unsigned int *__restrict__ counter, int max_pts,
-                                                                  int rows, int cap) {
+__global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const __grid_constant__ ExtremaParams P,
+                                                                        KpStage *__restrict__ d_stage,
+                                                                        unsigned int *__restrict__ counter, int max_pts,
+                                                                        int cap) {
   __shared__ unsigned int s_cnt;
   __shared__ unsigned short s_list[XT_CAP];   // local column | local row << 7 | scale << 13
 
+  // which octave does this CTA belong to?  (octave 0 owns the first, and by far the most, CTAs)
+  int oi = 0;
+#pragma unroll 1
+  for (int i = 1; i < P.n_oct; i++)
+    if ((int)blockIdx.x >= P.oct[i].cta_begin) oi = i;
+  const ExtremaOctave &O = P.oct[oi];
+  const float *__restrict__ dog = O.dog;
+  const int w = O.w, h = O.h, pitch = O.pitch, rows = P.rows;
+  const int local = (int)blockIdx.x - O.cta_begin;
+  const int bx = local % O.tiles_x, by = local / O.tiles_x;
+  KpStage *stage = d_stage + (size_t)O.octave * max_pts;
+  unsigned int *oct_counter = counter + 1 + O.octave;
+
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x = blockIdx.x * XT_TW + warp * XT_COLS - 1 + lane;
+  const int x = bx * XT_TW + warp * XT_COLS - 1 + lane;
   const int cx = clampi(x, 0, w - 1);
-  const int y0 = blockIdx.y * rows;
+  const int y0 = by * rows;
   const size_t plane = (size_t)pitch * h;
   // image-border pixels can never be strict extrema (their clamped neighbours include
   // the pixel itself, cuSIFT_D.cu:416,427-429); lanes 0 and 31 are halo columns
@@ -252,7 +237,7 @@ __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const fl
     const unsigned int big = hmax3(hmax3(vc[0][M], vc[1][M], vc[2][M]), vc[3][M], vc[4][M]);
     const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + rows);
     if (rowOK && (eq & ge_pm(big, tp))) {                    // rare
-      const unsigned int loc = (unsigned int)(x - (int)blockIdx.x * XT_TW) | ((unsigned int)(y - y0) << 7);
+      const unsigned int loc = (unsigned int)(x - bx * XT_TW) | ((unsigned int)(y - y0) << 7);
 #pragma unroll
       for (int sc = 0; sc < CSB_NUM_SCALES; sc++)
         if (flag_pm(vc[sc][M], mx[sc], tp)) {
@@ -267,7 +252,7 @@ __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const fl
     // more flagged pixels than the list holds (pathological input): forget the list and put every
     // pixel of the tile through the strict test instead
     const bool dense = flagged > (unsigned int)cap;
-    const int tile_w = min(XT_TW, w - (int)blockIdx.x * XT_TW), tile_h = min(rows, h - y0);
+    const int tile_w = min(XT_TW, w - bx * XT_TW), tile_h = min(rows, h - y0);
     const unsigned int n = dense ? (unsigned int)(tile_w * tile_h * CSB_NUM_SCALES) : flagged;
     for (unsigned int base = 0; base < n; base += XT_WARPS * 32) {
       const unsigned int i = base + threadIdx.x;
@@ -277,16 +262,16 @@ __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const fl
         int ex, ey, es;
         if (dense) {
           es = (int)(i % CSB_NUM_SCALES);
-          ex = (int)blockIdx.x * XT_TW + (int)((i / CSB_NUM_SCALES) % (unsigned int)tile_w);
+          ex = bx * XT_TW + (int)((i / CSB_NUM_SCALES) % (unsigned int)tile_w);
           ey = y0 + (int)((i / CSB_NUM_SCALES) / (unsigned int)tile_w);
         } else {
           const unsigned int en = s_list[i];
-          ex = (int)blockIdx.x * XT_TW + (int)(en & 0x7fu), ey = y0 + (int)((en >> 7) & 0x3fu), es = (int)(en >> 13);
+          ex = bx * XT_TW + (int)(en & 0x7fu), ey = y0 + (int)((en >> 7) & 0x3fu), es = (int)(en >> 13);
         }
         const bool inner = ex >= 1 && ex <= w - 2 && ey >= 1 && ey <= h - 2;
         if (inner) emit = verify_refine(dog, plane, pitch, P, ex, ey, es, r);
       }
-      emit_warp(emit, r, P, d_sift, d_oct, counter, max_pts, lane);
+      emit_warp(emit, r, stage, oct_counter, max_pts, lane);
     }
   };
   using I0 = std::integral_constant<int, 0>;
@@ -313,22 +298,37 @@ __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const fl
 
 }  // namespace
 
-void launch_find_points(const float *dog, int w, int h, int pitch, const ExtremaParams &ep, csb_sift_point *d_sift,
-                        int *d_oct, unsigned int *d_counter, int max_pts, int sm_count, cudaStream_t st) {
-  const int tiles_x = (w + XT_TW - 1) / XT_TW;
-  // rows per CTA: about one full wave of CTAs (6 resident per SM), so that the serial row loop of a
-  // CTA is as short as the image allows; multiple of 3 (the register window rotates in threes)
+int plan_find_points(ExtremaParams *ep, int sm_count) {
+  // rows per CTA: about one full wave of CTAs over ALL octaves (K2_MINB resident per SM), so that the
+  // serial row loop of a CTA is as short as the frame allows and every CTA carries the same work;
+  // multiple of 3 (the register window rotates in threes)
+  long long row_tiles = 0;
+  for (int i = 0; i < ep->n_oct; i++) {
+    ep->oct[i].tiles_x = (ep->oct[i].w + XT_TW - 1) / XT_TW;
+    row_tiles += (long long)ep->oct[i].h * ep->oct[i].tiles_x;
+  }
   const long long slots = (long long)sm_count * K2_MINB * K2_WAVES;
-  int rows = (int)(((long long)h * tiles_x + slots - 1) / slots);
+  int rows = (int)((row_tiles + slots - 1) / slots);
   rows = ((rows + 2) / 3) * 3;
   if (rows < 6) rows = 6;
   if (rows > XT_MAX_ROWS) rows = XT_MAX_ROWS;
-  dim3 grd(tiles_x, (h + rows - 1) / rows);
+  ep->rows = rows;
+  int ctas = 0;
+  for (int i = 0; i < ep->n_oct; i++) {
+    ep->oct[i].cta_begin = ctas;
+    ctas += ep->oct[i].tiles_x * ((ep->oct[i].h + rows - 1) / rows);
+  }
+  return ctas;
+}
+
+void launch_find_points(const ExtremaParams &ep, int n_ctas, KpStage *d_stage, unsigned int *d_counter, int max_pts,
+                        cudaStream_t st) {
+  if (n_ctas <= 0) return;
   static int cap = 0;                                  // CSB_XT_CAP: shrink the per-CTA list (tests of the dense fallback)
   if (!cap) {
     const char *e = getenv("CSB_XT_CAP");
     cap = e ? atoi(e) : XT_CAP;
     if (cap < 1 || cap > XT_CAP) cap = XT_CAP;
   }
-  k_find_points<<<grd, XT_WARPS * 32, 0, st>>>(dog, w, h, pitch, ep, d_sift, d_oct, d_counter, max_pts, rows, cap);
+  k_find_points<<<n_ctas, XT_WARPS * 32, 0, st>>>(ep, d_stage, d_counter, max_pts, cap);
 }
