@@ -182,12 +182,16 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
 // number of floating-point issue slots halves.  A CTA therefore processes TWO adjacent
 // 120-column strips in lock-step: every value is a float2 {strip A, strip B}.
 //
-// Shared-memory layout of the vertically blurred rows: positions are grouped in quads;
-// a quad of 4 float2 (32 B) is followed by 16 B of padding, which makes both the
-// 128-bit reads of the horizontal pass (lane stride one quad: 3 x 16 B, odd) and the
-// 64-bit writes of the vertical pass (lanes permuted so that a half-warp covers quads
-// Q, Q+2, Q+4, Q+6) bank-conflict free.
-constexpr int V2_QUAD = 6;                      // float2 slots per quad (4 data + 2 pad)
+// Shared-memory layout of the vertically blurred rows: a row of 128 float2 positions = 32 quads of 32 B,
+// no padding.  The horizontal pass reads one 16-byte chunk per lane with lane stride one quad (32 B),
+// so lanes q and q+4 of a quarter-warp would share a bank group; the two 16-byte halves of every quad
+// whose index has bit 2 set are therefore swapped (an XOR swizzle): 128-bit reads and the 64-bit writes
+// of the vertical pass (16 consecutive positions = 128 contiguous bytes) are both conflict-free, and the
+// tile is 32 KB instead of 48 KB, which lets more CTAs share an SM.
+#ifndef K1_MINB
+#define K1_MINB 4           // resident CTAs per SM the register budget is sized for
+#endif
+constexpr int V2_QUAD = 4;                      // float2 slots per quad
 constexpr int V2_ROW = (NT / 4) * V2_QUAD;      // float2 slots per (batch row, level)
 constexpr int ROWS2 = 16;                       // output rows per CTA
 constexpr size_t K1V2_SMEM = sizeof(float2) * (BATCH * NLEV * V2_ROW + BATCH * NT);
@@ -220,7 +224,7 @@ __device__ __forceinline__ float2 down_v2(float2 rm1, float2 r0, float2 r1, floa
 }
 
 template <bool kDown>
-__global__ void __launch_bounds__(NT, 4) k_blur_dog2(const float *__restrict__ src, int w, int h, int pitch,
+__global__ void __launch_bounds__(NT, K1_MINB) k_blur_dog2(const float *__restrict__ src, int w, int h, int pitch,
                                                   float *__restrict__ dog, const __grid_constant__ DogWeights2 W,
                                                   float *__restrict__ next, int npitch, DownK dk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -229,9 +233,9 @@ __global__ void __launch_bounds__(NT, 4) k_blur_dog2(const float *__restrict__ s
 
   const int t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
-  // vertical phase: lane -> strip position (permuted inside the warp's 32 positions, see above)
-  const int pos = 32 * warp + 4 * (((lane >> 2) & 3) * 2 + (lane >> 4)) + (lane & 3);
-  const int vslot = (pos >> 2) * V2_QUAD + (pos & 3);         // float2 slot of this position in a V row
+  const int pos = t;                                          // vertical phase: thread -> strip position
+  // float2 slot of this position in a V row: quad * 4 + (index in quad, halves swapped when quad bit 2 is set)
+  const int vslot = (pos & ~3) + ((pos & 3) ^ (((pos >> 4) & 1) << 1));
   const int xA = blockIdx.x * (2 * TW), xB = xA + TW;         // first output column of strip A / B
   const int y0 = blockIdx.y * ROWS2;
   const int cA = clampi(xA + pos - 4, 0, w - 1), cB = clampi(xB + pos - 4, 0, w - 1);
@@ -301,14 +305,17 @@ __global__ void __launch_bounds__(NT, 4) k_blur_dog2(const float *__restrict__ s
       const int y = r0 - 4 + warp;
       if (lane < TW / 4 && y < h) {
         const int xoA = xA + 4 * lane, xoB = xB + 4 * lane;
-        const float4 *q4 = reinterpret_cast<const float4 *>(V + (size_t)(warp * NLEV) * V2_ROW + lane * V2_QUAD);
+        const float4 *q4 = reinterpret_cast<const float4 *>(V + (size_t)(warp * NLEV) * V2_ROW);
+        int ch[6];                                          // swizzled 16-byte chunk indices of quads lane .. lane+2
+#pragma unroll
+        for (int i = 0; i < 6; i++) ch[i] = 2 * (lane + (i >> 1)) + ((i & 1) ^ (((lane + (i >> 1)) >> 2) & 1));
         constexpr int LSTRIDE = V2_ROW / 2;                 // float4 units between levels
         float *oA = dog + (size_t)y * pitch + xoA;          // plane 0; advanced by `plane` per level
         const bool fullA = xoA + 3 < w, fullB = xoB + 3 < w;
         const bool fast = __all_sync(__activemask(), fullA && fullB);
         float4 ld[6];                                       // software-pipelined shared loads (next level)
 #pragma unroll
-        for (int i = 0; i < 6; i++) ld[i] = q4[(i >> 1) * 3 + (i & 1)];
+        for (int i = 0; i < 6; i++) ld[i] = q4[ch[i]];
         float2 prev[4];
 #pragma unroll
         for (int s = 0; s < NLEV; s++) {
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(NT, 4) k_blur_dog2(const float *__restrict__ s
           }
           if (s + 1 < NLEV) {
 #pragma unroll
-            for (int i = 0; i < 6; i++) ld[i] = q4[(s + 1) * LSTRIDE + (i >> 1) * 3 + (i & 1)];
+            for (int i = 0; i < 6; i++) ld[i] = q4[(s + 1) * LSTRIDE + ch[i]];
           }
           float2 L[4];
 #pragma unroll
