@@ -216,6 +216,21 @@ class Context:
                     "csb_extract_batch_u8")
         return counts
 
+    def rigid_transform(self, coord: np.ndarray, indices, num_loops: int, thresh2: float, type3d: bool = True, seed: int = 1):
+        """csb_rigid_transform. indices: [num_loops, 3] int32 or None (drawn on the device).
+        Returns (Rt[12], num_inliers, mask[num_pts] bool)."""
+        coord = np.ascontiguousarray(coord, np.float32)
+        n = len(coord)
+        idx = None if indices is None else np.ascontiguousarray(indices, np.int32)
+        Rt = np.zeros(12, np.float32)
+        ninl = C.c_int(0)
+        mask = np.zeros(max(n, 1), np.int8)
+        self._check(self._L.csb_rigid_transform(
+            self.h, coord.ctypes.data_as(C.POINTER(C.c_float)), n, int(type3d),
+            None if idx is None else idx.ctypes.data_as(C.POINTER(C.c_int)), num_loops, thresh2, seed,
+            Rt.ctypes.data_as(C.POINTER(C.c_float)), C.byref(ninl), mask.ctypes.data_as(C.c_char_p)), "csb_rigid_transform")
+        return Rt, ninl.value, mask[:n].astype(bool)
+
     def ingest_u8(self, img: np.ndarray, preblur: bool) -> np.ndarray:
         """csb_ingest_u8 of a host uint8 frame; returns the fp32 device image downloaded again."""
         img = np.ascontiguousarray(img, np.uint8)

@@ -725,6 +725,74 @@ int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int 
   return 0;
 }
 
+int csb_rigid_transform(csb_ctx *ctx, const float *h_coord, int num_pts, int type, const int *h_indices, int num_loops,
+                        float thresh2, unsigned int seed, float *Rt12, int *num_inliers, char *h_inliers) {
+  if (!ctx || !h_coord || !Rt12 || !num_inliers || num_loops <= 0 || (type != 0 && type != 1))
+    return fail(ctx, CSB_E_INVALID, "csb_rigid_transform: bad argument");
+  *num_inliers = 0;
+  for (int i = 0; i < 12; i++) Rt12[i] = (i % 5 == 0) ? 1.0f : 0.0f;   // identity [I | 0]
+  if (num_pts < 3) return 0;
+  if (h_indices)
+    for (int i = 0; i < 3 * num_loops; i++)
+      if (h_indices[i] < 0 || h_indices[i] >= num_pts) return fail(ctx, CSB_E_INVALID, "csb_rigid_transform: index out of range");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  cudaStream_t st = s->stream;
+  int rc = finalize_frame(ctx, s);
+  if (rc) return rc;
+  // one scratch allocation: coords | indices | Rt | counts | mask
+  const size_t b_coord = ((size_t)num_pts * 6 * 4 + 255) & ~(size_t)255, b_idx = ((size_t)num_loops * 12 + 255) & ~(size_t)255,
+               b_rt = ((size_t)num_loops * 48 + 255) & ~(size_t)255, b_cnt = ((size_t)num_loops * 4 + 255) & ~(size_t)255,
+               b_mask = ((size_t)num_pts + 255) & ~(size_t)255;
+  char *d = nullptr;
+  CSB_CHECK(ctx, cudaMalloc((void **)&d, b_coord + b_idx + b_rt + b_cnt + b_mask));
+  float *d_coord = (float *)d;
+  int *d_idx = (int *)(d + b_coord);
+  float *d_rt = (float *)(d + b_coord + b_idx);
+  int *d_cnt = (int *)(d + b_coord + b_idx + b_rt);
+  char *d_mask = d + b_coord + b_idx + b_rt + b_cnt;
+  std::vector<int> counts(num_loops);
+  std::vector<char> mask(num_pts);
+  cudaError_t e = cudaMemcpyAsync(d_coord, h_coord, (size_t)num_pts * 24, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && h_indices) e = cudaMemcpyAsync(d_idx, h_indices, (size_t)num_loops * 12, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    ctx->launches += 2;
+    launch_rigid_hypotheses(d_coord, num_pts, d_idx, h_indices ? 0 : 1, seed, type, num_loops, thresh2, d_rt, d_cnt, st);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(counts.data(), d_cnt, (size_t)num_loops * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  int best = -1, best_cnt = -1;
+  if (e == cudaSuccess) {
+    for (int i = 0; i < num_loops; i++)          // rigidTransform.cu:451-457: `>=`, the last maximum wins
+      if (counts[i] >= best_cnt) { best_cnt = counts[i]; best = i; }
+    ctx->launches += 1;
+    launch_rigid_mask(d_coord, num_pts, d_rt, best, thresh2, d_mask, st);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(mask.data(), d_mask, (size_t)num_pts, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(Rt12, d_rt + 12 * (size_t)best, 48, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("csb_rigid_transform: ") + cudaGetErrorString(e);
+    return (int)e;
+  }
+  *num_inliers = best_cnt;
+  if (h_inliers) memcpy(h_inliers, mask.data(), (size_t)num_pts);
+  if (type == 1 && best_cnt >= 3) {              // rigidTransform.cu:476-484: refit on every inlier of the winner
+    std::vector<int> idx;
+    for (int i = 0; i < num_pts; i++)
+      if (mask[i] == 1) idx.push_back(i);
+    rigid_refit_host(h_coord, idx.data(), (int)idx.size(), Rt12);
+  }
+  return 0;
+}
+
+unsigned int csb_rigid_sample_hash(unsigned int seed, unsigned int loop, unsigned int k, unsigned int attempt) {
+  return rigid_hash_host(seed, loop, k, attempt);
+}
+
 int csb_ingest_u8(csb_ctx *ctx, const unsigned char *src, int src_on_host, int w, int h, int stride, int preblur,
                   float *d_dst, int dst_pitch_floats) {
   if (!ctx || !src || !d_dst || w < 1 || h < 1 || stride < w || dst_pitch_floats < w)

@@ -86,6 +86,13 @@ void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min
                         int *d_nvalid, float *d_coord, int *d_rand, float *d_homo, int *d_counts, int num_loops,
                         float thresh2, unsigned int seed, unsigned int pair, float *H_out, int *inl_out, int *nvalid_out,
                         cudaStream_t st);
+// rigid-transform RANSAC (kernels_rigid.cu)
+void launch_rigid_hypotheses(const float *d_coord, int num_pts, int *d_indices, int draw, unsigned int seed, int type3d,
+                             int num_loops, float thresh2, float *d_Rt, int *d_counts, cudaStream_t st);
+void launch_rigid_mask(const float *d_coord, int num_pts, const float *d_Rt, int loop, float thresh2, char *d_mask,
+                       cudaStream_t st);
+void rigid_refit_host(const float *h_coord, const int *idx, int n, float *Rt);
+unsigned int rigid_hash_host(unsigned int seed, unsigned int loop, unsigned int k, unsigned int attempt);
 unsigned int csb_sample_hash_host(unsigned int seed, unsigned int pair, unsigned int loop, unsigned int k,
                                   unsigned int attempt);
 

@@ -26,6 +26,7 @@
 #include "cusift/cuSIFT.h"
 #include "cusift/extras/homography.h"
 #include "cusift/extras/matching.h"
+#include "cusift/extras/rigidTransform.h"
 
 static_assert(sizeof(SiftPoint) == sizeof(csb_sift_point), "SiftPoint layout");
 static_assert(sizeof(SiftPoint) == 588, "SiftPoint must be 588 bytes (cuSIFT.h:10-30)");
@@ -388,4 +389,25 @@ int ImproveHomography(SiftData &data, float *homography, int numLoops, float min
   for (int i = 0; i < 8; i++) homography[i] = A[i];
   homography[8] = 1.0f;
   return numfit;
+}
+
+// ---------------------------------------------------------- rigid transform ---
+void EstimateRigidTransformH(const float *h_coord, float *Rt_relative, int *numInliers, int numLoops, int numPts,
+                             float thresh2, RigidTransformType type, int *h_indices, char *h_inliers) {
+  csb_ctx *ctx = shim_ctx();
+  static unsigned int call = 0;   // the reference seeds cuRAND with time(0): a different draw per call
+  shim_check(ctx, csb_rigid_transform(ctx, h_coord, numPts, type == RigidTransformType3D ? 1 : 0, h_indices, numLoops, thresh2,
+                                      0x5bd1e995u + 7919u * call++, Rt_relative, numInliers, h_inliers),
+             "EstimateRigidTransformH");
+}
+
+void EstimateRigidTransform(vector<SiftMatch *> matches, float *Rt_relative, int *numInliers, int numLoops, float thresh,
+                            RigidTransformType type, int *h_indices, char *h_inliers) {
+  std::vector<float> coord(6 * matches.size());
+  for (size_t i = 0; i < matches.size(); i++) {
+    memcpy(&coord[6 * i], matches[i]->pt1->coords3D, sizeof(float) * 3);
+    memcpy(&coord[6 * i + 3], matches[i]->pt2->coords3D, sizeof(float) * 3);
+  }
+  EstimateRigidTransformH(coord.data(), Rt_relative, numInliers, numLoops, (int)matches.size(), thresh * thresh, type,
+                          h_indices, h_inliers);
 }

@@ -118,6 +118,19 @@ int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int 
                       int pitch_floats, const csb_params *p, void *const *d_sifts, void *const *h_sifts,
                       int max_pts, int *num_pts);
 
+/* Rigid-transform RANSAC (EstimateRigidTransformH, extras/rigidTransform.cu:387-520).
+ * h_coord: num_pts x 6 floats (reference-frame xyz, moving-frame xyz); type 0 = planar two-point fit
+ * (x, z; y ignored), 1 = 3-D three-point quaternion fit.  h_indices: num_loops x 3 point indices, or
+ * NULL to draw them on the device (counter-based hash of `seed`; the reference seeds cuRAND with
+ * time(0)).  Returns the hypothesis with the most inliers (the LAST one on ties, like the reference's
+ * `>=` scan), its inlier count and mask (h_inliers: num_pts bytes, may be NULL); for type 1 the
+ * transform is re-estimated from all inliers on the host, as the reference does. */
+int csb_rigid_transform(csb_ctx *ctx, const float *h_coord, int num_pts, int type, const int *h_indices, int num_loops,
+                        float thresh2, unsigned int seed, float *Rt12, int *num_inliers, char *h_inliers);
+
+/* the device-side sample generator of csb_rigid_transform (h_indices == NULL), for tests */
+unsigned int csb_rigid_sample_hash(unsigned int seed, unsigned int loop, unsigned int k, unsigned int attempt);
+
 /* Frame ingest (reference: the host-side preparation in main.cpp:301-318).
  * csb_ingest_u8: 8-bit grey frame (host or device memory, `stride` bytes per row) -> pitched fp32
  * device image; preblur != 0 applies cv::GaussianBlur(Size(3,3), 0.5) (main.cpp:308-309), bit-identical

@@ -324,3 +324,94 @@ def ref_homography(s1: np.ndarray, workdir, num_loops, min_score, max_amb, thres
         res["num_fit"] = int(v[0])
         res["H_improved"] = np.array(v[1:], np.float32)
     return res
+
+
+# ---------------------------------------------------------------- rigid transform ---
+def read_matlab_ransac(path):
+    """ReadMATLABRANSAC (extras/debug.cpp:318-372): (coord [n,6] f32, indices [loops,3] 0-based, Rt [12] f32)."""
+    b = Path(path).read_bytes()
+    n, loops = np.frombuffer(b, np.uint32, 2)
+    off = 8
+    ci = np.frombuffer(b, np.float32, 3 * n, off).reshape(n, 3); off += 12 * n
+    cj = np.frombuffer(b, np.float32, 3 * n, off).reshape(n, 3); off += 12 * n
+    idx = np.frombuffer(b, np.int32, 3 * loops, off).reshape(loops, 3) - 1; off += 12 * loops
+    Rt = np.frombuffer(b, np.float32, 12, off).copy()
+    return np.ascontiguousarray(np.concatenate([ci, cj], 1)), np.ascontiguousarray(idx.astype(np.int32)), Rt
+
+
+def rigid3d(coord: np.ndarray, idx) -> np.ndarray:
+    """estimateRigidTransform3D (extras/rigidTransform.cu:15-205) in numpy: centroids and B in float32 like the
+    reference, the smallest singular vector of B from LAPACK (the reference: float Numerical-Recipes dsvd)."""
+    f = np.float32
+    x = coord[idx, :3].astype(f); y = coord[idx, 3:].astype(f)
+    n = f(len(idx))
+    xc = np.zeros(3, f); yc = np.zeros(3, f)
+    for i in range(len(idx)):                       # sequential float sums, as written
+        xc = (xc + x[i]).astype(f); yc = (yc + y[i]).astype(f)
+    xc = (xc / n).astype(f); yc = (yc / n).astype(f)
+    x = (x - xc).astype(f); y = (y - yc).astype(f)
+    B = np.zeros((4, 4), f)
+    for i in range(len(idx)):
+        d = (y[i] - x[i]).astype(f); s = (y[i] + x[i]).astype(f)
+        A = np.array([[0, d[0], d[1], d[2]],
+                      [-d[0], 0, -s[2], s[1]],
+                      [-d[1], s[2], 0, -s[0]],
+                      [-d[2], -s[1], s[0], 0]], f)
+        B = (B + (A @ A.T).astype(f)).astype(f)
+    _, S, Vt = np.linalg.svd(B.astype(np.float64))
+    Q = Vt[int(np.argmin(S))].astype(f)
+    q0, q1, q2, q3 = (np.float64(v) for v in Q)
+    R = np.array([[1 - 2 * (q2 * q2 + q3 * q3), 2 * (q1 * q2 - q0 * q3), 2 * (q1 * q3 + q0 * q2)],
+                  [2 * (q1 * q2 + q0 * q3), 1 - 2 * (q1 * q1 + q3 * q3), 2 * (q2 * q3 - q0 * q1)],
+                  [2 * (q1 * q3 - q0 * q2), 2 * (q2 * q3 + q0 * q1), 1 - 2 * (q1 * q1 + q2 * q2)]]).astype(f)
+    t = ((R @ (-yc)).astype(f) + xc).astype(f)
+    return np.concatenate([R, t[:, None]], 1).astype(f).ravel()
+
+
+def rigid2d(coord: np.ndarray, a: int, b: int) -> np.ndarray:
+    """estimateRigidTransform2D (extras/rigidTransform.cu:214-290)."""
+    f = np.float32
+    A, Bp = coord[a].astype(f), coord[b].astype(f)
+    dxw, dzw = f(A[0] - Bp[0]), f(A[2] - Bp[2])
+    lw = f(np.sqrt(f(dxw * dxw + dzw * dzw)))
+    dxc, dzc = f(A[3] - Bp[3]), f(A[5] - Bp[5])
+    lc = f(np.sqrt(f(dxc * dxc + dzc * dzc)))
+    dxwn, dzwn, dxcn, dzcn = f(dxw / lw), f(dzw / lw), f(dxc / lc), f(dzc / lc)
+    c = f(dxwn * dxcn + dzwn * dzcn); s = f(dzwn * dxcn - dxwn * dzcn)
+    sxw, szw, sxc, szc = f(A[0] + Bp[0]), f(A[2] + Bp[2]), f(A[3] + Bp[3]), f(A[5] + Bp[5])
+    return np.array([c, 0, -s, (sxw - c * sxc + s * szc) / 2, 0, 1, 0, 0, s, 0, c, (szw - s * sxc - c * szc) / 2], f)
+
+
+def rigid_inliers(coord: np.ndarray, Rt: np.ndarray, thresh2: float) -> np.ndarray:
+    """testRigidTransform (extras/rigidTransform.cu:292-328): boolean mask."""
+    R = Rt.reshape(3, 4).astype(np.float32)
+    p = (coord[:, 3:].astype(np.float32) @ R[:, :3].T + R[:, 3]).astype(np.float32)
+    err = ((p - coord[:, :3]) ** 2).sum(1).astype(np.float32)
+    return err < np.float32(thresh2)
+
+
+def rigid_transform(coord: np.ndarray, indices: np.ndarray, thresh2: float, type3d: bool = True):
+    """EstimateRigidTransformH (extras/rigidTransform.cu:387-520) with given indices: (Rt[12], numInliers, mask)."""
+    best, best_cnt, hyp = -1, -1, []
+    for l in range(len(indices)):
+        Rt = rigid3d(coord, indices[l]) if type3d else rigid2d(coord, int(indices[l][0]), int(indices[l][1]))
+        hyp.append(Rt)
+        c = int(rigid_inliers(coord, Rt, thresh2).sum())
+        if c >= best_cnt:                           # `>=`: the last maximum wins
+            best_cnt, best = c, l
+    mask = rigid_inliers(coord, hyp[best], thresh2)
+    Rt = hyp[best]
+    if type3d and best_cnt >= 3:
+        Rt = rigid3d(coord, np.nonzero(mask)[0])
+    return Rt, best_cnt, mask
+
+
+def ref_rigid(coord: np.ndarray, indices: np.ndarray, thresh2: float, type3d: bool, workdir, tag="ref"):
+    """The unmodified reference's EstimateRigidTransformH through oracle/_ref/ref_driver (needs a GPU)."""
+    workdir = Path(workdir)
+    c, i, o = workdir / f"{tag}_rt_coord.f32", workdir / f"{tag}_rt_idx.i32", workdir / f"{tag}_rt.txt"
+    np.ascontiguousarray(coord, np.float32).tofile(c)
+    np.ascontiguousarray(indices, np.int32).tofile(i)
+    _run_ref(["rigid", c, len(coord), i, len(indices), repr(float(thresh2)), int(type3d), o])
+    v = o.read_text().split()
+    return np.array(v[1:13], np.float32), int(v[0]), np.array(v[13:], np.int32).astype(bool)

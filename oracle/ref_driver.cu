@@ -29,6 +29,7 @@
 
 #include "extras/homography.h"
 #include "extras/matching.h"
+#include "extras/rigidTransform.h"
 
 int ImproveHomography(SiftData &data, float *homography, int numLoops, float minScore,
                       float maxAmbiguity, float thresh);  // extras/homography.cu:280
@@ -321,9 +322,38 @@ static int cmdBenchMatch(int argc, char **argv) {
   return 0;
 }
 
+// rigid coord.f32(numPts x 6) numPts indices.i32(numLoops x 3) numLoops thresh2 type(0|1) out.txt
+// -> unmodified EstimateRigidTransformH (extras/rigidTransform.cu:387-520) with the given indices
+static int cmdRigid(int argc, char **argv) {
+  if (argc < 7) return 2;
+  const int numPts = atoi(argv[1]), numLoops = atoi(argv[3]);
+  const float thresh2 = (float)atof(argv[4]);
+  const int type = atoi(argv[5]);
+  std::vector<float> coord((size_t)6 * numPts);
+  std::vector<int> idx((size_t)3 * numLoops);
+  FILE *f = fopen(argv[0], "rb");
+  if (!f || fread(coord.data(), 4, coord.size(), f) != coord.size()) return 3;
+  fclose(f);
+  f = fopen(argv[2], "rb");
+  if (!f || fread(idx.data(), 4, idx.size(), f) != idx.size()) return 3;
+  fclose(f);
+  float Rt[12];
+  int numInliers = 0;
+  std::vector<char> inl(numPts, 0);
+  EstimateRigidTransformH(coord.data(), Rt, &numInliers, numLoops, numPts, thresh2,
+                          type ? RigidTransformType3D : RigidTransformType2D, idx.data(), inl.data());
+  f = fopen(argv[6], "w");
+  if (!f) return 4;
+  fprintf(f, "%d\n", numInliers);
+  for (int i = 0; i < 12; i++) fprintf(f, "%.9g\n", Rt[i]);
+  for (int i = 0; i < numPts; i++) fprintf(f, "%d\n", (int)inl[i]);
+  fclose(f);
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc < 2) {
-    fprintf(stderr, "usage: ref_driver {extract|extract_safe|stages|match|homography|bench|benchmatch} ...\n");
+    fprintf(stderr, "usage: ref_driver {extract|extract_safe|stages|match|homography|rigid|bench|benchmatch} ...\n");
     return 1;
   }
   InitCuda(0);
@@ -334,6 +364,7 @@ int main(int argc, char **argv) {
   else if (cmd == "stages") rc = cmdStages(argc - 2, argv + 2);
   else if (cmd == "match") rc = cmdMatch(argc - 2, argv + 2);
   else if (cmd == "homography") rc = cmdHomography(argc - 2, argv + 2);
+  else if (cmd == "rigid") rc = cmdRigid(argc - 2, argv + 2);
   else if (cmd == "bench") rc = cmdBench(argc - 2, argv + 2);
   else if (cmd == "benchmatch") rc = cmdBenchMatch(argc - 2, argv + 2);
   if (rc == 1) fprintf(stderr, "ref_driver: bad arguments for %s\n", cmd.c_str());

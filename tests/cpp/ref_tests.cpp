@@ -4,11 +4,14 @@
 //   Matching.MatchingTest        test/test.cpp:25-46   326 MATLAB nearest-neighbour pairs
 //   Matching.MatchingRatioTest   test/test.cpp:48-56   exactly 340 ratio-test matches
 //   Detector.DetectorCUSIFTTest  test/detector.cpp:18-88   count + "found" test against cusift1_check
+//   RigidTransform.RANSACWithIndices / RANSACWithRandom  test/test.cpp:58-127  (the reference only prints its result
+//                                next to the MATLAB Rt stored in the file; here the two are compared)
 // usage: csb_ref_tests <golden dir> <gray1 640x480 float32 raw>; prints one JSON line, exit code =
 // number of failed expectations.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -17,6 +20,7 @@
 #include "extras/debug.h"
 #include "extras/homography.h"
 #include "extras/matching.h"
+#include "extras/rigidTransform.h"
 
 static int g_fail = 0;
 #define EXPECT(cond)                                                       \
@@ -118,7 +122,39 @@ int main(int argc, char **argv) {
     }
     fclose(fp);
   }
-  printf("{\"nn_checked\": %d, \"nn_equal\": %d, \"ratio_matches\": %d, \"det_pts\": %d, \"det_rows\": %d, \"det_found\": %d, "
+  // ---- RigidTransform.RANSACWithIndices / RANSACWithRandom ----
+  int rt_inliers = 0, rt_inliers_random = 0;
+  double rt_maxdiff = 0.0, rt_maxdiff_random = 0.0;
+  {
+    vector<int> indices;
+    float Rt[12], Rt_test[12];
+    vector<SiftMatch *> matches = ReadMATLABRANSAC((dir + "/rigid_ransac.bin").c_str(), indices, Rt);
+    EXPECT(matches.size() == 120 && indices.size() == 30);
+    const int numLoops = (int)indices.size() / 3;
+    std::vector<float> h_coord(6 * matches.size());
+    for (size_t i = 0; i < matches.size(); i++) {
+      memcpy(&h_coord[6 * i], matches[i]->pt1->coords3D, sizeof(float) * 3);
+      memcpy(&h_coord[6 * i + 3], matches[i]->pt2->coords3D, sizeof(float) * 3);
+    }
+    std::vector<char> h_inliers(matches.size());
+    EstimateRigidTransformH(h_coord.data(), Rt_test, &rt_inliers, numLoops, (int)matches.size(), 0.05f * 0.05f,
+                            RigidTransformType3D, indices.data(), h_inliers.data());
+    for (int i = 0; i < 12; i++) rt_maxdiff = fmax(rt_maxdiff, fabs((double)Rt_test[i] - (double)Rt[i]));
+    EXPECT(rt_inliers == 114);
+    EXPECT(rt_maxdiff < 1e-5);
+    EstimateRigidTransform(matches, Rt_test, &rt_inliers_random, 4096, 0.05f, RigidTransformType3D);   // test.cpp:112-127
+    for (int i = 0; i < 12; i++) rt_maxdiff_random = fmax(rt_maxdiff_random, fabs((double)Rt_test[i] - (double)Rt[i]));
+    EXPECT(rt_inliers_random >= 114);
+    EXPECT(rt_maxdiff_random < 2e-2);   // a larger consensus set (116 of 120) than the 10 stored loops find: its refit differs slightly
+    for (SiftMatch *m : matches) {
+      delete m->pt1;
+      delete m->pt2;
+      delete m;
+    }
+  }
+  printf("{\"rt_inliers\": %d, \"rt_maxdiff\": %.3g, \"rt_inliers_random\": %d, \"rt_maxdiff_random\": %.3g, ", rt_inliers,
+         rt_maxdiff, rt_inliers_random, rt_maxdiff_random);
+  printf("\"nn_checked\": %d, \"nn_equal\": %d, \"ratio_matches\": %d, \"det_pts\": %d, \"det_rows\": %d, \"det_found\": %d, "
          "\"det_found_abs\": %d, \"failed\": %d}\n",
          nn_checked, nn_equal, ratio_matches, det_pts, det_rows, det_found, det_found_abs, g_fail);
   return g_fail > 255 ? 255 : g_fail;

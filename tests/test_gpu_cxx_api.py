@@ -55,4 +55,6 @@ def test_reference_test_suite_restated_in_cpp(workdir):
     assert r["ratio_matches"] == 340                            # test.cpp:55
     assert r["det_pts"] == 4096 and r["det_rows"] == 4096       # detector.cpp:68
     assert r["det_found"] == 4096 and r["det_found_abs"] == 4096
+    assert r["rt_inliers"] == 114 and r["rt_maxdiff"] < 1e-5     # test.cpp:58-110 vs the MATLAB Rt in the file
+    assert r["rt_inliers_random"] >= 114 and r["rt_maxdiff_random"] < 2e-2
     assert r["failed"] == 0

@@ -554,3 +554,78 @@ def test_extract_batch_u8_equals_float_path(gpu_ctx, frames):
     finally:
         for d in ds:
             gpu_ctx.free(d)
+
+
+# ---------------------------------------------------------- rigid transform ---
+def _rigid_scene(n, n_out, seed):
+    r = np.random.default_rng(seed)
+    ang = r.uniform(-0.6, 0.6, 3)
+    cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+    R = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
+         np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+    t = r.uniform(-0.5, 0.5, 3)
+    mov = r.uniform(-1, 1, (n, 3)) + np.array([0, 0, 2.0])
+    ref = mov @ R.T + t + r.normal(0, 0.002, (n, 3))
+    ref[:n_out] = r.uniform(-2, 2, (n_out, 3))
+    return np.ascontiguousarray(np.concatenate([ref, mov], 1), np.float32), R, t
+
+
+def test_rigid_transform_golden_and_reference(gpu_ctx, workdir):
+    """EstimateRigidTransformH on the reference's golden file with its stored indices: equals the numpy oracle,
+    the MATLAB Rt stored in the file and the unmodified reference run on this GPU."""
+    coord, idx, Rt_matlab = O.read_matlab_ransac(PU.GOLDEN / "rigid_ransac.bin")
+    Rt, n_inl, mask = gpu_ctx.rigid_transform(coord, idx, len(idx), 0.05 * 0.05, True)
+    Rt_o, n_o, mask_o = O.rigid_transform(coord, idx, 0.05 * 0.05, True)
+    assert n_inl == n_o == 114 and np.array_equal(mask, mask_o)
+    assert np.abs(Rt - Rt_o).max() < 1e-5 and np.abs(Rt - Rt_matlab).max() < 1e-5
+    Rt_r, n_r, mask_r = O.ref_rigid(coord, idx, 0.05 * 0.05, True, workdir)
+    assert n_r == n_inl and np.array_equal(mask_r, mask)
+    assert np.abs(Rt - Rt_r).max() < 1e-4                    # the reference's float SVD vs eigen-decomposition in double
+
+
+@pytest.mark.parametrize("type3d", [True, False])
+def test_rigid_transform_synthetic_vs_oracle(gpu_ctx, type3d):
+    coord, R, t = _rigid_scene(2000, 600, 11)
+    if not type3d:                                           # planar motion about y for the two-point fit
+        a = 0.4
+        R = np.array([[np.cos(a), 0, -np.sin(a)], [0, 1, 0], [np.sin(a), 0, np.cos(a)]])
+        mov = coord[:, 3:].astype(np.float64)
+        ref = mov @ R.T + np.array([0.3, 0.0, -0.2])
+        ref[:600] = np.random.default_rng(3).uniform(-2, 2, (600, 3))
+        coord = np.ascontiguousarray(np.concatenate([ref, mov], 1), np.float32)
+    r = np.random.default_rng(12)
+    idx = np.stack([r.choice(2000, 3, replace=False) for _ in range(256)]).astype(np.int32)
+    Rt, n_inl, mask = gpu_ctx.rigid_transform(coord, idx, 256, 0.01 * 0.01, type3d)
+    Rt_o, n_o, mask_o = O.rigid_transform(coord, idx, 0.01 * 0.01, type3d)
+    assert abs(n_inl - n_o) <= 2 and (mask != mask_o).sum() <= 2   # borderline points may flip with FMA contraction
+    assert n_inl > 1200
+    assert np.abs(Rt - Rt_o).max() < 2e-4
+    assert np.abs(Rt.reshape(3, 4)[:, :3] - R).max() < 5e-3
+
+
+def test_rigid_transform_device_sampling_and_edges(gpu_ctx):
+    coord, R, t = _rigid_scene(500, 100, 21)
+    Rt, n_inl, mask = gpu_ctx.rigid_transform(coord, None, 512, 0.01 * 0.01, True, seed=5)
+    assert n_inl >= 380 and mask.sum() == n_inl
+    assert np.abs(Rt.reshape(3, 4)[:, :3] - R).max() < 5e-3 and np.abs(Rt.reshape(3, 4)[:, 3] - t).max() < 5e-3
+    again = gpu_ctx.rigid_transform(coord, None, 512, 0.01 * 0.01, True, seed=5)
+    assert np.array_equal(again[0], Rt) and again[1] == n_inl          # deterministic for a given seed
+    # the generator restated on the host draws the same indices
+    L = csb.lib()
+    idx = np.zeros((512, 3), np.int32)
+    for l in range(512):
+        picks = []
+        for k in range(3):
+            a = 0
+            while True:
+                c = L.csb_rigid_sample_hash(5, l, k, a) % 500
+                a += 1
+                if c not in picks:
+                    picks.append(c)
+                    break
+        idx[l] = picks
+    same = gpu_ctx.rigid_transform(coord, idx, 512, 0.01 * 0.01, True)
+    assert np.array_equal(same[0], Rt) and same[1] == n_inl
+    # fewer than 3 points: identity, no inliers (nothing to fit)
+    Rt0, n0, _ = gpu_ctx.rigid_transform(coord[:2], None, 16, 1.0, True)
+    assert n0 == 0 and np.array_equal(Rt0.reshape(3, 4), np.eye(3, 4, dtype=np.float32))

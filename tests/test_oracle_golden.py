@@ -172,3 +172,15 @@ def test_homography_recovers_known_transform():
     H2, nfit, _ = O.improve_homography(pts, Hf, 5, 0.0, 0.8, 2.0)
     assert nfit >= 138
     assert np.allclose(H2[:6], H[:6], atol=5e-2) and np.allclose(H2[6:8], H[6:8], atol=1e-4)
+
+
+def test_rigid_transform_oracle_reproduces_matlab_rt():
+    """test/test.cpp:58-110 (RigidTransform.RANSACWithIndices) prints its result next to the MATLAB Rt stored in
+    test/data/RigidTransform_RANSAC.bin; the numpy restatement of EstimateRigidTransformH reproduces that Rt."""
+    coord, idx, Rt = O.read_matlab_ransac(PU.GOLDEN / "rigid_ransac.bin")
+    assert coord.shape == (120, 6) and idx.shape == (10, 3) and idx.min() >= 0 and idx.max() < 120
+    got, n_inl, mask = O.rigid_transform(coord, idx, 0.05 * 0.05, True)
+    assert n_inl == 114 and mask.sum() == 114
+    assert np.abs(got - Rt).max() < 1e-6
+    R = got.reshape(3, 4)[:, :3]
+    assert np.abs(R @ R.T - np.eye(3)).max() < 1e-6 and abs(np.linalg.det(R) - 1) < 1e-6
