@@ -267,81 +267,109 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
     // (chunks of 32 columns).  m2 <= the true second largest value, so thr = m2 - 2 eps is still a valid
     // (slightly more inclusive) listing threshold, and a chunk costs 16 three-input max + 3 ops instead
     // of 96 (FMNMX runs at half rate: this epilogue is ALU-pipe bound).  Padding columns hold 0.
+    // TMEM reads are software-pipelined: the tcgen05.ld of the next 64 columns is in flight while the
+    // current 64 are reduced (tcgen05.wait::ld waits for every outstanding load, so it sits after the
+    // arithmetic), and the accumulator is handed back to the MMA warp as soon as its last columns are in
+    // registers, before they are reduced.
     float m1 = -1.0f, m2 = -1.0f;
+    auto reduce64 = [&](const uint32_t (&r)[32], const uint32_t (&q)[32]) {
+      float g[8];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        g[k] = fmaxf(fmaxf(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])), __uint_as_float(r[8 * k + 2]));
+        g[k] = fmaxf(fmaxf(g[k], __uint_as_float(r[8 * k + 3])), __uint_as_float(r[8 * k + 4]));
+        g[k] = fmaxf(fmaxf(g[k], __uint_as_float(r[8 * k + 5])), __uint_as_float(r[8 * k + 6]));
+        g[k] = fmaxf(g[k], __uint_as_float(r[8 * k + 7]));
+        g[4 + k] = fmaxf(fmaxf(__uint_as_float(q[8 * k]), __uint_as_float(q[8 * k + 1])), __uint_as_float(q[8 * k + 2]));
+        g[4 + k] = fmaxf(fmaxf(g[4 + k], __uint_as_float(q[8 * k + 3])), __uint_as_float(q[8 * k + 4]));
+        g[4 + k] = fmaxf(fmaxf(g[4 + k], __uint_as_float(q[8 * k + 5])), __uint_as_float(q[8 * k + 6]));
+        g[4 + k] = fmaxf(g[4 + k], __uint_as_float(q[8 * k + 7]));
+      }
+      const float ca = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+      const float cb = fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]));
+      float lo = fminf(m1, ca);
+      m1 = fmaxf(m1, ca);
+      m2 = fmaxf(m2, lo);
+      lo = fminf(m1, cb);
+      m1 = fmaxf(m1, cb);
+      m2 = fmaxf(m2, lo);
+    };
+    static_assert(TC_CT / 64 == 4, "sweep 1 is unrolled for four 64-column chunks per tile");
     for (int i = 0; i < n_tiles; i++) {
       mbar_wait(acc_full + qh, i & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < TC_CT / 64; ch++) {
-        uint32_t r[32], q[32];
-        tc_ld32(taddr + (uint32_t)(ch * 64), r);
-        tc_ld32(taddr + (uint32_t)(ch * 64 + 32), q);
-        tc_ld_wait();
-        float g[8];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          g[k] = fmaxf(fmaxf(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])), __uint_as_float(r[8 * k + 2]));
-          g[k] = fmaxf(fmaxf(g[k], __uint_as_float(r[8 * k + 3])), __uint_as_float(r[8 * k + 4]));
-          g[k] = fmaxf(fmaxf(g[k], __uint_as_float(r[8 * k + 5])), __uint_as_float(r[8 * k + 6]));
-          g[k] = fmaxf(g[k], __uint_as_float(r[8 * k + 7]));
-          g[4 + k] = fmaxf(fmaxf(__uint_as_float(q[8 * k]), __uint_as_float(q[8 * k + 1])), __uint_as_float(q[8 * k + 2]));
-          g[4 + k] = fmaxf(fmaxf(g[4 + k], __uint_as_float(q[8 * k + 3])), __uint_as_float(q[8 * k + 4]));
-          g[4 + k] = fmaxf(fmaxf(g[4 + k], __uint_as_float(q[8 * k + 5])), __uint_as_float(q[8 * k + 6]));
-          g[4 + k] = fmaxf(g[4 + k], __uint_as_float(q[8 * k + 7]));
-        }
-        const float ca = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-        const float cb = fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]));
-        float lo = fminf(m1, ca);
-        m1 = fmaxf(m1, ca);
-        m2 = fmaxf(m2, lo);
-        lo = fminf(m1, cb);
-        m1 = fmaxf(m1, cb);
-        m2 = fmaxf(m2, lo);
-      }
+      uint32_t ra[32], qa[32], rb[32], qb[32];
+      tc_ld32(taddr + 0, ra);
+      tc_ld32(taddr + 32, qa);
+      tc_ld_wait();
+      tc_ld32(taddr + 64, rb);
+      tc_ld32(taddr + 96, qb);
+      reduce64(ra, qa);
+      tc_ld_wait();
+      tc_ld32(taddr + 128, ra);
+      tc_ld32(taddr + 160, qa);
+      reduce64(rb, qb);
+      tc_ld_wait();
+      tc_ld32(taddr + 192, rb);
+      tc_ld32(taddr + 224, qb);
+      reduce64(ra, qa);
+      tc_ld_wait();
       tc_fence_before();
       mbar_arrive(acc_empty + qh);           // 128 arrivals free the accumulator
+      reduce64(rb, qb);
     }
     // ---- sweep 2: list every candidate with approximate dot >= m2 - 2 eps ----
     const float thr = m2 - 2.0f * TC_EPS;
-    int li[TC_TOPK];
-#pragma unroll
-    for (int k = 0; k < TC_TOPK; k++) li[k] = -1;
+    // Hits (about 2 per query and split) are appended straight to the global short list.  The append path
+    // runs for the whole warp whenever ANY lane has a hit in an 8-column group (about a quarter of the
+    // groups), so it must be short: a bit mask of the group's hits, then one iteration per set bit.
+    int *const out_list = out_idx + ((size_t)(qtile * TC_QT + row) * n_splits + split) * TC_TOPK;
     int cnt = 0;
-    for (int i = 0; i < n_tiles; i++) {
-      mbar_wait(acc_full + qh, (n_tiles + i) & 1);
-      tc_fence_after();
-      const int col0 = (t0 + i) * TC_CT;
-#pragma unroll 1
-      for (int ch = 0; ch < TC_CT / 32; ch++) {
-        uint32_t r[32];
-        tc_ld32(taddr + (uint32_t)(ch * 32), r);
-        tc_ld_wait();
+    auto list32 = [&](const uint32_t (&r)[32], int cbase) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {          // groups of 8 columns: the append path below is rare per group
-          float g = fmaxf(fmaxf(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])), __uint_as_float(r[8 * k + 2]));
-          g = fmaxf(fmaxf(g, __uint_as_float(r[8 * k + 3])), __uint_as_float(r[8 * k + 4]));
-          g = fmaxf(fmaxf(g, __uint_as_float(r[8 * k + 5])), __uint_as_float(r[8 * k + 6]));
-          g = fmaxf(g, __uint_as_float(r[8 * k + 7]));
-          if (g >= thr) {
+      for (int k = 0; k < 4; k++) {
+        float g = fmaxf(fmaxf(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])), __uint_as_float(r[8 * k + 2]));
+        g = fmaxf(fmaxf(g, __uint_as_float(r[8 * k + 3])), __uint_as_float(r[8 * k + 4]));
+        g = fmaxf(fmaxf(g, __uint_as_float(r[8 * k + 5])), __uint_as_float(r[8 * k + 6]));
+        g = fmaxf(g, __uint_as_float(r[8 * k + 7]));
+        if (g >= thr) {
+          unsigned int m = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const int cidx = col0 + ch * 32 + 8 * k + j;
-              if (__uint_as_float(r[8 * k + j]) >= thr && cidx < nc) {
-#pragma unroll
-                for (int kk = 0; kk < TC_TOPK; kk++)
-                  if (kk == cnt) li[kk] = cidx;
-                cnt++;
-              }
+          for (int j = 0; j < 8; j++) m |= (__uint_as_float(r[8 * k + j]) >= thr) ? (1u << j) : 0u;
+          while (m) {
+            const int cidx = cbase + 8 * k + (__ffs(m) - 1);
+            m &= m - 1;
+            if (cidx < nc) {
+              if (cnt < TC_TOPK) out_list[cnt] = cidx;
+              cnt++;
             }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(acc_empty + qh);
+    };
+    for (int i = 0; i < n_tiles; i++) {
+      mbar_wait(acc_full + qh, (n_tiles + i) & 1);
+      tc_fence_after();
+      const int col0 = (t0 + i) * TC_CT;
+      uint32_t ra[32], rb[32];
+      tc_ld32(taddr, ra);
+      tc_ld_wait();
+#pragma unroll 1
+      for (int ch = 0; ch < TC_CT / 32; ch += 2) {        // same double buffering as sweep 1
+        tc_ld32(taddr + (uint32_t)((ch + 1) * 32), rb);
+        list32(ra, col0 + ch * 32);
+        tc_ld_wait();
+        if (ch + 2 < TC_CT / 32) {
+          tc_ld32(taddr + (uint32_t)((ch + 2) * 32), ra);
+        } else {
+          tc_fence_before();
+          mbar_arrive(acc_empty + qh);
+        }
+        list32(rb, col0 + (ch + 1) * 32);
+        if (ch + 2 < TC_CT / 32) tc_ld_wait();
+      }
     }
-    const size_t o = ((size_t)(qtile * TC_QT + row) * n_splits + split) * TC_TOPK;
-#pragma unroll
-    for (int k = 0; k < TC_TOPK; k++) out_idx[o + k] = li[k];
+    for (int k = min(cnt, TC_TOPK); k < TC_TOPK; k++) out_list[k] = -1;
     out_val[(size_t)(qtile * TC_QT + row) * n_splits + split] = (float)cnt;   // entries found (may exceed TC_TOPK)
   }
 
