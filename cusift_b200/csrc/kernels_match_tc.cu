@@ -55,6 +55,7 @@ constexpr uint32_t SMEM_A = 2 /*query halves*/ * 2 /*K halves*/ * A_HALF_BYTES; 
 constexpr uint32_t SMEM_B_STAGE = 2 * B_HALF_BYTES;                                 // 64 KB
 constexpr uint32_t SMEM_TC = SMEM_A + TC_STAGES * SMEM_B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 32 * (2 + 8);
+constexpr int RS_ROWS = 16;        // staged candidate rows per rescoring round (per warp)
 constexpr float TC_EPS = 6.5e-4f;   // bound on |fp16-input dot - exact dot| for unit descriptors
 
 // ---- PTX wrappers ---------------------------------------------------------------
@@ -400,17 +401,46 @@ __global__ void __launch_bounds__(128) k_rescore(csb_sift_point *__restrict__ s1
   if (lane < n_splits) overflow = sl_val[(size_t)q * n_splits + lane] > (float)TC_TOPK;
   const bool proven = !__any_sync(0xffffffffu, overflow);
 
-  // exact score in the reference's rotated k order (matching.cu:84-89), lane = one listed candidate
+  // exact score in the reference's rotated k order (matching.cu:84-89), lane = one listed candidate.
+  // The listed descriptors are first staged in shared memory by the whole warp (coalesced 512-byte row
+  // reads; 32 lanes each walking their own global row cost ~10 sectors per load instruction and made
+  // this kernel as slow as the tensor-core scan), then every lane runs its 128-step FFMA chain from
+  // shared memory: row stride 129 words spreads the lanes' rows over the banks.
+  __shared__ float s_q[4][128];
+  __shared__ float s_c[4][RS_ROWS * 129];
+  const int wib = threadIdx.x >> 5;
+  float *sq = s_q[wib], *sc = s_c[wib];
+#pragma unroll
+  for (int j = 0; j < 4; j++) sq[lane + 32 * j] = s1[q].data[lane + 32 * j];
   float score = kL2 ? 999.0f : -1.0f;
-  if (ci >= 0) {
-    const float *pa = s1[q].data, *pb = s2[ci].data;
-    const int tx = ci & 15;
-    float sum = 0.0f;
-    for (int i = 0; i < 128; i++) {
-      const int k = (i + tx) & 127;
-      sum = __fmaf_rn(pa[k], pb[k], sum);
+  // listed candidates are compacted to rows 0.. of the staging tile, RS_ROWS at a time (usually one round)
+  const unsigned int have = __ballot_sync(0xffffffffu, ci >= 0);
+  const int my_row = __popc(have & ((1u << lane) - 1u));
+  const int n_have = __popc(have);
+  for (int r0 = 0; r0 < n_have; r0 += RS_ROWS) {
+    __syncwarp();
+    unsigned int m = have;
+    for (int r = 0; m; r++) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      if (r < r0 || r >= r0 + RS_ROWS) continue;
+      const int c = __shfl_sync(0xffffffffu, ci, src);
+      const float *pb = s2[c].data;
+#pragma unroll
+      for (int j = 0; j < 4; j++) sc[(r - r0) * 129 + lane + 32 * j] = pb[lane + 32 * j];
     }
-    score = kL2 ? __fsub_rn(2.0f, __fadd_rn(sum, sum)) : sum;
+    __syncwarp();
+    if (ci >= 0 && my_row >= r0 && my_row < r0 + RS_ROWS) {
+      const float *pb = sc + (my_row - r0) * 129;
+      const int tx = ci & 15;
+      float sum = 0.0f;
+#pragma unroll 16
+      for (int i = 0; i < 128; i++) {
+        const int k = (i + tx) & 127;
+        sum = __fmaf_rn(sq[k], pb[k], sum);
+      }
+      score = kL2 ? __fsub_rn(2.0f, __fadd_rn(sum, sum)) : sum;
+    }
   }
   // best: FindMinCorr's winner = lowest (score, bitrev4(col % 16), col / 16); second = best of the rest
   // (an equal duplicate lands in `second`, matching.cu:229-235)
