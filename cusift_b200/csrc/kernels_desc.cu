@@ -32,6 +32,9 @@ constexpr int WARPS = 4;
 #ifndef K3_MINB
 #define K3_MINB 8          // resident CTAs per SM the register budget is sized for
 #endif
+#ifndef K3_GRIDMUL
+#define K3_GRIDMUL 1
+#endif
 #ifndef K3_BATCH
 #define K3_BATCH 2         // descriptor samples whose texture fetches are in flight together
 #endif
@@ -359,7 +362,9 @@ __global__ void __launch_bounds__(128) k_rootsift(csb_sift_point *__restrict__ d
 
 void launch_orient_desc(const OctaveTexSet &texs, int n_oct, const float *subs, const KpStage *d_stage, csb_sift_point *d_sift,
                         unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st) {
-  int blocks = sm_count * K3_MINB;                // resident CTAs per SM (register budget, 26 KB shared each)
+  // K3_GRIDMUL x the resident capacity: with about one keypoint per warp the hardware CTA scheduler
+  // balances the load (CTAs start as others retire) instead of a static two-keypoints-or-one split
+  int blocks = sm_count * K3_MINB * K3_GRIDMUL;
   const int need = (max_pts + WARPS - 1) / WARPS;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
