@@ -194,9 +194,8 @@ __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const __
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
 
-  // per plane: packed horizontal max3 of three consecutive rows (slots rotate), packed centre values
-  // of those rows for the 5 centre planes, and three source rows in flight
-  unsigned int hx[NPL][3], vc[CSB_NUM_SCALES][3];
+  // per plane: the packed values of three consecutive rows (slots rotate) and three source rows in flight
+  unsigned int c3[NPL][3];
   float ring[3][NPL];
   const float *col = dog + cx;
   const unsigned int tpk = pack_pm(P.thresh) & 0xffffu, tp = tpk | (tpk << 16);   // (rn(t), rn(t))
@@ -215,32 +214,35 @@ __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const __
   auto place = [&](auto SLOT, auto RS) {
     constexpr int S = decltype(SLOT)::value, R = decltype(RS)::value;
 #pragma unroll
-    for (int p = 0; p < NPL; p++) {
-      const unsigned int c = pack_pm(ring[R][p]);
-      const unsigned int l = __shfl_up_sync(FULL, c, 1), r = __shfl_down_sync(FULL, c, 1);
-      hx[p][S] = hmax3(l, c, r);
-      if (p >= 1 && p <= CSB_NUM_SCALES) vc[p - 1][S] = c;
-    }
+    for (int p = 0; p < NPL; p++) c3[p][S] = pack_pm(ring[R][p]);
   };
+  // The 3x3x3 maximum is separable; taking the column (3 rows) and the plane (3 planes) maxima first and
+  // the horizontal one last means only the 5 per-scale partial maxima travel through shuffles
+  // (10 per row instead of 14 when every plane is shuffled: shuffles and loads share the LSU pipe,
+  // which bounds this scan together with the half-rate min/max pipe).
   auto test = [&](auto SM, int y) {   // output row y = slot SM; the other two slots are rows y-1 / y+1
     constexpr int M = decltype(SM)::value;
-    unsigned int fx[NPL];
+    unsigned int vx[NPL];
 #pragma unroll
-    for (int p = 0; p < NPL; p++) fx[p] = hmax3(hx[p][0], hx[p][1], hx[p][2]);
-    // flagged: packed value equals the 27-neighbourhood maximum at some scale AND some scale of this
-    // pixel reaches the threshold (a superset of "at the same scale", refined in the rare path below)
+    for (int p = 0; p < NPL; p++) vx[p] = hmax3(c3[p][0], c3[p][1], c3[p][2]);
     unsigned int mx[CSB_NUM_SCALES];
 #pragma unroll
-    for (int sc = 0; sc < CSB_NUM_SCALES; sc++) mx[sc] = hmax3(fx[sc], fx[sc + 1], fx[sc + 2]);
-    const unsigned int eq = (eq_pm(vc[0][M], mx[0]) | eq_pm(vc[1][M], mx[1]) | eq_pm(vc[2][M], mx[2])) |
-                            (eq_pm(vc[3][M], mx[3]) | eq_pm(vc[4][M], mx[4]));
-    const unsigned int big = hmax3(hmax3(vc[0][M], vc[1][M], vc[2][M]), vc[3][M], vc[4][M]);
+    for (int sc = 0; sc < CSB_NUM_SCALES; sc++) {
+      const unsigned int wv = hmax3(vx[sc], vx[sc + 1], vx[sc + 2]);
+      const unsigned int l = __shfl_up_sync(FULL, wv, 1), r = __shfl_down_sync(FULL, wv, 1);
+      mx[sc] = hmax3(l, wv, r);
+    }
+    // flagged: packed value equals the 27-neighbourhood maximum at some scale AND some scale of this
+    // pixel reaches the threshold (a superset of "at the same scale", refined in the rare path below)
+    const unsigned int eq = (eq_pm(c3[1][M], mx[0]) | eq_pm(c3[2][M], mx[1]) | eq_pm(c3[3][M], mx[2])) |
+                            (eq_pm(c3[4][M], mx[3]) | eq_pm(c3[5][M], mx[4]));
+    const unsigned int big = hmax3(hmax3(c3[1][M], c3[2][M], c3[3][M]), c3[4][M], c3[5][M]);
     const bool rowOK = colOK && (y >= 1) && (y <= h - 2) && (y < y0 + rows);
     if (rowOK && (eq & ge_pm(big, tp))) {                    // rare
       const unsigned int loc = (unsigned int)(x - bx * XT_TW) | ((unsigned int)(y - y0) << 7);
 #pragma unroll
       for (int sc = 0; sc < CSB_NUM_SCALES; sc++)
-        if (flag_pm(vc[sc][M], mx[sc], tp)) {
+        if (flag_pm(c3[sc + 1][M], mx[sc], tp)) {
           const unsigned int slot = atomicAdd(&s_cnt, 1u);
           if (slot < (unsigned int)cap) s_list[slot] = (unsigned short)(loc | ((unsigned int)sc << 13));
         }
