@@ -197,19 +197,19 @@ __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const __
   // per plane: the packed values of three consecutive rows (slots rotate) and three source rows in flight
   unsigned int c3[NPL][3];
   float ring[3][NPL];
-  const float *col = dog + cx;
   const unsigned int tpk = pack_pm(P.thresh) & 0xffffu, tp = tpk | (tpk << 16);   // (rn(t), rn(t))
 
-  // one 64-bit base per plane, so that a row address is a single IMAD.WIDE (FMA pipe) per load: the
-  // scan is bound by the half-rate ALU pipe, where 64-bit adds would compete with the max network
-  const float *pbase[NPL];
+  // 32-bit element offsets from ONE base pointer (a pyramid level has < 2^31 elements): a load address is
+  // one 32-bit add plus one IMAD.WIDE; per-plane 64-bit pointers cost two LEA each on the half-rate ALU
+  // pipe that bounds this scan (38 address instructions per row were measured, a third of the loop)
+  unsigned int poff[NPL];
 #pragma unroll
-  for (int p = 0; p < NPL; p++) pbase[p] = col + (size_t)p * plane;
+  for (int p = 0; p < NPL; p++) poff[p] = (unsigned int)p * (unsigned int)plane + (unsigned int)cx;
   auto fetch = [&](int r, auto RS) {
     constexpr int R = decltype(RS)::value;
     const unsigned int off = (unsigned int)clampi(r, 0, h - 1) * (unsigned int)pitch;
 #pragma unroll
-    for (int p = 0; p < NPL; p++) ring[R][p] = pbase[p][off];
+    for (int p = 0; p < NPL; p++) ring[R][p] = dog[poff[p] + off];
   };
   auto place = [&](auto SLOT, auto RS) {
     constexpr int S = decltype(SLOT)::value, R = decltype(RS)::value;
