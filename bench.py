@@ -346,6 +346,51 @@ def main():
                     "frac": d["frac"], "traffic": ncu_traffic(dom), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": d["alg_bytes"], "avg_launch_us": d["avg_us"]}
 
+    # BASELINE config 5 in miniature (informational): all-pairs MatchSiftData + 1024-hypothesis RANSAC over
+    # 8 keypoint sets of 8192 points per GPU; the sets are exchanged with ONE NCCL all-gather, the unordered
+    # pairs partitioned cyclically (tools/allpairs_bench.py runs the full 256-set configuration)
+    allpairs = None
+    try:
+        P, per = 8192, 8
+        prm5 = csb.make_params(N_OCT, 0.0, 0.5, EDGE, 0.0)
+        local = torch.zeros((per, P, 588), dtype=torch.uint8, device="cuda")
+        cnts_local = torch.zeros(per, dtype=torch.int32, device="cuda")
+        for k in range(per):
+            pts = ctx.extract(csb.synth(W, H, 3000 + rank * per + k), prm5, max_pts=32768)
+            order = np.lexsort((pts["scale"], pts["coords2D"][:, 1], pts["coords2D"][:, 0], pts["subsampling"]))
+            pts = np.ascontiguousarray(pts[order][:P])
+            local[k, : len(pts)].copy_(torch.from_numpy(pts.view(np.uint8).reshape(len(pts), 588)))
+            cnts_local[k] = len(pts)
+        torch.cuda.synchronize()
+        if dist is not None:
+            allsets = torch.empty((world * per, P, 588), dtype=torch.uint8, device="cuda")
+            allcnts = torch.empty(world * per, dtype=torch.int32, device="cuda")
+            dist.all_gather_into_tensor(allsets, local)
+            dist.all_gather_into_tensor(allcnts, cnts_local)
+        else:
+            allsets, allcnts = local, cnts_local
+        cnts = allcnts.cpu().numpy()
+        n_sets = world * per
+        ptrs = [allsets[i].data_ptr() for i in range(n_sets)]
+        mine = [(k, pr) for k, pr in enumerate(csb.all_pairs(n_sets)) if k % world == rank]
+        ids, prs = [k for k, _ in mine], [pr for _, pr in mine]
+        ctx.allpairs(ptrs, cnts, prs[:2], "l2", 1024, 0.0, 0.80, 5.0, 1, ids[:2])
+        barrier()
+        t0 = time.perf_counter()
+        ctx.allpairs(ptrs, cnts, prs, "l2", 1024, 0.0, 0.80, 5.0, 1, ids)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        wk = torch.tensor([float(sum(int(cnts[i]) for i, _ in prs)), float(len(prs))], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(wk, op=dist.ReduceOp.SUM)
+        allpairs = {"sets": n_sets, "points_per_set": P, "pairs": int(wk[1]), "seconds": float(tt[0]),
+                    "Mmatches_per_s": float(wk[0]) / float(tt[0]) / 1e6, "pairs_per_s": float(wk[1]) / float(tt[0]),
+                    "ransac_loops": 1024, "exchange": "nccl all_gather of SiftPoint arrays" if dist is not None else "none (1 GPU)"}
+        del local, allsets
+    except Exception as e:  # noqa: BLE001  (informational arm: never fail the headline line)
+        allpairs = {"unavailable": repr(e)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
@@ -395,6 +440,7 @@ def main():
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e / args.steps},
             "e2e_u8": e2e_u8,
             "gpu_launches": int(launches) * world, "gpu_launches_e2e": int(launches_e) * world,
+            "allpairs_c5_sample": allpairs,
             "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
