@@ -61,11 +61,11 @@ __device__ __forceinline__ float sumsq_tree(const float (&b)[4], int lane) {
   return __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
 }
 
-// Descriptor accumulator of one warp: buf[row][bank], 16 rows x 32 banks.  Rows 0-7 hold angular bin
-// `row` of cell c of half-warp h at bank 16 h + c; rows 8-15 are the scratch bins of lane 16 h + c.
+// Descriptor accumulator of one warp: buf[row][bank], 8 rows x 32 banks: row = angular bin, bank 16 h + c =
+// cell c of half-warp h.
 // At one vote site the 32 lanes address 32 different (half, cell) pairs, hence 32 different banks
 // whatever their angular bins are (the cell-major layout measured 72 % conflict wavefronts).
-constexpr int DBUF = 16 * 32;
+constexpr int DBUF = 8 * 32;
 
 // Plain read-modify-write vote: the caller guarantees that no two lanes of the warp
 // target the same address in the same call (see the lane->cell mapping below).
@@ -77,10 +77,14 @@ __device__ __forceinline__ void vote(float *q, float v) {
 // The two angular shares of one spatial share: q0 != q1 unless both are scratch (a lane's a1 and angp
 // differ, and a spilled a1 goes to the scratch cell), and at one vote site the 16 lanes of a half hit
 // 16 different cells, so both read-modify-writes can be in flight together.
-__device__ __forceinline__ void vote2(float *q0, float v0, float *q1, float v1) {
-  const float o0 = *q0, o1 = *q1;
-  *q0 = __fadd_rn(o0, v0);
-  *q1 = __fadd_rn(o1, v1);
+__device__ __forceinline__ void vote2(bool ok0, float *q0, float v0, bool ok1, float *q1, float v1) {
+  // predicated, not branched: a share without a destination (outside the 4x4 grid, or spilled) simply
+  // makes no access, so the 32 lanes never meet in a bank
+  float o0 = 0.f, o1 = 0.f;
+  if (ok0) o0 = *q0;
+  if (ok1) o1 = *q1;
+  if (ok0) *q0 = __fadd_rn(o0, v0);
+  if (ok1) *q1 = __fadd_rn(o1, v1);
   __syncwarp();
 }
 
@@ -232,7 +236,6 @@ __global__ void __launch_bounds__(WARPS * 32, K3_MINB) k_orient_desc(const __gri
                        tex2D<float>(tex, __fadd_rn(xpos, sina), __fsub_rn(ypos, cosa)));
       return g;
     };
-    float *dummy = copy + 8 * 32 + (lane & 15);    // private 8-bin scratch cell (rows 8-15)
 #pragma unroll 1
     for (int it0 = 0; it0 < 8; it0 += K3_BATCH) {
     Grad gs[K3_BATCH];                             // 4 K3_BATCH texture fetches of the lane in flight at once
@@ -260,22 +263,21 @@ __global__ void __launch_bounds__(WARPS * 32, K3_MINB) k_orient_desc(const __gri
       const int cell = 4 * veri + hori;              // the UL cell; DL = +4, UR = +1, DR = +5 (may be -5 .. 20)
       // the four spatial shares (guards of cuSIFT_D.cu:230-255; `tx<=14` sic).  A share whose cell
       // lies outside buffer[128] is dropped (in the reference it lands beyond its last shared array);
-      // invalid shares are simply accumulated into the lane's scratch cell.
+      // invalid shares make no access.
       const bool gl = tx >= 2, gr = tx <= 14, gu = y >= 2, gd = y <= 13;
       const float gUL = __fmul_rn(iverf, __fmul_rn(ihorf, grad)), gDL = __fmul_rn(verf, __fmul_rn(ihorf, grad));
       const float gUR = __fmul_rn(iverf, __fmul_rn(horf, grad)), gDR = __fmul_rn(verf, __fmul_rn(horf, grad));
       const bool vUL = gl && gu, vDL = gl && gd && (cell + 4 < 16);
       const bool vUR = gr && gu && (cell + 1 < 16), vDR = gr && gd && (cell + 5 < 16);
-      float *cUL = vUL ? copy + cell : dummy, *cDL = vDL ? copy + cell + 4 : dummy;
-      float *cUR = vUR ? copy + cell + 1 : dummy, *cDR = vDR ? copy + cell + 5 : dummy;
+      float *cUL = copy + cell, *cDL = copy + cell + 4, *cUR = copy + cell + 1, *cDR = copy + cell + 5;
       // angi == 8 (atan2f >= 3.1415, e.g. dy == +0, dx < 0) makes p1 point at bin 0 of the NEXT cell,
       // which another lane may be voting into at the same site: those votes go through an atomic pass.
       const bool spill = angi >= 8;
       const int a1 = spill ? 0 : 32 * angi, a2 = 32 * angp;
-      vote2((spill ? dummy : cUL) + a1, __fmul_rn(iangf, gUL), cUL + a2, __fmul_rn(angf, gUL));
-      vote2((spill ? dummy : cDL) + a1, __fmul_rn(iangf, gDL), cDL + a2, __fmul_rn(angf, gDL));
-      vote2((spill ? dummy : cUR) + a1, __fmul_rn(iangf, gUR), cUR + a2, __fmul_rn(angf, gUR));
-      vote2((spill ? dummy : cDR) + a1, __fmul_rn(iangf, gDR), cDR + a2, __fmul_rn(angf, gDR));
+      vote2(vUL && !spill, cUL + a1, __fmul_rn(iangf, gUL), vUL, cUL + a2, __fmul_rn(angf, gUL));
+      vote2(vDL && !spill, cDL + a1, __fmul_rn(iangf, gDL), vDL, cDL + a2, __fmul_rn(angf, gDL));
+      vote2(vUR && !spill, cUR + a1, __fmul_rn(iangf, gUR), vUR, cUR + a2, __fmul_rn(angf, gUR));
+      vote2(vDR && !spill, cDR + a1, __fmul_rn(iangf, gDR), vDR, cDR + a2, __fmul_rn(angf, gDR));
       if (__any_sync(FULL, spill)) {
         if (spill) {
           if (vUL && cell + 1 < 16) atomicAdd(copy + cell + 1, __fmul_rn(iangf, gUL));
