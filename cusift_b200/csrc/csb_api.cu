@@ -691,6 +691,20 @@ int csb_extract_host(csb_ctx *ctx, const float *h_img, int w, int h, const csb_p
   return finalize_frame(ctx, s);
 }
 
+// A frame whose output buffers are still owned by a frame in flight on ANOTHER slot must wait for it
+// (a caller may reuse one d_sift / h_sift for every frame of a batch).
+static int wait_for_aliases(csb_ctx *ctx, const Slot *self, const void *d_sift, const void *h_sift) {
+  for (int i = 0; i < ctx->n_slots; i++) {
+    Slot *t = &ctx->slots[i];
+    if (t == self || !t->busy) continue;
+    if (t->cur_d_sift == d_sift || (h_sift != nullptr && t->user_h == h_sift)) {
+      int rc = finalize_frame(ctx, t);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
 int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int imgs_on_host, int w, int h,
                       int pitch_floats, const csb_params *p, void *const *d_sifts, void *const *h_sifts, int max_pts,
                       int *num_pts) {
@@ -712,6 +726,7 @@ int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int 
       d_img = s->img0;
     }
     void *hs = h_sifts ? h_sifts[f] : nullptr;
+    if ((rc = wait_for_aliases(ctx, s, d_sifts[f], hs))) return rc;
     if ((rc = enqueue_frame(ctx, s, d_img, w, h, pitch, p, (csb_sift_point *)d_sifts[f], max_pts, hs, &num_pts[f])))
       return rc;
     // two-stage pipeline: the frame queued n_slots/2 iterations ago moves on to its download while the
@@ -855,6 +870,7 @@ int csb_extract_batch_u8(csb_ctx *ctx, int n_frames, const unsigned char *const 
       launch_ingest_u8(s->u8, w, w, h, s->img0, pitch, preblur, k0, k1, s->stream);
     }
     void *hs = h_sifts ? h_sifts[f] : nullptr;
+    if ((rc = wait_for_aliases(ctx, s, d_sifts[f], hs))) return rc;
     if ((rc = enqueue_frame(ctx, s, s->img0, w, h, pitch, p, (csb_sift_point *)d_sifts[f], max_pts, hs, &num_pts[f])))
       return rc;
     const int lag = ctx->n_slots / 2;

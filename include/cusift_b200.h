@@ -113,7 +113,9 @@ int csb_extract_host(csb_ctx *ctx, const float *h_img, int w, int h, const csb_p
  * throughput path; the reference has no equivalent — a caller would loop over
  * SiftData::Extract).  imgs[i] is a device pitched image (imgs_on_host == 0) or a
  * dense host frame (imgs_on_host != 0).  d_sifts[i] / h_sifts[i] receive frame i
- * (h_sifts or any h_sifts[i] may be NULL); num_pts[i] its count. */
+ * (h_sifts or any h_sifts[i] may be NULL); num_pts[i] its count.  Frames are in flight on up to
+ * num_slots slots at once; a frame whose d_sifts[i] / h_sifts[i] is still in use by an earlier frame
+ * waits for it, so reusing one buffer for every frame is legal but serialises the pipeline. */
 int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int imgs_on_host, int w, int h,
                       int pitch_floats, const csb_params *p, void *const *d_sifts, void *const *h_sifts,
                       int max_pts, int *num_pts);

@@ -253,6 +253,28 @@ def test_batch_equals_single_and_is_deterministic(gpu_ctx):
             pa.free()
 
 
+def test_batch_with_one_shared_device_buffer(gpu_ctx):
+    """A caller may pass the same d_sift for every frame of a batch (it only wants the host copies):
+    frames then wait for the buffer instead of racing on it."""
+    imgs = [csb.synth(640, 480, 400 + i) for i in range(6)]
+    p = csb.make_params(5, 0.0, 0.5)
+    dev = [gpu_ctx.upload_image(im) for im in imgs]
+    d_one = gpu_ctx.alloc(588 * 8192)
+    pins = [csb.PinnedArray(8192) for _ in imgs]
+    try:
+        cnt = gpu_ctx.extract_batch([d for d, _ in dev], 640, 480, dev[0][1], p, [d_one] * len(imgs), [q.ptr for q in pins], 8192)
+        for k, im in enumerate(imgs):
+            want = PU.canonical_sort(gpu_ctx.extract(im, p, max_pts=8192))
+            got = PU.canonical_sort(pins[k].array[: cnt[k]].copy())
+            assert len(got) == len(want) > 500
+            for f in ("coords2D", "scale", "orientation", "data"):
+                assert np.array_equal(got[f], want[f]), (k, f)
+    finally:
+        gpu_ctx.free(d_one)
+        for d, _ in dev:
+            gpu_ctx.free(d)
+
+
 def test_full_size_properties_4k_rootsift(gpu_ctx):
     """BASELINE config 3 (3840x2160, ExtractRootSift, ~95 k keypoints): size-independent
     properties — determinism of the keypoint set, unit-L2 RootSIFT descriptors, count in
