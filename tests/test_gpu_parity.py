@@ -123,7 +123,8 @@ def test_extract_synth_vs_oracle(gpu_ctx):
 
 
 @needs_ref
-@pytest.mark.parametrize("case", ["gray1", "gray2_preblur", "synth_1080p", "synth_640_rootsift"])
+@pytest.mark.parametrize("case", ["gray1", "gray2_preblur", "synth_1080p", "synth_640_rootsift", "synth_4k_rootsift",
+                                  "initblur_odd_size"])
 def test_extract_vs_reference(gpu_ctx, frames, synth1080, workdir, case):
     """Ours vs the unmodified reference on the same GPU: identical keypoint sets with
     bit-identical x, y, scale, sharpness, edgeness; orientation and descriptors within
@@ -135,10 +136,14 @@ def test_extract_vs_reference(gpu_ctx, frames, synth1080, workdir, case):
         img, prm = PU.preblur(frames[1]), (6, 0.0, 0.1)          # main.cpp:308-309 pre-blur
     elif case == "synth_1080p":
         img, prm = synth1080, (5, 0.0, 1.0)
+    elif case == "synth_4k_rootsift":                            # BASELINE config 3
+        img, prm, root = csb.synth(3840, 2160, 2000), (5, 0.0, 2.0), True
+    elif case == "initblur_odd_size":
+        img, prm = csb.synth(517, 389, 91), (4, 0.5, 0.3)
     else:
         img, prm, root = csb.synth(640, 480, 33), (5, 0.0, 0.5), True
-    ours = gpu_ctx.extract(img, csb.make_params(*prm, 10.0, 0.0, rootsift=root), max_pts=32768)
-    ref = O.ref_extract(img, workdir, prm[0], prm[1], prm[2], 10.0, 0.0, root, 32768, safe=True, tag=case)
+    ours = gpu_ctx.extract(img, csb.make_params(*prm, 10.0, 0.0, rootsift=root), max_pts=65536)
+    ref = O.ref_extract(img, workdir, prm[0], prm[1], prm[2], 10.0, 0.0, root, 65536, safe=True, tag=case)
     r = PU.compare_keypoints(ours, ref)
     assert r["n_ours"] == r["n_ref"] == r["matched"] and r["only_ours"] == 0 and r["only_ref"] == 0, r
     assert r["pos_exact"] == r["matched"], r                  # bit-exact positions and scales
