@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
 #endif
 constexpr int V2_QUAD = 4;                      // float2 slots per quad
 constexpr int V2_ROW = (NT / 4) * V2_QUAD;      // float2 slots per (batch row, level)
-constexpr int ROWS2 = 16;                       // output rows per CTA
+constexpr int ROWS2 = 16;                       // output rows per CTA (large octaves)
+constexpr int ROWS2_SMALL = 4;                  // ... when the octave would not fill the GPU otherwise: the
+                                                // row loop is what a small octave's launch waits for
 constexpr size_t K1V2_SMEM = sizeof(float2) * (BATCH * NLEV * V2_ROW + BATCH * NT);
 
 struct DogWeights2 {
@@ -223,7 +225,7 @@ __device__ __forceinline__ float2 down_v2(float2 rm1, float2 r0, float2 r1, floa
   return t;
 }
 
-template <bool kDown>
+template <bool kDown, int kRows>
 __global__ void __launch_bounds__(NT, K1_MINB) k_blur_dog2(const float *__restrict__ src, int w, int h, int pitch,
                                                   float *__restrict__ dog, const __grid_constant__ DogWeights2 W,
                                                   float *__restrict__ next, int npitch, DownK dk) {
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(NT, K1_MINB) k_blur_dog2(const float *__restri
   // float2 slot of this position in a V row: quad * 4 + (index in quad, halves swapped when quad bit 2 is set)
   const int vslot = (pos & ~3) + ((pos & 3) ^ (((pos >> 4) & 1) << 1));
   const int xA = blockIdx.x * (2 * TW), xB = xA + TW;         // first output column of strip A / B
-  const int y0 = blockIdx.y * ROWS2;
+  const int y0 = blockIdx.y * kRows;
   const int cA = clampi(xA + pos - 4, 0, w - 1), cB = clampi(xB + pos - 4, 0, w - 1);
   const size_t plane = (size_t)pitch * h;
 
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(NT, K1_MINB) k_blur_dog2(const float *__restri
     pre2[b] = make_float2(r[cA], r[cB]);
   }
 
-  constexpr int NB = (ROWS2 + 8) / BATCH;
+  constexpr int NB = (kRows + 8) / BATCH;
   for (int nb = 0; nb < NB; nb++) {
     const int r0 = y0 - 4 + nb * BATCH;      // first source row of this batch
     // window holds source rows r0-8 .. r0+3 after this: shift by BATCH, append the batch
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(NT, K1_MINB) k_blur_dog2(const float *__restri
           for (int i = 0; i < 4; i++) hw[i] = hw[i + 1];
           hw[4] = hv;
           const int twoj = r - 3;   // window = rows r-4..r = 2j-1..2j+3
-          if (twoj >= y0 && twoj < y0 + ROWS2 && !(twoj & 1)) {
+          if (twoj >= y0 && twoj < y0 + kRows && !(twoj & 1)) {
             const int j = twoj >> 1;
             if (j < (h >> 1)) {
               const float2 o = down_v2(hw[0], hw[1], hw[2], hw[3], hw[4], dk0, dk1, dk2);
@@ -437,10 +439,16 @@ DogWeights2 dup_weights(const DogWeights &wts) {
     for (int j = 0; j < 5; j++) w2.k[s][j] = make_float2(wts.k[s][j], wts.k[s][j]);
   return w2;
 }
-template <bool kDown>
-void set_smem_attr_once() {   // > 48 KB of dynamic shared memory needs the opt-in (per device; cheap to repeat)
-  cudaFuncSetAttribute(k_blur_dog2<kDown>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1V2_SMEM);
+template <bool kDown, int kRows>
+void launch_blur_dog2(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next, int npitch,
+                      DownK dk, cudaStream_t st) {
+  // > 48 KB of dynamic shared memory would need the opt-in; harmless (per device, cheap) for the 36 KB used now
+  cudaFuncSetAttribute(k_blur_dog2<kDown, kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1V2_SMEM);
+  dim3 grd((w + 2 * TW - 1) / (2 * TW), (h + kRows - 1) / kRows);
+  k_blur_dog2<kDown, kRows><<<grd, NT, K1V2_SMEM, st>>>(base, w, h, pitch, dog, dup_weights(wts), next, npitch, dk);
 }
+// fewer than two CTAs per SM with 16-row tiles: use 4-row tiles (the frame's latency, not its SM time)
+inline bool small_octave(int w, int h) { return ((w + 2 * TW - 1) / (2 * TW)) * ((h + ROWS2 - 1) / ROWS2) < 2 * 148; }
 }  // namespace
 
 void launch_blur_dog(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, cudaStream_t st) {
@@ -450,9 +458,8 @@ void launch_blur_dog(const float *base, int w, int h, int pitch, float *dog, con
     k_blur_dog<false><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, nullptr, 0, dk);
     return;
   }
-  set_smem_attr_once<false>();
-  dim3 grd((w + 2 * TW - 1) / (2 * TW), (h + ROWS2 - 1) / ROWS2);
-  k_blur_dog2<false><<<grd, NT, K1V2_SMEM, st>>>(base, w, h, pitch, dog, dup_weights(wts), nullptr, 0, dk);
+  if (small_octave(w, h)) launch_blur_dog2<false, ROWS2_SMALL>(base, w, h, pitch, dog, wts, nullptr, 0, dk, st);
+  else launch_blur_dog2<false, ROWS2>(base, w, h, pitch, dog, wts, nullptr, 0, dk, st);
 }
 
 void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next,
@@ -463,7 +470,6 @@ void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog
     k_blur_dog<true><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, next, npitch, dk);
     return;
   }
-  set_smem_attr_once<true>();
-  dim3 grd((w + 2 * TW - 1) / (2 * TW), (h + ROWS2 - 1) / ROWS2);
-  k_blur_dog2<true><<<grd, NT, K1V2_SMEM, st>>>(base, w, h, pitch, dog, dup_weights(wts), next, npitch, dk);
+  if (small_octave(w, h)) launch_blur_dog2<true, ROWS2_SMALL>(base, w, h, pitch, dog, wts, next, npitch, dk, st);
+  else launch_blur_dog2<true, ROWS2>(base, w, h, pitch, dog, wts, next, npitch, dk, st);
 }
