@@ -109,7 +109,7 @@ struct csb_ctx {
   size_t coord_cap = 0, loops_cap = 0;
   int *h_counts = nullptr;
   // all-pairs scratch (grow-only, csb_allpairs_match_ransac)
-  static constexpr int AP_STREAMS = 4;
+  static constexpr int AP_STREAMS = 8;
   cudaStream_t ap_stream[AP_STREAMS] = {};
   cudaEvent_t ap_done[AP_STREAMS] = {};
   cudaEvent_t ap_packed = nullptr;
