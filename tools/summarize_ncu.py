@@ -103,6 +103,30 @@ if lf.exists():
         ns = float(r[iv].replace(",", ""))
         lines.append(f"| {r[ik].split('(')[0]} | {r[ig]} | {ns:.0f} | {100*ns/tot:.1f} % |")
     lines += ["", f"sum {tot/1000:.1f} us per 1080p frame (serialised, cold cache)", ""]
+bf = OUT / f"launches_bench_{tag}.csv"
+if bf.exists():
+    rows = list(csv.reader(bf.read_text().splitlines()))
+    start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[start]
+    ik, iv, ig = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
+    data = rows[start + 1:]
+    with open(PROF / f"{tag}_bench_launches.csv", "w", newline="") as fp:
+        wr = csv.writer(fp)
+        wr.writerow(["kernel", "grid", "gpu__time_duration_ns"])
+        for r in data:
+            wr.writerow([r[ik].split("(")[0], r[ig], r[iv]])
+    agg = {}
+    for r in data:
+        key = (r[ik].split("(")[0].replace("void <unnamed>::", "").replace("<unnamed>::", ""), r[ig])
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[iv].replace(",", ""))
+    tot = sum(a[1] for a in agg.values())
+    lines += [f"## launch list of `python bench.py --steps 2 --warmup 3 --frames-per-step 64` (first {len(data)} launches)", "",
+              "| kernel | grid | launches | mean ns | share of the step |", "|---|---|---|---|---|"]
+    for (k, g), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"| {k} | {g} | {n} | {t / n:.0f} | {100 * t / tot:.1f} % |")
+    lines.append("")
 import json
 (PROF / f"{tag}_traffic.json").write_text(json.dumps(traffic, indent=1))
 (PROF / f"{tag}_summary.md").write_text("\n".join(lines))
