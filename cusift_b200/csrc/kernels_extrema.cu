@@ -39,6 +39,9 @@ constexpr int XT_TW = XT_COLS * XT_WARPS;   // 120 output columns per CTA
 #ifndef K2_MINB
 #define K2_MINB 6           // resident CTAs per SM the register budget is sized for
 #endif
+#ifndef K2_LOAD
+#define K2_LOAD(p) (*(p))    // plain cached load (variants tried: __ldcs, __ldg)
+#endif
 #ifndef K2_WAVES
 #define K2_WAVES 1          // CTAs launched per resident slot
 #endif
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(XT_WARPS * 32, K2_MINB) k_find_points(const __
     constexpr int R = decltype(RS)::value;
     const unsigned int off = (unsigned int)clampi(r, 0, h - 1) * (unsigned int)pitch;
 #pragma unroll
-    for (int p = 0; p < NPL; p++) ring[R][p] = dog[poff[p] + off];
+    for (int p = 0; p < NPL; p++) ring[R][p] = K2_LOAD(dog + (poff[p] + off));
   };
   auto place = [&](auto SLOT, auto RS) {
     constexpr int S = decltype(SLOT)::value, R = decltype(RS)::value;
