@@ -63,7 +63,12 @@ def test_reference_cxx_api_is_exported():
                 "ScaleDown(cuImage&, cuImage&, float)",
                 "MatchSiftData(SiftData&, SiftData&, MatchSiftDistance, float, float, MatchType)",
                 "FindHomography(SiftData&, float*, int*, int, float, float, float)",
-                "ImproveHomography(SiftData&, float*, int, float, float, float)"):
+                "ImproveHomography(SiftData&, float*, int, float, float, float)",
+                # next rows: extras/rigidTransform.h and the OpenCV-free part of extras/debug.h
+                "EstimateRigidTransformH(float const*, float*, int*, int, int, float, RigidTransformType, int*, char*)",
+                "ReadVLFeatSiftData(SiftData&, char const*)", "ReadMATLABMatchIndices(char const*, unsigned int*, unsigned int*)",
+                "ReadMATLABRANSAC(char const*, std::vector<int, std::allocator<int> >&, float*)",
+                "AddSiftData(SiftData&, SiftPoint*, int)", "PrintSiftData(SiftData&)"):
         assert sym in out, sym
 
 
