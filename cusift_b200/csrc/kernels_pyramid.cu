@@ -193,8 +193,14 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
 #endif
 constexpr int V2_QUAD = 4;                      // float2 slots per quad
 constexpr int V2_ROW = (NT / 4) * V2_QUAD;      // float2 slots per (batch row, level)
-constexpr int ROWS2 = 16;                       // output rows per CTA (large octaves)
-constexpr int ROWS2_SMALL = 4;                  // ... when the octave would not fill the GPU otherwise: the
+#ifndef K1_ROWS
+#define K1_ROWS 16
+#endif
+#ifndef K1_ROWS_SMALL
+#define K1_ROWS_SMALL 4
+#endif
+constexpr int ROWS2 = K1_ROWS;                  // output rows per CTA (large octaves)
+constexpr int ROWS2_SMALL = K1_ROWS_SMALL;                  // ... when the octave would not fill the GPU otherwise: the
                                                 // row loop is what a small octave's launch waits for
 constexpr size_t K1V2_SMEM = sizeof(float2) * (BATCH * NLEV * V2_ROW + BATCH * NT);
 
