@@ -516,7 +516,15 @@ void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2,
   const int nq_pad = tc_pad(n1), nc_pad = tc_pad(n2);
   const int ctiles = nc_pad / TC_CT;
   const int tiles_per_split = (ctiles + n_splits - 1) / n_splits;
-  cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC);
+  {   // > 48 KB of dynamic shared memory needs the opt-in, once per device
+    static bool opted[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
+      cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC);
+      if (dev >= 0 && dev < 64) opted[dev] = true;
+    }
+  }
   dim3 grd(nq_pad / TC_QT, n_splits);
   k_match_tc<<<grd, TC_THREADS, SMEM_TC, st>>>(reinterpret_cast<const __half *>(q_packed), nq_pad,
                                                reinterpret_cast<const __half *>(c_packed), n2, nc_pad, tiles_per_split,

@@ -448,8 +448,7 @@ DogWeights2 dup_weights(const DogWeights &wts) {
 template <bool kDown, int kRows>
 void launch_blur_dog2(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next, int npitch,
                       DownK dk, cudaStream_t st) {
-  // > 48 KB of dynamic shared memory would need the opt-in; harmless (per device, cheap) for the 36 KB used now
-  cudaFuncSetAttribute(k_blur_dog2<kDown, kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1V2_SMEM);
+  static_assert(K1V2_SMEM <= 48 * 1024, "needs cudaFuncAttributeMaxDynamicSharedMemorySize above 48 KB");
   dim3 grd((w + 2 * TW - 1) / (2 * TW), (h + kRows - 1) / kRows);
   k_blur_dog2<kDown, kRows><<<grd, NT, K1V2_SMEM, st>>>(base, w, h, pitch, dog, dup_weights(wts), next, npitch, dk);
 }
