@@ -26,7 +26,7 @@ inline int iAlignUp(int a, int b) { return (a % b != 0) ? (a - a % b + b) : a; }
 struct Octave {
   int w = 0, h = 0, pitch = 0;
   float *base = nullptr;   // octave base image (octave 0: the caller's frame or slot->img0)
-  float *dog = nullptr;    // 7 planes, plane stride pitch*h
+  float *dog = nullptr;    // 7 planes, layout CSB_DOG_PS / CSB_DOG_RS (csb_internal.h)
   cudaTextureObject_t tex = 0;
 };
 
@@ -1216,8 +1216,8 @@ int csb_debug_octave(csb_ctx *ctx, int oct, float *h_base, float *h_dog, int *w,
   }
   if (h_dog) {
     for (int i = 0; i < CSB_NUM_DOG; i++)
-      CSB_CHECK(ctx, cudaMemcpy2D(h_dog + (size_t)i * o.w * o.h, sizeof(float) * o.w, o.dog + (size_t)i * o.pitch * o.h,
-                                  sizeof(float) * o.pitch, sizeof(float) * o.w, o.h, cudaMemcpyDeviceToHost));
+      CSB_CHECK(ctx, cudaMemcpy2D(h_dog + (size_t)i * o.w * o.h, sizeof(float) * o.w, o.dog + (size_t)i * CSB_DOG_PS(o.pitch, o.h),
+                                  sizeof(float) * CSB_DOG_RS(o.pitch), sizeof(float) * o.w, o.h, cudaMemcpyDeviceToHost));
   }
   return 0;
 }

@@ -10,6 +10,20 @@
 #define CSB_NUM_LEVELS (CSB_NUM_SCALES + 3)   // blur levels per octave (LAPLACE_S, cuSIFT_D.h:23)
 #define CSB_NUM_DOG (CSB_NUM_SCALES + 2)      // DoG planes per octave
 
+// Layout of the 7 DoG planes of an octave (internal: only k_blur_dog*, k_find_points and csb_debug_octave
+// see it).  Element (plane p, row y, column x) lives at  dog[p * csb_dog_ps + y * csb_dog_rs + x].
+//   planar      (the reference's): ps = pitch * h, rs = pitch
+//   interleaved (default here)   : ps = pitch,     rs = 7 * pitch  — the 7 planes of one image row are
+//     adjacent, so a CTA that streams a band of rows through all planes walks ONE contiguous region
+//     instead of seven regions megabytes apart.
+#ifndef CSB_DOG_PLANAR
+#define CSB_DOG_PS(pitch, h) ((size_t)(pitch))
+#define CSB_DOG_RS(pitch) ((size_t)(pitch) * CSB_NUM_DOG)
+#else
+#define CSB_DOG_PS(pitch, h) ((size_t)(pitch) * (size_t)(h))
+#define CSB_DOG_RS(pitch) ((size_t)(pitch))
+#endif
+
 // 9-tap symmetric Gaussian weights of the 8 blur levels of one octave, k[s][0..4]
 // = taps at distance 4,3,2,1,0 (same indexing as d_Kernel2, cuSIFT.cu:405-410).
 struct DogWeights {

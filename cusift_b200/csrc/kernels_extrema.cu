@@ -229,7 +229,8 @@ __global__ void __launch_bounds__((XT_WARPS + 1) * 32, K2_MINB) k_find_points(co
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int y0 = by * rows;
-  const size_t plane = (size_t)pitch * h;
+  const size_t plane = CSB_DOG_PS(pitch, h);
+  const int drow = (int)CSB_DOG_RS(pitch);                    // elements between consecutive rows of one plane
   // staged columns [s0, s0 + 128): the tile's 120 output columns with a 4-column halo, shifted inwards at
   // the image borders so that the 512-byte segment stays inside the row (pitch >= 128, multiple of 128)
   const int s0 = clampi(bx * XT_TW - 4, 0, pitch - ST_COLS);
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__((XT_WARPS + 1) * 32, K2_MINB) k_find_points(co
         mbar_expect_tx(s_full + s, ST_BYTES);
 #pragma unroll
         for (int j = 0; j < ST_ROWS; j++) {
-          const float *src = dog + (size_t)clampi(y0 - 1 + st * ST_ROWS + j, 0, h - 1) * pitch + s0;
+          const float *src = dog + (size_t)clampi(y0 - 1 + st * ST_ROWS + j, 0, h - 1) * drow + s0;
 #pragma unroll
           for (int p = 0; p < NPL; p++) bulk_g2s(&s_tile[s][j][p][0], src + (size_t)p * plane, ST_COLS * sizeof(float), s_full + s);
         }
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__((XT_WARPS + 1) * 32, K2_MINB) k_find_points(co
           ex = bx * XT_TW + (int)(en & 0x7fu), ey = y0 + (int)((en >> 7) & 0x3fu), es = (int)(en >> 13);
         }
         const bool inner = ex >= 1 && ex <= w - 2 && ey >= 1 && ey <= h - 2;
-        if (inner) emit = verify_refine(dog, plane, pitch, P, ex, ey, es, r);
+        if (inner) emit = verify_refine(dog, plane, drow, P, ex, ey, es, r);
       }
       emit_warp(emit, r, stage, oct_counter, max_pts, lane);
     }

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
   const int x0 = blockIdx.x * TW;
   const int y0 = blockIdx.y * ROWS;
   const int cx = clampi(x0 + t - 4, 0, w - 1);
-  const size_t plane = (size_t)pitch * h;
+  const size_t plane = CSB_DOG_PS(pitch, h), drow = CSB_DOG_RS(pitch);
   const int warp = t >> 5, lane = t & 31;
 
   float win[9];
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
             L[j] = tap9(W.k[s], v[j + 4], __fadd_rn(v[j + 3], v[j + 5]), __fadd_rn(v[j + 2], v[j + 6]),
                         __fadd_rn(v[j + 1], v[j + 7]), __fadd_rn(v[j], v[j + 8]));
           if (s > 0) {
-            float *o = dog + (size_t)(s - 1) * plane + (size_t)y * pitch + xo;
+            float *o = dog + (size_t)(s - 1) * plane + (size_t)y * drow + xo;
             const float d0 = __fsub_rn(prev[0], L[0]), d1 = __fsub_rn(prev[1], L[1]);
             const float d2 = __fsub_rn(prev[2], L[2]), d3 = __fsub_rn(prev[3], L[3]);
             if (xo + 3 < w) {
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NT, K1_MINB) k_blur_dog2(const float *__restri
   const int xA = blockIdx.x * (2 * TW), xB = xA + TW;         // first output column of strip A / B
   const int y0 = blockIdx.y * kRows;
   const int cA = clampi(xA + pos - 4, 0, w - 1), cB = clampi(xB + pos - 4, 0, w - 1);
-  const size_t plane = (size_t)pitch * h;
+  const size_t plane = CSB_DOG_PS(pitch, h), drow = CSB_DOG_RS(pitch);
 
   float2 win[8 + BATCH];
 #pragma unroll
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(NT, K1_MINB) k_blur_dog2(const float *__restri
 #pragma unroll
         for (int i = 0; i < 6; i++) ch[i] = 2 * (lane + (i >> 1)) + ((i & 1) ^ (((lane + (i >> 1)) >> 2) & 1));
         constexpr int LSTRIDE = V2_ROW / 2;                 // float4 units between levels
-        float *oA = dog + (size_t)y * pitch + xoA;          // plane 0; advanced by `plane` per level
+        float *oA = dog + (size_t)y * drow + xoA;           // plane 0; advanced by `plane` per level
         const bool fullA = xoA + 3 < w, fullB = xoB + 3 < w;
         const bool fast = __all_sync(__activemask(), fullA && fullB);
         float4 ld[6];                                       // software-pipelined shared loads (next level)
