@@ -28,6 +28,7 @@ struct Octave {
   float *base = nullptr;   // octave base image (octave 0: the caller's frame or slot->img0)
   float *dog = nullptr;    // 7 planes, layout CSB_DOG_PS / CSB_DOG_RS (csb_internal.h)
   cudaTextureObject_t tex = 0;
+  CUtensorMap dog_map;     // 2-D TMA descriptor over dog (k_find_points)
 };
 
 struct TexCacheEntry {
@@ -252,6 +253,8 @@ int slot_prepare(csb_ctx *ctx, Slot *s, int w, int h, int n_oct) {
   for (int o = 0; o < n_oct; o++) {
     s->oct[o].base = reinterpret_cast<float *>(base + off_base[o]);
     s->oct[o].dog = reinterpret_cast<float *>(base + off_dog[o]);
+    if (make_dog_tensor_map(&s->oct[o].dog_map, s->oct[o].dog, s->oct[o].h, s->oct[o].pitch))
+      return fail(ctx, CSB_E_INVALID, "cuTensorMapEncodeTiled failed for a DoG buffer");
     if (o > 0) {
       int rc = make_texture(ctx, s->oct[o].base, s->oct[o].w, s->oct[o].h, s->oct[o].pitch, &s->oct[o].tex);
       if (rc) return rc;
@@ -429,15 +432,17 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
   // its own list, k_orient_desc lays them out coarse -> fine, the reference's order (cuSIFT.cu:181-196)
   {
     ExtremaParams E;
+    ExtremaMaps M;
     extrema_params(p, &E);
     for (int o = 0; o < n_oct; o++) {
       if (!active[o]) continue;
+      M.m[E.n_oct] = oct[o].dog_map;
       ExtremaOctave &X = E.oct[E.n_oct++];
       X.dog = oct[o].dog; X.w = oct[o].w; X.h = oct[o].h; X.pitch = oct[o].pitch; X.octave = o;
     }
     const int n_ctas = plan_find_points(&E, ctx->sm_count);
     LaunchScope ls(ctx, s, "find_points");
-    launch_find_points(E, n_ctas, s->d_stage, s->d_counter, max_pts, st);
+    launch_find_points(E, M, n_ctas, s->d_stage, s->d_counter, max_pts, st);
   }
   {
     OctaveTexSet T;

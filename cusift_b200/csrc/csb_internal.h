@@ -2,6 +2,7 @@
 #ifndef CSB_INTERNAL_H
 #define CSB_INTERNAL_H
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -57,6 +58,15 @@ struct ExtremaParams {
   ExtremaOctave oct[CSB_MAX_OCTAVES];
 };
 
+// One 2-D TMA descriptor per octave over its row-interleaved DoG buffer viewed as a (pitch x 7h) matrix:
+// a box of 128 columns x 21 matrix rows is "3 image rows x 7 planes", i.e. one pipeline stage of
+// k_find_points in ONE cp.async.bulk.tensor (index = ExtremaParams::oct[] index).
+struct alignas(64) ExtremaMaps {
+  CUtensorMap m[CSB_MAX_OCTAVES];
+};
+// encodes the descriptor of one octave (host; returns 0 on success)
+int make_dog_tensor_map(CUtensorMap *out, const float *dog, int h, int pitch);
+
 // Per-octave view handed to the orientation/descriptor kernel.
 struct OctaveTexSet {
   cudaTextureObject_t tex[CSB_MAX_OCTAVES];
@@ -70,8 +80,8 @@ void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog
                           int npitch, const float k[3], cudaStream_t st);
 // fills ep.rows / tiles_x / cta_begin from the octave geometry already in ep.oct[]; returns the grid size
 int plan_find_points(ExtremaParams *ep, int sm_count);
-void launch_find_points(const ExtremaParams &ep, int n_ctas, KpStage *d_stage, unsigned int *d_counter, int max_pts,
-                        cudaStream_t st);
+void launch_find_points(const ExtremaParams &ep, const ExtremaMaps &maps, int n_ctas, KpStage *d_stage,
+                        unsigned int *d_counter, int max_pts, cudaStream_t st);
 // subs[o] = subsampling of octave o (multiplies coords2D / scale in the final record)
 void launch_orient_desc(const OctaveTexSet &texs, int n_oct, const float *subs, const KpStage *d_stage, csb_sift_point *d_sift,
                         unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st);

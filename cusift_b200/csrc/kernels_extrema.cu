@@ -79,10 +79,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+// one 2-D tiled TMA load: box (ST_COLS x 21 matrix rows) at (x, yp) of the tensor map -> shared memory
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int x, int yp, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                    smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               "l"(map), "r"(x), "r"(yp), "r"(smem_u32(bar))
                : "memory");
 }
 
@@ -202,11 +203,14 @@ __device__ __forceinline__ void emit_warp(bool emit, const Refined &r, KpStage *
 }
 
 __global__ void __launch_bounds__((XT_WARPS + 1) * 32, K2_MINB) k_find_points(const __grid_constant__ ExtremaParams P,
+                                                                              const __grid_constant__ ExtremaMaps TM,
                                                                               KpStage *__restrict__ d_stage,
                                                                               unsigned int *__restrict__ counter,
                                                                               int max_pts, int cap) {
-  // Warp-specialised: warp 4 is the LOADER (one elected lane issues 512-byte bulk copies, 21 per stage,
-  // through the TMA unit into a 3-stage shared-memory ring, completion on mbarriers); warps 0-3 scan.
+  // Warp-specialised: warp 4 is the LOADER (one elected lane issues ONE 2-D tiled TMA load per stage —
+  // 128 columns x (3 rows x 7 planes), 10.5 KB — into a 3-stage shared-memory ring, completion on
+  // mbarriers); warps 0-3 scan.  Out-of-image rows / columns of a box are zero-filled by the TMA unit:
+  // they only ever feed border pixels, which cannot be extrema.
   // With loads issued by the scanning warps themselves the kernel ran at 3.2 TB/s although the same access
   // pattern alone reaches about 5 TB/s: the memory pipeline only moved when the compute warps got round to it.
   __shared__ __align__(128) float s_tile[ST_N][ST_ROWS][NPL][ST_COLS];
@@ -231,9 +235,8 @@ __global__ void __launch_bounds__((XT_WARPS + 1) * 32, K2_MINB) k_find_points(co
   const int y0 = by * rows;
   const size_t plane = CSB_DOG_PS(pitch, h);
   const int drow = (int)CSB_DOG_RS(pitch);                    // elements between consecutive rows of one plane
-  // staged columns [s0, s0 + 128): the tile's 120 output columns with a 4-column halo, shifted inwards at
-  // the image borders so that the 512-byte segment stays inside the row (pitch >= 128, multiple of 128)
-  const int s0 = clampi(bx * XT_TW - 4, 0, pitch - ST_COLS);
+  // staged columns [s0, s0 + 128): the tile's 120 output columns with a 4-column halo
+  const int s0 = bx * XT_TW - 4;
   const int n_stages = (rows + 2 + ST_ROWS - 1) / ST_ROWS;    // source rows y0-1 .. y0+rows
   if (threadIdx.x == 0) {
     s_cnt = 0;
@@ -252,18 +255,13 @@ __global__ void __launch_bounds__((XT_WARPS + 1) * 32, K2_MINB) k_find_points(co
         const int s = st % ST_N;
         if (st >= ST_N) mbar_wait(s_empty + s, ((st / ST_N) - 1) & 1);
         mbar_expect_tx(s_full + s, ST_BYTES);
-#pragma unroll
-        for (int j = 0; j < ST_ROWS; j++) {
-          const float *src = dog + (size_t)clampi(y0 - 1 + st * ST_ROWS + j, 0, h - 1) * drow + s0;
-#pragma unroll
-          for (int p = 0; p < NPL; p++) bulk_g2s(&s_tile[s][j][p][0], src + (size_t)p * plane, ST_COLS * sizeof(float), s_full + s);
-        }
+        tma_load_2d(&s_tile[s][0][0][0], &TM.m[oi], s0, (y0 - 1 + st * ST_ROWS) * NPL, s_full + s);
       }
     }
   } else {
   // ===== scanning warps =====
   const int x = bx * XT_TW + warp * XT_COLS - 1 + lane;
-  const int tcol = clampi(x, 0, w - 1) - s0;                 // this lane's column inside the staged tile
+  const int tcol = clampi(x, 0, w - 1) - s0;                 // this lane's column inside the staged tile (0 .. 127)
   // image-border pixels can never be strict extrema (their clamped neighbours include
   // the pixel itself, cuSIFT_D.cu:416,427-429); lanes 0 and 31 are halo columns
   const bool colOK = (lane >= 1) && (lane <= XT_COLS) && (x >= 1) && (x <= w - 2);
@@ -384,8 +382,29 @@ int plan_find_points(ExtremaParams *ep, int sm_count) {
   return ctas;
 }
 
-void launch_find_points(const ExtremaParams &ep, int n_ctas, KpStage *d_stage, unsigned int *d_counter, int max_pts,
-                        cudaStream_t st) {
+int make_dog_tensor_map(CUtensorMap *out, const float *dog, int h, int pitch) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {   // the driver entry point, without linking libcuda
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)h * NPL};          // x, interleaved (row, plane)
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)ST_COLS, (cuuint32_t)(ST_ROWS * NPL)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(dog), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+void launch_find_points(const ExtremaParams &ep, const ExtremaMaps &maps, int n_ctas, KpStage *d_stage,
+                        unsigned int *d_counter, int max_pts, cudaStream_t st) {
   if (n_ctas <= 0) return;
   static int cap = 0;                                  // CSB_XT_CAP: shrink the per-CTA list (tests of the dense fallback)
   if (!cap) {
@@ -393,5 +412,5 @@ void launch_find_points(const ExtremaParams &ep, int n_ctas, KpStage *d_stage, u
     cap = e ? atoi(e) : XT_CAP;
     if (cap < 1 || cap > XT_CAP) cap = XT_CAP;
   }
-  k_find_points<<<n_ctas, (XT_WARPS + 1) * 32, 0, st>>>(ep, d_stage, d_counter, max_pts, cap);
+  k_find_points<<<n_ctas, (XT_WARPS + 1) * 32, 0, st>>>(ep, maps, d_stage, d_counter, max_pts, cap);
 }
