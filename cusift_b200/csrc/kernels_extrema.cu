@@ -49,7 +49,10 @@ constexpr int XT_MAX_ROWS = 36;      // output rows per CTA: a launch parameter,
 constexpr int NPL = CSB_NUM_DOG;     // 7 planes
 constexpr int XT_CAP = 1024;         // flagged pixels per CTA held for the dense second phase
 constexpr int ST_ROWS = 3;           // source rows per pipeline stage (one turn of the 3-row register window)
-constexpr int ST_N = 3;              // stages: 9 rows x 7 planes of loads in flight per CTA
+#ifndef K2_STAGES
+#define K2_STAGES 3
+#endif
+constexpr int ST_N = K2_STAGES;      // stages: 9 rows x 7 planes of loads in flight per CTA
 constexpr int ST_COLS = 128;         // columns staged per row: the 120 output columns + halo, 512 bytes
 constexpr uint32_t ST_BYTES = ST_ROWS * NPL * ST_COLS * sizeof(float);
 constexpr unsigned FULL = 0xffffffffu;
