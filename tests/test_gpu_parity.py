@@ -84,10 +84,13 @@ def check_vs_oracle(ours, orc):
     r = PU.compare_keypoints(ours, orc)
     assert r["n_ours"] == r["n_ref"] == r["matched"], r
     assert r["only_ours"] == 0 and r["only_ref"] == 0
-    assert r["pos_max"] < 5e-4 and r["scale_max"] < 1e-4, r      # MUFU.RCP / ex2 vs exact division
+    # measured on the B200: positions 1.5e-5 px, scales 7.6e-6 (MUFU.RCP / ex2 vs exact division), orientations
+    # 6.1e-5 deg, descriptors 97.9-99.5 % within 1e-4 relative L2 (median 1.7e-7, max 6.8e-4: a last-ulp angle
+    # difference occasionally moves a vote across a bin edge).  Tolerances (north_star): 1e-3 px, 1e-3 rad, 1e-4.
+    assert r["pos_max"] < 1e-4 and r["scale_max"] < 5e-5, r
     assert r["sharp_max"] < 1e-5 and r["edge_rel_max"] < 1e-5 and r["subs_equal"]
-    assert r["ori_within_tol"] > 0.92 and r["ori_median_deg"] < 0.005, r   # CPU texture emulation
-    assert r["desc_median"] < 2e-3, r
+    assert r["ori_within_tol"] == 1.0 and r["ori_max_deg"] < 1e-3, r       # the oracle carries the fitted texture-filter model
+    assert r["desc_within_tol"] >= 0.97 and r["desc_median"] < 1e-6 and r["desc_max"] < 2e-3, r
     return r
 
 
