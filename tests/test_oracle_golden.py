@@ -184,3 +184,20 @@ def test_rigid_transform_oracle_reproduces_matlab_rt():
     assert np.abs(got - Rt).max() < 1e-6
     R = got.reshape(3, 4)[:, :3]
     assert np.abs(R @ R.T - np.eye(3)).max() < 1e-6 and abs(np.linalg.det(R) - 1) < 1e-6
+
+
+def test_rigid_transform_oracle_planar_and_3d_recover_known_motion():
+    """estimateRigidTransform2D / 3D restatements on synthetic correspondences with 25 % outliers."""
+    r = np.random.default_rng(4)
+    mov = r.uniform(-1, 1, (400, 3)) + np.array([0, 0, 2.0])
+    a = 0.35
+    R = np.array([[np.cos(a), 0, -np.sin(a)], [0, 1, 0], [np.sin(a), 0, np.cos(a)]])      # rotation about y (planar x-z motion)
+    t = np.array([0.2, 0.0, -0.1])
+    ref = mov @ R.T + t
+    ref[:100] = r.uniform(-2, 2, (100, 3))
+    coord = np.ascontiguousarray(np.concatenate([ref, mov], 1), np.float32)
+    idx = np.stack([r.choice(400, 3, replace=False) for _ in range(64)]).astype(np.int32)
+    for type3d in (False, True):
+        Rt, n_inl, mask = O.rigid_transform(coord, idx, 1e-3 ** 2, type3d)
+        assert n_inl >= 295 and mask[100:].mean() > 0.98 and mask[:100].sum() <= 3
+        assert np.abs(Rt.reshape(3, 4)[:, :3] - R).max() < 1e-4 and np.abs(Rt.reshape(3, 4)[:, 3] - t).max() < 1e-4
