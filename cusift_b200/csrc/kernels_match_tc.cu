@@ -434,8 +434,13 @@ __global__ void __launch_bounds__(128) k_rescore(csb_sift_point *__restrict__ s1
       const float *pb = sc + (my_row - r0) * 129;
       const int tx = ci & 15;
       float sum = 0.0f;
-#pragma unroll 16
-      for (int i = 0; i < 128; i++) {
+      // k = (i + tx) & 127 for i = 0..127: the first 112 steps never wrap (tx <= 15), so they run off two
+      // base pointers with immediate offsets; only the last 16 need the mask.  Same FFMA order.
+      const float *qa = sq + tx, *pa = pb + tx;
+#pragma unroll
+      for (int i = 0; i < 112; i++) sum = __fmaf_rn(qa[i], pa[i], sum);
+#pragma unroll
+      for (int i = 112; i < 128; i++) {
         const int k = (i + tx) & 127;
         sum = __fmaf_rn(sq[k], pb[k], sum);
       }
