@@ -2,24 +2,26 @@
 //
 // Replaces FindPointsMulti_D (reference cuSIFT_D.cu:402-523, host side
 // cuSIFT.cu:424-455).  Same results, different structure:
-//   * ONE pass over the 7 DoG planes of an octave (28 B/pixel, each value fetched
-//     once) instead of 5 overlapping scale-blocks that re-read every plane ~3x.
-//     A warp owns 30 columns (+1 halo lane each side) and streams rows downwards;
-//     per plane a 3-row window lives in registers and horizontal neighbours come
-//     from warp shuffles.
+//   * ONE launch for all octaves, ONE pass over the 7 DoG planes (28 B/pixel, each value fetched
+//     once) instead of 5 overlapping scale-blocks per octave that re-read every plane ~3x.
+//   * warp-specialised CTA: a loader warp feeds a 3-stage shared-memory ring with one 2-D tiled TMA
+//     load per stage (3 rows x 7 planes x 128 columns; the DoG buffer is stored row-interleaved, so
+//     that box is one rectangle of a (pitch x 7h) matrix), mbarriers in both directions; four
+//     scanning warps own 30 columns each (+1 halo lane each side) and stream the rows out of the
+//     ring: per plane a 3-row window lives in registers, horizontal neighbours come from shuffles.
 //   * the scan is a conservative PREFILTER in packed fp16: every value travels as the
 //     half2 (rn(v), rn(-v)), so ONE 3-input packed max (VHMNMX) advances the maximum
 //     and the minimum network together (min/max issue at half rate on sm_100a and were
-//     the bound of the fp32 scan): per plane hx = max3(left, c, right), F = max3 over
-//     the three rows, M = max3(F[plane-1], F[plane], F[plane+1]).  Rounding is monotone,
-//     so a true fp32 extremum above the threshold always satisfies rn(v) == M and
+//     the bound of the fp32 scan).  The 3x3x3 maximum is taken rows first, planes second,
+//     columns last, so only the 5 per-scale partial maxima go through shuffles.  Rounding is
+//     monotone, so a true fp32 extremum above the threshold always satisfies rn(v) == M and
 //     rn(|v|) >= rn(thresh); the scan flags those pixels (plus fp16 ties).
 //   * flagged pixels go to a per-CTA list; after the scan the whole CTA applies the
 //     reference's STRICT fp32 comparison against each of the 26 neighbours
 //     (cuSIFT_D.cu:450-470) and its |v| > thresh test, refines the survivors and compacts
-//     them with warp ballots, one global atomicAdd per warp.  (The reference's 32-entry
-//     list silently wraps, cuSIFT_D.cu:455,465; here a pixel that finds the list full is
-//     verified and emitted on the spot by its own lane.)
+//     them with warp ballots into the octave's keypoint list, one global atomicAdd per warp.
+//     (The reference's 32-entry list silently wraps, cuSIFT_D.cu:455,465; here a tile whose
+//     flagged pixels exceed the list is re-examined pixel by pixel.)
 //   * the refinement is evaluated in the exact multiply-add order of the
 //     reference's sm_100a SASS, so x, y, scale, sharpness and edgeness are
 //     bit-identical to the reference's for the same DoG input.
@@ -38,9 +40,6 @@ constexpr int XT_WARPS = 4;
 constexpr int XT_TW = XT_COLS * XT_WARPS;   // 120 output columns per CTA
 #ifndef K2_MINB
 #define K2_MINB 6           // resident CTAs per SM (35 KB of shared memory each)
-#endif
-#ifndef K2_LOAD
-#define K2_LOAD(p) (*(p))    // plain cached load (variants tried: __ldcs, __ldg)
 #endif
 #ifndef K2_WAVES
 #define K2_WAVES 1          // CTAs launched per resident slot
