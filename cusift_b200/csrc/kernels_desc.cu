@@ -67,16 +67,10 @@ __device__ __forceinline__ float sumsq_tree(const float (&b)[4], int lane) {
 // whatever their angular bins are (the cell-major layout measured 72 % conflict wavefronts).
 constexpr int DBUF = 8 * 32;
 
-// Plain read-modify-write vote: the caller guarantees that no two lanes of the warp
-// target the same address in the same call (see the lane->cell mapping below).
-__device__ __forceinline__ void vote(float *q, float v) {
-  *q = __fadd_rn(*q, v);
-  __syncwarp();
-}
-
-// The two angular shares of one spatial share: q0 != q1 unless both are scratch (a lane's a1 and angp
-// differ, and a spilled a1 goes to the scratch cell), and at one vote site the 16 lanes of a half hit
-// 16 different cells, so both read-modify-writes can be in flight together.
+// The two angular shares of one spatial share as plain read-modify-writes: q0 != q1 (a lane's a1 and
+// angp differ; a spilled a1 is handled by the atomic pass instead), and at one vote site the 16 lanes of a
+// half hit 16 different cells, so no two lanes of the warp touch the same address in one call and both
+// read-modify-writes can be in flight together.
 __device__ __forceinline__ void vote2(bool ok0, float *q0, float v0, bool ok1, float *q1, float v1) {
   // predicated, not branched: a share without a destination (outside the 4x4 grid, or spilled) simply
   // makes no access, so the 32 lanes never meet in a bank

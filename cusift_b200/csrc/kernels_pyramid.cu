@@ -10,12 +10,13 @@
 // pinned with __fmul_rn/__fmaf_rn/__fadd_rn in the order the reference's own
 // sm_100a SASS evaluates it (FMUL k3*(a1+b1); FFMA c*k4; FFMA k2; k1; k0).
 //
-// Data movement: a CTA owns a strip of 120 output columns x ROWS output rows.
-// Thread t streams source column x0-4+t (clamped) downwards with coalesced 512-B
-// row reads, keeping the 9-row vertical window in registers.  Per batch of 4 rows
-// the 8 vertically-blurred levels go to shared memory ([4][8][128] floats), then
-// warp b filters row b horizontally, 4 adjacent outputs per lane from three
-// 128-bit shared loads per level, and stores the 7 DoG rows as 128-bit words.
+// Data movement (scalar kernel k_blur_dog; the packed kernel k_blur_dog2 further down is the one the
+// pipeline uses and processes two such strips as float2): a CTA owns a strip of 120 output columns x
+// ROWS output rows.  Thread t streams source column x0-4+t (clamped) downwards with coalesced 512-B
+// row reads, keeping the 9-row vertical window in registers.  Per batch of 4 rows the 8
+// vertically-blurred levels go to shared memory ([4][8][128] floats), then warp b filters row b
+// horizontally, 4 adjacent outputs per lane from three 128-bit shared loads per level, and stores the
+// 7 DoG rows as 128-bit words (DoG layout: csb_internal.h, CSB_DOG_PS / CSB_DOG_RS).
 // Algorithmic HBM traffic: 4 B read + 28 B (+1 B next octave) written per pixel.
 #include <cstdlib>
 
