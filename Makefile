@@ -15,7 +15,7 @@ all: lib demo oracle ref
 
 lib: $(LIB)
 
-build/obj/%.o: cusift_b200/csrc/%.cu cusift_b200/csrc/csb_internal.h include/cusift_b200.h $(wildcard include/cusift/*.h include/cusift/extras/*.h)
+build/obj/%.o: cusift_b200/csrc/%.cu cusift_b200/csrc/csb_internal.h cusift_b200/csrc/tma_util.h include/cusift_b200.h $(wildcard include/cusift/*.h include/cusift/extras/*.h)
 	@mkdir -p build/obj
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/obj/$*.ptxas.log || (cat build/obj/$*.ptxas.log; exit 1)
 

@@ -29,12 +29,16 @@ struct Octave {
   float *dog = nullptr;    // 7 planes, layout CSB_DOG_PS / CSB_DOG_RS (csb_internal.h)
   cudaTextureObject_t tex = 0;
   CUtensorMap dog_map;     // 2-D TMA descriptor over dog (k_find_points)
+  CUtensorMap src_map;     // 2-D TMA descriptor over base (k_pyramid); octave 0: valid for slot->img0 only
+  bool src_map_ok = false;
 };
 
 struct TexCacheEntry {
   const float *ptr;
   int w, h, pitch;
   cudaTextureObject_t tex;
+  CUtensorMap src_map;     // k_pyramid's descriptor over the same caller-owned frame
+  bool src_map_ok;
 };
 
 struct ProfRec {
@@ -259,23 +263,37 @@ int slot_prepare(csb_ctx *ctx, Slot *s, int w, int h, int n_oct) {
       int rc = make_texture(ctx, s->oct[o].base, s->oct[o].w, s->oct[o].h, s->oct[o].pitch, &s->oct[o].tex);
       if (rc) return rc;
     }
+    // octave 0's entry describes slot->img0 (the upload target); caller-owned frames go through tex_cache
+    if (pyramid_source_map(&s->oct[o].src_map, o == 0 ? s->img0 : s->oct[o].base, s->oct[o].w, s->oct[o].h, s->oct[o].pitch))
+      return fail(ctx, CSB_E_INVALID, "cuTensorMapEncodeTiled failed for an octave base");
+    s->oct[o].src_map_ok = true;
   }
   s->w = w; s->h = h; s->n_oct = n_oct;
   return 0;
 }
 
-int slot_tex0(csb_ctx *ctx, Slot *s, const float *ptr, int w, int h, int pitch, cudaTextureObject_t *out) {
+// Texture object + TMA descriptor over a caller-owned octave-0 frame (small per-slot cache keyed by geometry).
+int slot_tex0(csb_ctx *ctx, Slot *s, const float *ptr, int w, int h, int pitch, cudaTextureObject_t *out,
+              const CUtensorMap **map_out) {
   for (TexCacheEntry &e : s->tex_cache)
-    if (e.ptr == ptr && e.w == w && e.h == h && e.pitch == pitch) { *out = e.tex; return 0; }
+    if (e.ptr == ptr && e.w == w && e.h == h && e.pitch == pitch) {
+      *out = e.tex;
+      *map_out = e.src_map_ok ? &e.src_map : nullptr;
+      return 0;
+    }
   if (s->tex_cache.size() >= 256) {   // bounded: drop the oldest
     cudaDestroyTextureObject(s->tex_cache.front().tex);
     s->tex_cache.erase(s->tex_cache.begin());
   }
-  TexCacheEntry e{ptr, w, h, pitch, 0};
+  TexCacheEntry e;
+  memset(&e, 0, sizeof(e));
+  e.ptr = ptr; e.w = w; e.h = h; e.pitch = pitch;
   int rc = make_texture(ctx, ptr, w, h, pitch, &e.tex);
   if (rc) return rc;
+  e.src_map_ok = pyramid_tma_ok(ptr, pitch) && pyramid_source_map(&e.src_map, ptr, w, h, pitch) == 0;
   s->tex_cache.push_back(e);
   *out = e.tex;
+  *map_out = s->tex_cache.back().src_map_ok ? &s->tex_cache.back().src_map : nullptr;
   return 0;
 }
 
@@ -372,19 +390,22 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
 
   CSB_CHECK(ctx, cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int) * (1 + CSB_MAX_OCTAVES), st));   // count + run ends
 
-  // octave geometry, blur schedule (cuSIFT.cu:188) and per-octave constants
+  // octave geometry, blur schedule (cuSIFT.cu:188) and per-octave constants.  The DoG stack always uses the
+  // slot's pitch (iAlignUp(w,128)); the caller's pitch only describes the octave-0 source image.
   Octave oct[CSB_MAX_OCTAVES];
   for (int o = 0; o < n_oct; o++) oct[o] = s->oct[o];
   oct[0].base = const_cast<float *>(d_img0);
-  oct[0].pitch = pitch0;
-  if (d_img0 == s->img0) {
+  const int src_pitch0 = pitch0;
+  const CUtensorMap *src_map0 = nullptr;
+  if (d_img0 == s->img0 && pitch0 == s->oct[0].pitch) {
     if (!s->oct[0].tex) {
       int rc = make_texture(ctx, s->img0, w, h, pitch0, &s->oct[0].tex);
       if (rc) return rc;
     }
     oct[0].tex = s->oct[0].tex;
+    src_map0 = &s->oct[0].src_map;
   } else {
-    int rc = slot_tex0(ctx, s, d_img0, w, h, pitch0, &oct[0].tex);
+    int rc = slot_tex0(ctx, s, d_img0, w, h, pitch0, &oct[0].tex, &src_map0);
     if (rc) return rc;
   }
 
@@ -403,28 +424,80 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
   float k3[3];
   scale_down_kernel(k3);
 
-  // pyramid: fine -> coarse (each octave base feeds its DoG stack and the next base)
-  static const char *kNameFused[CSB_MAX_OCTAVES] = {"blur_dog_down_o0", "blur_dog_down_o1", "blur_dog_down_o2",
-                                                    "blur_dog_down_o3", "blur_dog_down_o4", "blur_dog_down_o5",
-                                                    "blur_dog_down_o6", "blur_dog_down_o7"};
-  static const char *kNameBlur[CSB_MAX_OCTAVES] = {"blur_dog_o0", "blur_dog_o1", "blur_dog_o2", "blur_dog_o3",
-                                                   "blur_dog_o4", "blur_dog_o5", "blur_dog_o6", "blur_dog_o7"};
-  for (int o = 0; o < n_oct; o++) {
-    const bool need_down = (o + 1 < n_oct);
-    DogWeights W;
-    if (active[o]) laplace_weights((float)initBlur[o], &W);
-    if (active[o] && need_down && !ctx->no_fuse) {
-      LaunchScope ls(ctx, s, kNameFused[o]);
-      launch_blur_dog_down(oct[o].base, oct[o].w, oct[o].h, oct[o].pitch, oct[o].dog, W, oct[o + 1].base,
-                           oct[o + 1].pitch, k3, st);
-    } else {
-      if (need_down) {
-        LaunchScope ls(ctx, s, "scale_down");
-        launch_scale_down(oct[o].base, oct[o].w, oct[o].h, oct[o].pitch, oct[o + 1].base, oct[o + 1].pitch, k3, st);
-      }
-      if (active[o]) {
-        LaunchScope ls(ctx, s, kNameBlur[o]);
-        launch_blur_dog(oct[o].base, oct[o].w, oct[o].h, oct[o].pitch, oct[o].dog, W, st);
+  if (src_map0 && !ctx->no_fuse) {
+    // TMA pyramid: (A) octave 0 fused with the downsample that seeds octave 1, (B) the remaining octave bases in one
+    // chain launch, (C) ALL coarser octaves in one launch.  Three launches instead of one per octave.
+    if (active[0]) {
+      PyramidParams A;
+      PyramidMaps MA;
+      A.n_oct = 1;
+      A.dk = DownK{k3[0], k3[1], k3[2]};
+      A.oct[0].dog = oct[0].dog; A.oct[0].w = oct[0].w; A.oct[0].h = oct[0].h; A.oct[0].dpitch = oct[0].pitch;
+      A.oct[0].next = n_oct > 1 ? oct[1].base : nullptr;
+      A.oct[0].npitch = n_oct > 1 ? oct[1].pitch : 0;
+      DogWeights W;
+      laplace_weights((float)initBlur[0], &W);
+      pyramid_set_weights(&A, 0, W);
+      MA.m[0] = *src_map0;
+      const int n_ctas = plan_pyramid(&A, ctx->sm_count);
+      LaunchScope ls(ctx, s, "pyramid_o0");
+      launch_pyramid(A, MA, n_ctas, n_oct > 1, st);
+    } else if (n_oct > 1) {
+      LaunchScope ls(ctx, s, "scale_down");
+      launch_scale_down(oct[0].base, oct[0].w, oct[0].h, src_pitch0, oct[1].base, oct[1].pitch, k3, st);
+    }
+    if (n_oct > 2) {
+      float *dst[CSB_MAX_OCTAVES];
+      int dw[CSB_MAX_OCTAVES], dh[CSB_MAX_OCTAVES], dp[CSB_MAX_OCTAVES];
+      for (int o = 2; o < n_oct; o++) { dst[o - 2] = oct[o].base; dw[o - 2] = oct[o].w; dh[o - 2] = oct[o].h; dp[o - 2] = oct[o].pitch; }
+      LaunchScope ls(ctx, s, "down_chain");
+      ctx->launches += (n_oct - 2 + 2) / 3 - 1;
+      launch_down_chain(oct[1].base, oct[1].w, oct[1].h, oct[1].pitch, dst, dw, dh, dp, n_oct - 2, k3, st);
+    }
+    PyramidParams B;
+    PyramidMaps MB;
+    B.n_oct = 0;
+    B.dk = DownK{k3[0], k3[1], k3[2]};
+    for (int o = 1; o < n_oct; o++) {
+      if (!active[o]) continue;
+      PyramidOctave &X = B.oct[B.n_oct];
+      X.dog = oct[o].dog; X.w = oct[o].w; X.h = oct[o].h; X.dpitch = oct[o].pitch; X.next = nullptr; X.npitch = 0;
+      DogWeights W;
+      laplace_weights((float)initBlur[o], &W);
+      pyramid_set_weights(&B, B.n_oct, W);
+      MB.m[B.n_oct] = oct[o].src_map;
+      B.n_oct++;
+    }
+    if (B.n_oct > 0) {
+      const int n_ctas = plan_pyramid(&B, ctx->sm_count);
+      LaunchScope ls(ctx, s, "pyramid_rest");
+      launch_pyramid(B, MB, n_ctas, false, st);
+    }
+  } else {
+    // scalar fallback (source not addressable by the TMA unit, or CSB_NO_FUSE=1): fine -> coarse, one launch per octave
+    static const char *kNameFused[CSB_MAX_OCTAVES] = {"blur_dog_down_o0", "blur_dog_down_o1", "blur_dog_down_o2",
+                                                      "blur_dog_down_o3", "blur_dog_down_o4", "blur_dog_down_o5",
+                                                      "blur_dog_down_o6", "blur_dog_down_o7"};
+    static const char *kNameBlur[CSB_MAX_OCTAVES] = {"blur_dog_o0", "blur_dog_o1", "blur_dog_o2", "blur_dog_o3",
+                                                     "blur_dog_o4", "blur_dog_o5", "blur_dog_o6", "blur_dog_o7"};
+    for (int o = 0; o < n_oct; o++) {
+      const bool need_down = (o + 1 < n_oct);
+      const int sp = o == 0 ? src_pitch0 : oct[o].pitch;
+      DogWeights W;
+      if (active[o]) laplace_weights((float)initBlur[o], &W);
+      if (active[o] && need_down && !ctx->no_fuse) {
+        LaunchScope ls(ctx, s, kNameFused[o]);
+        launch_blur_dog_down(oct[o].base, oct[o].w, oct[o].h, sp, oct[o].dog, oct[o].pitch, W, oct[o + 1].base,
+                             oct[o + 1].pitch, k3, st);
+      } else {
+        if (need_down) {
+          LaunchScope ls(ctx, s, "scale_down");
+          launch_scale_down(oct[o].base, oct[o].w, oct[o].h, sp, oct[o + 1].base, oct[o + 1].pitch, k3, st);
+        }
+        if (active[o]) {
+          LaunchScope ls(ctx, s, kNameBlur[o]);
+          launch_blur_dog(oct[o].base, oct[o].w, oct[o].h, sp, oct[o].dog, oct[o].pitch, W, st);
+        }
       }
     }
   }

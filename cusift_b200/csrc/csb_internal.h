@@ -72,12 +72,49 @@ struct OctaveTexSet {
   cudaTextureObject_t tex[CSB_MAX_OCTAVES];
 };
 
+// ---- k_pyramid (kernels_pyramid.cu): blur + DoG (+ downsample) of any set of octaves in ONE launch ----
+struct DogWeights2 {
+  float2 k[CSB_NUM_LEVELS][5];     // each tap duplicated {k, k} (operands of the packed f32x2 instructions)
+};
+struct DownK {
+  float k0, k1, k2;                // ScaleDown taps (cuSIFT.cu:320-338): k0 = outer, k1 = inner, k2 = centre
+};
+struct PyramidOctave {
+  float *dog;                      // 7 DoG planes, layout CSB_DOG_PS / CSB_DOG_RS of dpitch
+  float *next;                     // base of the next octave (written when the launch downsamples), else unused
+  int w, h, dpitch, npitch;
+  int rows;                        // output rows per CTA (multiple of 4)
+  int tiles_x;                     // CTAs per row band (one CTA = two 120-column strips)
+  int cta_begin;                   // first linear CTA index of this octave
+};
+struct PyramidParams {
+  int n_oct;
+  DownK dk;
+  PyramidOctave oct[CSB_MAX_OCTAVES];
+  DogWeights2 W[CSB_MAX_OCTAVES];  // index = oct[] index (the weights depend on the octave's initBlur)
+};
+// one 2-D TMA descriptor per octave over its BASE image (w x h floats, row pitch in bytes): box = 248 x 4
+struct alignas(64) PyramidMaps {
+  CUtensorMap m[CSB_MAX_OCTAVES];
+};
+int pyramid_source_map(CUtensorMap *out, const float *base, int w, int h, int pitch);
+bool pyramid_tma_ok(const float *base, int pitch);     // 16-byte aligned base, pitch multiple of 4 floats
+void pyramid_set_weights(PyramidParams *pp, int idx, const DogWeights &wts);
+// fills rows / tiles_x / cta_begin from the geometry already in pp->oct[]; returns the grid size
+int plan_pyramid(PyramidParams *pp, int sm_count);
+void launch_pyramid(const PyramidParams &pp, const PyramidMaps &maps, int n_ctas, bool down, cudaStream_t st);
+// octave bases dst[0..n-1] (each half the size of the one before) from `src` in ceil(n/3) launches
+void launch_down_chain(const float *src, int sw, int sh, int spitch, float *const *dst, const int *dw, const int *dh,
+                       const int *dpitch, int n, const float k[3], cudaStream_t st);
+
 // ---- kernel launchers (defined in the .cu files) ---------------------------
 void launch_scale_down(const float *src, int w, int h, int spitch, float *dst, int dpitch, const float k[3],
                        cudaStream_t st);
-void launch_blur_dog(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, cudaStream_t st);
-void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next,
-                          int npitch, const float k[3], cudaStream_t st);
+// scalar fallback of k_pyramid (sources the TMA unit cannot address; CSB_NO_FUSE=1)
+void launch_blur_dog(const float *base, int w, int h, int spitch, float *dog, int dpitch, const DogWeights &wts,
+                     cudaStream_t st);
+void launch_blur_dog_down(const float *base, int w, int h, int spitch, float *dog, int dpitch, const DogWeights &wts,
+                          float *next, int npitch, const float k[3], cudaStream_t st);
 // fills ep.rows / tiles_x / cta_begin from the octave geometry already in ep.oct[]; returns the grid size
 int plan_find_points(ExtremaParams *ep, int sm_count);
 void launch_find_points(const ExtremaParams &ep, const ExtremaMaps &maps, int n_ctas, KpStage *d_stage,

@@ -32,6 +32,7 @@
 #include <type_traits>
 
 #include "csb_internal.h"
+#include "tma_util.h"
 
 namespace {
 
@@ -57,36 +58,12 @@ constexpr uint32_t ST_BYTES = ST_ROWS * NPL * ST_COLS * sizeof(float);
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-// ---- PTX wrappers: mbarrier + 1-D bulk copies (cp.async.bulk -> UBLKCP, executed by the TMA unit) ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// one 2-D tiled TMA load: box (ST_COLS x 21 matrix rows) at (x, yp) of the tensor map -> shared memory
+using tma::mbar_arrive;
+using tma::mbar_expect_tx;
+using tma::mbar_init;
+using tma::mbar_wait;
 __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int x, int yp, uint64_t *bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(map), "r"(x), "r"(yp), "r"(smem_u32(bar))
-               : "memory");
+  tma::load_2d(dst_smem, map, x, yp, bar);
 }
 
 // packed fp16 helpers: p = (rn(v), rn(-v)); ptxas fuses the two max.f16x2 into one 3-input VHMNMX
@@ -385,24 +362,8 @@ int plan_find_points(ExtremaParams *ep, int sm_count) {
 }
 
 int make_dog_tensor_map(CUtensorMap *out, const float *dog, int h, int pitch) {
-  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {   // the driver entry point, without linking libcuda
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
-    encode = reinterpret_cast<EncodeFn>(fn);
-  }
-  const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)h * NPL};          // x, interleaved (row, plane)
-  const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)ST_COLS, (cuuint32_t)(ST_ROWS * NPL)};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(dog), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : (int)r;
+  // x, interleaved (row, plane): a (pitch x 7h) matrix
+  return csb_tmap_2d_f32(out, dog, (uint64_t)pitch, (uint64_t)h * NPL, (uint64_t)pitch * sizeof(float), ST_COLS, ST_ROWS * NPL);
 }
 
 void launch_find_points(const ExtremaParams &ep, const ExtremaMaps &maps, int n_ctas, KpStage *d_stage,

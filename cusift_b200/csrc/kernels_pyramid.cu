@@ -1,33 +1,37 @@
-// Gaussian scale-space for one octave: 8 blur levels -> 7 DoG planes, fused with
-// the 2x downsample that seeds the next octave, so the octave base image is read
-// from HBM once.
+// Gaussian scale-space: 8 blur levels -> 7 DoG planes per octave, fused with the 2x downsample that
+// seeds the next octave, so an octave base image is read from HBM once.
 //
 // Replaces (reference, danielsuo/cuSIFT):
 //   LaplaceMulti_D  cuSIFT_D.cu:525-553  (8 x separable 9-tap on texture fetches + DoG)
 //   ScaleDown_D     cuSIFT_D.cu:37-182   (5x5 separable blur + decimation)
 //
-// Results are bit-identical to the reference's: every multiply-add below is
-// pinned with __fmul_rn/__fmaf_rn/__fadd_rn in the order the reference's own
-// sm_100a SASS evaluates it (FMUL k3*(a1+b1); FFMA c*k4; FFMA k2; k1; k0).
+// Results are bit-identical to the reference's: every multiply-add below is pinned with
+// __fmul_rn/__fmaf_rn/__fadd_rn (or their packed f32x2 forms, each half an IEEE fp32 operation) in the
+// order the reference's own sm_100a SASS evaluates it (FMUL k3*(a1+b1); FFMA c*k4; FFMA k2; k1; k0).
 //
-// Data movement (scalar kernel k_blur_dog; the packed kernel k_blur_dog2 further down is the one the
-// pipeline uses and processes two such strips as float2): a CTA owns a strip of 120 output columns x
-// ROWS output rows.  Thread t streams source column x0-4+t (clamped) downwards with coalesced 512-B
-// row reads, keeping the 9-row vertical window in registers.  Per batch of 4 rows the 8
-// vertically-blurred levels go to shared memory ([4][8][128] floats), then warp b filters row b
-// horizontally, 4 adjacent outputs per lane from three 128-bit shared loads per level, and stores the
-// 7 DoG rows as 128-bit words (DoG layout: csb_internal.h, CSB_DOG_PS / CSB_DOG_RS).
-// Algorithmic HBM traffic: 4 B read + 28 B (+1 B next octave) written per pixel.
+// Kernels in this file:
+//   k_pyramid      the production kernel: ONE launch covers any set of octaves (a CTA looks its octave and
+//                  tile up in a table).  The octave base reaches shared memory through 2-D tiled TMA loads
+//                  (cp.async.bulk.tensor.2d -> UTMALDG, completion on mbarriers) into a 3-slot ring of
+//                  4-row chunks that runs ahead of the arithmetic; out-of-image parts of a box are
+//                  zero-filled by the TMA unit and never read (clamp-to-edge is applied to the indices).
+//   k_down_chain   octave bases k+1 .. k+3 from base k in one launch (tile-local recomputation of the
+//                  intermediate levels), so that all coarse octaves can then go through ONE k_pyramid launch.
+//   k_blur_dog     scalar fallback (source image not 16-byte aligned / pitch not a multiple of 4 floats:
+//                  TMA cannot address it), also selected by CSB_NO_FUSE=1.
+//   k_scale_down   stand-alone ScaleDown (cuSIFT.h:76).
+// Algorithmic HBM traffic of the pyramid: 4 B read + 28 B (+1 B next octave) written per pixel.
 #include <cstdlib>
 
 #include "csb_internal.h"
+#include "tma_util.h"
 
 namespace {
 
-constexpr int TW = 120;       // output columns per CTA
+constexpr int TW = 120;       // output columns per strip
 constexpr int NT = 128;       // threads = TW + 2*4 halo columns
 constexpr int BATCH = 4;      // rows per shared-memory batch (= warps per CTA)
-constexpr int ROWS = 32;      // output rows per CTA
+constexpr int ROWS = 32;      // output rows per CTA of the scalar kernel
 constexpr int NLEV = CSB_NUM_LEVELS;
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
@@ -58,13 +62,13 @@ __device__ __forceinline__ float down_v(float rm1, float r0, float r1, float r2,
   return t;
 }
 
-struct DownK {
-  float k0, k1, k2;
-};
-
+// ---------------------------------------------------------------------------------
+// Scalar fallback: a CTA owns 120 output columns x ROWS rows; thread t streams source column x0-4+t
+// (clamped) downwards with the 9-row window in registers, the 8 vertically blurred levels of 4 rows go
+// through shared memory, warp b filters row b horizontally.  Source pitch and DoG pitch are independent.
 template <bool kDown>
-__global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, int w, int h, int pitch,
-                                                 float *__restrict__ dog, const __grid_constant__ DogWeights W,
+__global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, int w, int h, int spitch,
+                                                 float *__restrict__ dog, int dpitch, const __grid_constant__ DogWeights W,
                                                  float *__restrict__ next, int npitch, DownK dk) {
   __shared__ __align__(16) float V[BATCH][NLEV][NT];
   __shared__ float Raw[kDown ? BATCH : 1][NT];
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
   const int x0 = blockIdx.x * TW;
   const int y0 = blockIdx.y * ROWS;
   const int cx = clampi(x0 + t - 4, 0, w - 1);
-  const size_t plane = CSB_DOG_PS(pitch, h), drow = CSB_DOG_RS(pitch);
+  const size_t plane = CSB_DOG_PS(dpitch, h), drow = CSB_DOG_RS(dpitch);
   const int warp = t >> 5, lane = t & 31;
 
   float win[9];
@@ -81,11 +85,9 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
   for (int i = 0; i < 9; i++) win[i] = 0.0f;
   float hw[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // down-sample window (threads < TW/2)
 
-  // source rows y0-4 .. y0+ROWS+3 stream through in batches of 4; the window is
-  // full (an output row exists) from the third batch on.
   float pre[BATCH];
 #pragma unroll
-  for (int b = 0; b < BATCH; b++) pre[b] = src[(size_t)clampi(y0 - 4 + b, 0, h - 1) * pitch + cx];
+  for (int b = 0; b < BATCH; b++) pre[b] = src[(size_t)clampi(y0 - 4 + b, 0, h - 1) * spitch + cx];
 
   constexpr int NB = (ROWS + 8) / BATCH;
   for (int nb = 0; nb < NB; nb++) {
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
     for (int b = 0; b < BATCH; b++) cur[b] = pre[b];
     if (nb + 1 < NB) {
 #pragma unroll
-      for (int b = 0; b < BATCH; b++) pre[b] = src[(size_t)clampi(r0 + BATCH + b, 0, h - 1) * pitch + cx];
+      for (int b = 0; b < BATCH; b++) pre[b] = src[(size_t)clampi(r0 + BATCH + b, 0, h - 1) * spitch + cx];
     }
     const bool hasOut = nb >= 2;             // block-uniform
 #pragma unroll
@@ -117,7 +119,6 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
     __syncthreads();
 
     if (hasOut) {
-      // warp `warp` filters batch row `warp` horizontally; lane q -> outputs 4q..4q+3
       const int y = r0 - 4 + warp;           // output row of V[warp]
       const int xo = x0 + 4 * lane;
       if (lane < TW / 4 && y < h && xo < w) {
@@ -152,7 +153,6 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
     }
 
     if constexpr (kDown) {
-      // threads 0..59: next-octave column x0/2+t, fed by source rows r0..r0+3
       if (t < TW / 2) {
 #pragma unroll
         for (int b = 0; b < BATCH; b++) {
@@ -162,8 +162,7 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
 #pragma unroll
           for (int i = 0; i < 4; i++) hw[i] = hw[i + 1];
           hw[4] = hv;
-          // window now holds rows r-4..r; output row j needs rows 2j-1..2j+3 = r-4..r
-          const int twoj = r - 3;
+          const int twoj = r - 3;            // window = rows r-4..r = 2j-1..2j+3
           if (twoj >= y0 && twoj < y0 + ROWS && !(twoj & 1)) {
             const int j = twoj >> 1, i = (x0 >> 1) + t;
             if (j < (h >> 1) && i < (w >> 1))
@@ -177,37 +176,32 @@ __global__ void __launch_bounds__(NT) k_blur_dog(const float *__restrict__ src, 
 }
 
 // ---------------------------------------------------------------------------------
-// Packed-fp32 version (the one the pipeline uses).  Blackwell issues two fp32
-// multiply-adds per instruction with FFMA2/FADD2/FMUL2 (fma.rn.f32x2): each half is an
-// ordinary IEEE single-precision operation, so results stay bit-identical while the
-// number of floating-point issue slots halves.  A CTA therefore processes TWO adjacent
-// 120-column strips in lock-step: every value is a float2 {strip A, strip B}.
+// k_pyramid.  Blackwell issues two fp32 multiply-adds per instruction with FFMA2/FADD2/FMUL2
+// (fma.rn.f32x2; measured 124 lane-ops/clk/SM, the same as scalar FFMA, in half the issue slots): each
+// half is an ordinary IEEE single-precision operation, so results stay bit-identical.  A CTA therefore
+// processes TWO adjacent 120-column strips in lock-step: every value is a float2 {strip A, strip B}.
+//
+// Source staging: the CTA's (rows+8) x 248 source rectangle arrives as 4-row chunks (one TMA box of
+// 248 x 4 floats each) in a 3-slot ring; the three first chunks are requested up front, chunk n+3 when
+// batch n has been consumed.  Thread = strip position: it reads its (clamped) column of both strips
+// from the chunk, keeps a 12-row register window that rotates by renaming (the batch loop is unrolled
+// three ways), writes the 8 vertically blurred levels of 4 rows to shared memory, then warp b filters
+// row b horizontally (4 outputs x 2 strips per lane) and stores the 7 DoG rows as 128-bit words.
 //
 // Shared-memory layout of the vertically blurred rows: a row of 128 float2 positions = 32 quads of 32 B,
 // no padding.  The horizontal pass reads one 16-byte chunk per lane with lane stride one quad (32 B),
 // so lanes q and q+4 of a quarter-warp would share a bank group; the two 16-byte halves of every quad
 // whose index has bit 2 set are therefore swapped (an XOR swizzle): 128-bit reads and the 64-bit writes
-// of the vertical pass (16 consecutive positions = 128 contiguous bytes) are both conflict-free, and the
-// tile is 32 KB instead of 48 KB, which lets more CTAs share an SM.
+// of the vertical pass are both conflict-free.
 #ifndef K1_MINB
-#define K1_MINB 4           // resident CTAs per SM the register budget is sized for
+#define K1_MINB 4             // resident CTAs per SM the register budget is sized for
 #endif
 constexpr int V2_QUAD = 4;                      // float2 slots per quad
 constexpr int V2_ROW = (NT / 4) * V2_QUAD;      // float2 slots per (batch row, level)
-#ifndef K1_ROWS
-#define K1_ROWS 16
-#endif
-#ifndef K1_ROWS_SMALL
-#define K1_ROWS_SMALL 4
-#endif
-constexpr int ROWS2 = K1_ROWS;                  // output rows per CTA (large octaves)
-constexpr int ROWS2_SMALL = K1_ROWS_SMALL;                  // ... when the octave would not fill the GPU otherwise: the
-                                                // row loop is what a small octave's launch waits for
-constexpr size_t K1V2_SMEM = sizeof(float2) * (BATCH * NLEV * V2_ROW + BATCH * NT);
-
-struct DogWeights2 {
-  float2 k[NLEV][5];   // each tap duplicated {k, k}
-};
+constexpr int PY_SRC_COLS = 2 * TW + 8;         // staged source columns (both strips + halo)
+constexpr int PY_SLOTS = 3;                     // ring of 4-row chunks
+constexpr uint32_t PY_CHUNK_BYTES = PY_SRC_COLS * BATCH * sizeof(float);   // 3968 = 31 * 128
+constexpr size_t PY_SMEM = sizeof(float2) * BATCH * NLEV * V2_ROW + PY_SLOTS * PY_CHUNK_BYTES + 64;
 
 __device__ __forceinline__ float2 tap9x2(const float2 (&k)[5], float2 c, float2 s1, float2 s2, float2 s3, float2 s4) {
   float2 t = __fmul2_rn(k[3], s1);
@@ -232,81 +226,119 @@ __device__ __forceinline__ float2 down_v2(float2 rm1, float2 r0, float2 r1, floa
   return t;
 }
 
-template <bool kDown, int kRows>
-__global__ void __launch_bounds__(NT, K1_MINB) k_blur_dog2(const float *__restrict__ src, int w, int h, int pitch,
-                                                  float *__restrict__ dog, const __grid_constant__ DogWeights2 W,
-                                                  float *__restrict__ next, int npitch, DownK dk) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *V = reinterpret_cast<float2 *>(smem_raw);          // [BATCH][NLEV][V2_ROW]
-  float2 *Raw = V + BATCH * NLEV * V2_ROW;                    // [BATCH][NT], plain position order
+// Vertical pass of one batch.  PH = batch index mod 3 fixes where the 12-row window starts in P[], so the
+// rotation costs no register moves.  The batch holds source rows r0 .. r0+3; the window then covers rows
+// r0-8 .. r0+3 and yields output rows r0-4 .. r0-1.
+template <int PH, bool kDown>
+__device__ __forceinline__ void py_vertical(float2 (&P)[12], float2 &last, const float *__restrict__ chunk,
+                                            const float *__restrict__ row0, float *chunk_w, float *row0_w, int r0, int h,
+                                            int colA, int colB, bool patchA, bool patchB, int pos, bool hasOut,
+                                            const DogWeights2 &W, float2 *__restrict__ V, int vslot) {
+#define PYWIN(i) P[((i) + 4 * PH) % 12]
+#pragma unroll
+  for (int b = 0; b < BATCH; b++) {
+    const int r = r0 + b;
+    if (r <= h - 1) {                          // CTA-uniform; rows past the image repeat the last one (clamp)
+      const float *src = (r < 0) ? row0 : chunk + b * PY_SRC_COLS;
+      last = make_float2(src[colA], src[colB]);
+      if constexpr (kDown) {
+        // positions outside the image get the clamped value written back, so that the downsample below can
+        // read its 5 taps without clamping (the TMA unit had zero-filled them)
+        float *dst = (r < 0) ? row0_w : chunk_w + b * PY_SRC_COLS;
+        if (patchA) dst[pos] = last.x;
+        if (patchB) dst[pos + TW] = last.y;
+      }
+    }
+    PYWIN(8 + b) = last;
+  }
+  if (hasOut) {
+#pragma unroll
+    for (int b = 0; b < BATCH; b++) {
+      const float2 c = PYWIN(b + 4);
+      const float2 s1 = __fadd2_rn(PYWIN(b + 3), PYWIN(b + 5));
+      const float2 s2 = __fadd2_rn(PYWIN(b + 2), PYWIN(b + 6));
+      const float2 s3 = __fadd2_rn(PYWIN(b + 1), PYWIN(b + 7));
+      const float2 s4 = __fadd2_rn(PYWIN(b), PYWIN(b + 8));
+#pragma unroll
+      for (int s = 0; s < NLEV; s++) V[(b * NLEV + s) * V2_ROW + vslot] = tap9x2(W.k[s], c, s1, s2, s3, s4);
+    }
+  }
+#undef PYWIN
+}
+
+// kMulti = false: the launch holds exactly one octave (index 0 is a compile-time constant, so the 40 filter
+// taps are constant-bank operands at fixed offsets instead of indexed loads).
+template <bool kDown, bool kMulti>
+__global__ void __launch_bounds__(NT, K1_MINB) k_pyramid(const __grid_constant__ PyramidParams P,
+                                                         const __grid_constant__ PyramidMaps TM) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *src_ring = reinterpret_cast<float *>(smem_raw);                                  // [PY_SLOTS][BATCH][PY_SRC_COLS]
+  float2 *V = reinterpret_cast<float2 *>(smem_raw + PY_SLOTS * PY_CHUNK_BYTES);           // [BATCH][NLEV][V2_ROW]
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + PY_SLOTS * PY_CHUNK_BYTES + sizeof(float2) * BATCH * NLEV * V2_ROW);
+
+  // which octave does this CTA belong to?
+  int oi = 0;
+  if constexpr (kMulti) {
+#pragma unroll 1
+    for (int i = 1; i < P.n_oct; i++)
+      if ((int)blockIdx.x >= P.oct[i].cta_begin) oi = i;
+  }
+  const PyramidOctave &O = P.oct[oi];
+  const DogWeights2 &W = P.W[oi];
+  const int w = O.w, h = O.h, rows = O.rows;
+  const int local = (int)blockIdx.x - O.cta_begin;
+  const int bx = local % O.tiles_x, by = local / O.tiles_x;
 
   const int t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
   const int pos = t;                                          // vertical phase: thread -> strip position
   // float2 slot of this position in a V row: quad * 4 + (index in quad, halves swapped when quad bit 2 is set)
   const int vslot = (pos & ~3) + ((pos & 3) ^ (((pos >> 4) & 1) << 1));
-  const int xA = blockIdx.x * (2 * TW), xB = xA + TW;         // first output column of strip A / B
-  const int y0 = blockIdx.y * kRows;
-  const int cA = clampi(xA + pos - 4, 0, w - 1), cB = clampi(xB + pos - 4, 0, w - 1);
-  const size_t plane = CSB_DOG_PS(pitch, h), drow = CSB_DOG_RS(pitch);
+  const int xA = bx * (2 * TW), xB = xA + TW;                 // first output column of strip A / B
+  const int xs = xA - 4;                                      // image column of staged column 0
+  const int y0 = by * rows;
+  const int colA = clampi(xs + pos, 0, w - 1) - xs, colB = clampi(xB - 4 + pos, 0, w - 1) - xs;
+  const bool patchA = colA != pos, patchB = colB != pos + TW;
+  float *dog = O.dog;
+  const size_t plane = CSB_DOG_PS(O.dpitch, h), drow = CSB_DOG_RS(O.dpitch);
+  const int NB = rows / BATCH + 2;
 
-  float2 win[8 + BATCH];
+  if (t == 0) {
 #pragma unroll
-  for (int i = 0; i < 8 + BATCH; i++) win[i] = make_float2(0.f, 0.f);
-  float2 hw[5];
+    for (int s = 0; s < PY_SLOTS; s++) tma::mbar_init(full + s, 1);
+    tma::mbar_fence_init();
 #pragma unroll
-  for (int i = 0; i < 5; i++) hw[i] = make_float2(0.f, 0.f);
-  const float2 dk0 = make_float2(dk.k0, dk.k0), dk1 = make_float2(dk.k1, dk.k1), dk2 = make_float2(dk.k2, dk.k2);
-
-  // two batches of source rows are kept in flight ahead of the window (load latency >> batch time)
-  float2 pre[BATCH], pre2[BATCH];
-#pragma unroll
-  for (int b = 0; b < BATCH; b++) {
-    const float *r = src + (size_t)clampi(y0 - 4 + b, 0, h - 1) * pitch;
-    pre[b] = make_float2(r[cA], r[cB]);
+    for (int s = 0; s < PY_SLOTS; s++) {                      // NB >= 3 always
+      tma::mbar_expect_tx(full + s, PY_CHUNK_BYTES);
+      tma::load_2d(src_ring + s * (BATCH * PY_SRC_COLS), &TM.m[oi], xs, y0 - 4 + s * BATCH, full + s);
+    }
   }
-#pragma unroll
-  for (int b = 0; b < BATCH; b++) {
-    const float *r = src + (size_t)clampi(y0 + b, 0, h - 1) * pitch;
-    pre2[b] = make_float2(r[cA], r[cB]);
-  }
+  __syncthreads();
 
-  constexpr int NB = (kRows + 8) / BATCH;
+  float2 win[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) win[i] = make_float2(0.f, 0.f);
+  float2 last = make_float2(0.f, 0.f);
+  float2 hc[3];                                               // downsample: row-filtered rows r0-3 .. r0-1
+#pragma unroll
+  for (int i = 0; i < 3; i++) hc[i] = make_float2(0.f, 0.f);
+  float2 hlast = make_float2(0.f, 0.f);
+  const float2 dk0 = make_float2(P.dk.k0, P.dk.k0), dk1 = make_float2(P.dk.k1, P.dk.k1), dk2 = make_float2(P.dk.k2, P.dk.k2);
+  float *row0 = src_ring + 1 * (BATCH * PY_SRC_COLS);         // image row 0 of a top-border tile: first row of chunk 1
+
   for (int nb = 0; nb < NB; nb++) {
-    const int r0 = y0 - 4 + nb * BATCH;      // first source row of this batch
-    // window holds source rows r0-8 .. r0+3 after this: shift by BATCH, append the batch
-#pragma unroll
-    for (int i = 0; i < 8; i++) win[i] = win[i + BATCH];
-#pragma unroll
-    for (int b = 0; b < BATCH; b++) {
-      win[8 + b] = pre[b];
-      pre[b] = pre2[b];
-    }
-    if (nb + 2 < NB) {
-#pragma unroll
-      for (int b = 0; b < BATCH; b++) {
-        const float *r = src + (size_t)clampi(r0 + 2 * BATCH + b, 0, h - 1) * pitch;
-        pre2[b] = make_float2(r[cA], r[cB]);
-      }
-    }
-    const bool hasOut = nb >= 2;             // block-uniform: window full
-    if constexpr (kDown) {
-#pragma unroll
-      for (int b = 0; b < BATCH; b++) Raw[b * NT + pos] = win[8 + b];
-    }
-    if (hasOut) {
-#pragma unroll
-      for (int b = 0; b < BATCH; b++) {
-        // output row r0+b-4: window rows b .. b+8, centre b+4
-        const float2 c = win[b + 4];
-        const float2 s1 = __fadd2_rn(win[b + 3], win[b + 5]);
-        const float2 s2 = __fadd2_rn(win[b + 2], win[b + 6]);
-        const float2 s3 = __fadd2_rn(win[b + 1], win[b + 7]);
-        const float2 s4 = __fadd2_rn(win[b], win[b + 8]);
-#pragma unroll
-        for (int s = 0; s < NLEV; s++) V[(b * NLEV + s) * V2_ROW + vslot] = tap9x2(W.k[s], c, s1, s2, s3, s4);
-      }
-    }
+    const int r0 = y0 - 4 + nb * BATCH;                       // first source row of this batch
+    const int slot = nb % PY_SLOTS;
+    float *chunk = src_ring + slot * (BATCH * PY_SRC_COLS);
+    tma::mbar_wait(full + slot, (nb / PY_SLOTS) & 1);
+    if (nb == 0 && y0 == 0) tma::mbar_wait(full + 1, 0);      // rows < 0 read image row 0, which is in chunk 1
+    const bool hasOut = nb >= 2;                              // block-uniform: window full
+    if (slot == 0)
+      py_vertical<0, kDown>(win, last, chunk, row0, chunk, row0, r0, h, colA, colB, patchA, patchB, pos, hasOut, W, V, vslot);
+    else if (slot == 1)
+      py_vertical<1, kDown>(win, last, chunk, row0, chunk, row0, r0, h, colA, colB, patchA, patchB, pos, hasOut, W, V, vslot);
+    else
+      py_vertical<2, kDown>(win, last, chunk, row0, chunk, row0, r0, h, colA, colB, patchA, patchB, pos, hasOut, W, V, vslot);
     __syncthreads();
 
     if (hasOut) {
@@ -377,31 +409,160 @@ __global__ void __launch_bounds__(NT, K1_MINB) k_blur_dog2(const float *__restri
     }
 
     if constexpr (kDown) {
-      // threads 0..59: next-octave columns xA/2+t and xB/2+t, fed by source rows r0..r0+3
+      // threads 0..59: next-octave columns xA/2+t and xB/2+t.  The batch's rows r0 .. r0+3 are row-filtered
+      // (5 taps read from the staged chunk, whose out-of-image positions the vertical pass patched); with the
+      // three rows carried over, output rows (r0-2)/2 [rows r0-3..r0+1] and r0/2 [rows r0-1..r0+3] follow.
       if (t < TW / 2) {
+        float2 hv[BATCH];
 #pragma unroll
         for (int b = 0; b < BATCH; b++) {
           const int r = r0 + b;
-          const float2 *rw = Raw + b * NT + 2 * t;
-          const float2 hv = down_h2(rw[2], rw[3], rw[4], rw[5], rw[6], dk0, dk1, dk2);
-#pragma unroll
-          for (int i = 0; i < 4; i++) hw[i] = hw[i + 1];
-          hw[4] = hv;
-          const int twoj = r - 3;   // window = rows r-4..r = 2j-1..2j+3
-          if (twoj >= y0 && twoj < y0 + kRows && !(twoj & 1)) {
-            const int j = twoj >> 1;
-            if (j < (h >> 1)) {
-              const float2 o = down_v2(hw[0], hw[1], hw[2], hw[3], hw[4], dk0, dk1, dk2);
-              const int iA = (xA >> 1) + t, iB = (xB >> 1) + t;
-              if (iA < (w >> 1)) next[(size_t)j * npitch + iA] = o.x;
-              if (iB < (w >> 1)) next[(size_t)j * npitch + iB] = o.y;
-            }
+          if (r <= h - 1) {
+            const float *rw = ((r < 0) ? row0 : chunk + b * PY_SRC_COLS) + 2 * t + 2;
+            hlast = down_h2(make_float2(rw[0], rw[TW]), make_float2(rw[1], rw[TW + 1]), make_float2(rw[2], rw[TW + 2]),
+                            make_float2(rw[3], rw[TW + 3]), make_float2(rw[4], rw[TW + 4]), dk0, dk1, dk2);
           }
+          hv[b] = hlast;
         }
+        const int iA = (xA >> 1) + t, iB = (xB >> 1) + t;
+        const int ja = (r0 - 2) >> 1, jb = r0 >> 1;
+        if (nb >= 2 && ja < (h >> 1)) {                       // 2*ja = r0-2 in [y0, y0+rows)
+          const float2 o = down_v2(hc[0], hc[1], hc[2], hv[0], hv[1], dk0, dk1, dk2);
+          if (iA < (w >> 1)) O.next[(size_t)ja * O.npitch + iA] = o.x;
+          if (iB < (w >> 1)) O.next[(size_t)ja * O.npitch + iB] = o.y;
+        }
+        if (nb >= 1 && nb + 1 < NB && jb < (h >> 1)) {        // 2*jb = r0 in [y0, y0+rows)
+          const float2 o = down_v2(hc[2], hv[0], hv[1], hv[2], hv[3], dk0, dk1, dk2);
+          if (iA < (w >> 1)) O.next[(size_t)jb * O.npitch + iA] = o.x;
+          if (iB < (w >> 1)) O.next[(size_t)jb * O.npitch + iB] = o.y;
+        }
+        hc[0] = hv[1];
+        hc[1] = hv[2];
+        hc[2] = hv[3];
       }
     }
     __syncthreads();
+    // the chunk has been consumed by everybody: refill its slot with the chunk three batches ahead
+    if (t == 0 && nb + PY_SLOTS < NB) {
+      tma::mbar_expect_tx(full + slot, PY_CHUNK_BYTES);
+      tma::load_2d(chunk, &TM.m[oi], xs, r0 + PY_SLOTS * BATCH, full + slot);
+    }
   }
+}
+
+// ---------------------------------------------------------------------------------
+// k_down_chain<N>: octave bases k+1 .. k+N (N <= 3) from base k in ONE launch.  A CTA owns a 4x4 tile of the
+// last level, the matching 8x8 / 16x16 tiles of the levels in between, and recomputes the halo each level
+// needs from the level below inside shared memory (2T+3 -> 4T+9 -> 8T+21 pixels per side), so there is no
+// grid-wide dependency between the levels.  Same arithmetic as ScaleDown_D (row filter, then the fork's
+// column filter); out-of-image coordinates are clamped at every level like the reference's loads
+// (cuSIFT_D.cu:65-67,78-79).
+constexpr int DC_T = 4;
+constexpr int DC_MAXL = 3;
+constexpr int DC_NT = 256;
+__host__ __device__ constexpr int dc_side(int levels_above) {   // region side at a level with `levels_above` coarser levels still to feed
+  return levels_above == 0 ? DC_T : 2 * dc_side(levels_above - 1) + 3;
+}
+
+struct ChainLevel {
+  float *ptr;
+  int w, h, pitch;
+};
+struct ChainParams {
+  const float *src;
+  int sw, sh, spitch;
+  ChainLevel lv[DC_MAXL];
+  int tiles_x;
+  DownK dk;
+};
+
+// one level: `in` holds the SI x SI region of level l-1 whose origin is (ixo, iyo); produces the SO x SO region of
+// level l with origin (oxo, oyo) = ((ixo+2)/2, (iyo+1)/2) into `out` and stores the owned part.  kClamp = false:
+// every region of the tile lies inside its image (all tiles but those on the image border), so region entry
+// (ry, cx) of level l reads columns 2cx .. 2cx+4 and rows 2ry .. 2ry+4 of the region below, no clamping.
+template <int SI, int SO, bool kClamp>
+__device__ __forceinline__ void dc_level(const float *__restrict__ in, float *__restrict__ mid, float *__restrict__ out,
+                                         int ixo, int iyo, int pw, int ph, int oxo, int oyo, const ChainLevel &L, int own,
+                                         int own_x, int own_y, const DownK &dk) {
+  const int cw = L.w, chh = L.h;
+  for (int e = threadIdx.x; e < SI * SO; e += DC_NT) {
+    const int ry = e / SO, cxo = e - ry * SO;
+    const float *r = in + ry * SI;
+    if constexpr (kClamp) {
+      // out-of-image coordinates are evaluated at their clamped coordinate.  Region-relative indices are clamped to
+      // the region too: tiles that exist only to cover an odd last column of a finer level hold no valid pixel of
+      // the coarser ones, whose values are then unused.
+      const int i = clampi(oxo + cxo, 0, cw - 1);
+      auto rc = [&](int c) { return clampi(clampi(c, 0, pw - 1) - ixo, 0, SI - 1); };
+      mid[e] = down_h(r[rc(2 * i - 2)], r[rc(2 * i - 1)], r[rc(2 * i)], r[rc(2 * i + 1)], r[rc(2 * i + 2)], dk.k0, dk.k1, dk.k2);
+    } else {
+      r += 2 * cxo;
+      mid[e] = down_h(r[0], r[1], r[2], r[3], r[4], dk.k0, dk.k1, dk.k2);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < SO * SO; e += DC_NT) {
+    const int ryo = e / SO, cxo = e - ryo * SO;
+    float v;
+    if constexpr (kClamp) {
+      const int j = clampi(oyo + ryo, 0, chh - 1);
+      const float *c = mid + cxo;
+      auto rr = [&](int r) { return clampi(clampi(r, 0, ph - 1) - iyo, 0, SI - 1) * SO; };
+      v = down_v(c[rr(2 * j - 1)], c[rr(2 * j)], c[rr(2 * j + 1)], c[rr(2 * j + 2)], c[rr(2 * j + 3)], dk.k0, dk.k1, dk.k2);
+    } else {
+      const float *c = mid + cxo + 2 * ryo * SO;
+      v = down_v(c[0], c[SO], c[2 * SO], c[3 * SO], c[4 * SO], dk.k0, dk.k1, dk.k2);
+    }
+    out[e] = v;
+    const int gx = oxo + cxo, gy = oyo + ryo;
+    if (gx >= own_x && gx < own_x + own && gy >= own_y && gy < own_y + own && gx < cw && gy < chh)
+      L.ptr[(size_t)gy * L.pitch + gx] = v;
+  }
+  __syncthreads();
+}
+
+template <int N, bool kClamp>
+__device__ __forceinline__ void dc_levels(float *bufA, float *bufB, float *bufC, const int *ox, const int *oy,
+                                          const ChainParams &C, int tx, int ty) {
+  constexpr int S0 = dc_side(N), S1 = dc_side(N - 1), S2 = N >= 2 ? dc_side(N - 2) : 1, S3 = N >= 3 ? dc_side(N - 3) : 1;
+  dc_level<S0, S1, kClamp>(bufA, bufB, bufC, ox[0], oy[0], C.sw, C.sh, ox[1], oy[1], C.lv[0], DC_T << (N - 1),
+                           tx * (DC_T << (N - 1)), ty * (DC_T << (N - 1)), C.dk);
+  if constexpr (N >= 2)
+    dc_level<S1, S2, kClamp>(bufC, bufB, bufA, ox[1], oy[1], C.lv[0].w, C.lv[0].h, ox[2], oy[2], C.lv[1], DC_T << (N - 2),
+                             tx * (DC_T << (N - 2)), ty * (DC_T << (N - 2)), C.dk);
+  if constexpr (N >= 3)
+    dc_level<S2, S3, kClamp>(bufA, bufB, bufC, ox[2], oy[2], C.lv[1].w, C.lv[1].h, ox[3], oy[3], C.lv[2], DC_T, tx * DC_T,
+                             ty * DC_T, C.dk);
+}
+
+template <int N>
+__global__ void __launch_bounds__(DC_NT) k_down_chain(const __grid_constant__ ChainParams C) {
+  constexpr int S0 = dc_side(N), S1 = dc_side(N - 1);
+  __shared__ float bufA[S0 * S0];          // level 0 region, later level 2
+  __shared__ float bufB[S0 * S1];          // row-filtered intermediate [in_rows][out_cols]
+  __shared__ float bufC[S1 * S1];          // level 1 region, later level 3
+  const int tx = blockIdx.x % C.tiles_x, ty = blockIdx.x / C.tiles_x;
+  // origin (column, row) of the region held at every level, from the last level backwards:
+  // level l-1 needs columns 2i-2 .. 2i+2 and rows 2j-1 .. 2j+3 of what level l holds
+  int ox[DC_MAXL + 1], oy[DC_MAXL + 1];
+  ox[N] = tx * DC_T; oy[N] = ty * DC_T;
+#pragma unroll
+  for (int l = N - 1; l >= 0; l--) {
+    ox[l] = 2 * ox[l + 1] - 2;
+    oy[l] = 2 * oy[l + 1] - 1;
+  }
+  for (int e = threadIdx.x; e < S0 * S0; e += DC_NT) {
+    const int ry = e / S0, rx = e - ry * S0;
+    bufA[e] = C.src[(size_t)clampi(oy[0] + ry, 0, C.sh - 1) * C.spitch + clampi(ox[0] + rx, 0, C.sw - 1)];
+  }
+  __syncthreads();
+  // interior tile: the region of every level (incl. the source) lies inside its image
+  bool inside = ox[0] >= 0 && oy[0] >= 0 && ox[0] + S0 <= C.sw && oy[0] + S0 <= C.sh;
+#pragma unroll
+  for (int l = 1; l <= N; l++)
+    inside = inside && ox[l] >= 0 && oy[l] >= 0 && ox[l] + dc_side(N - l) <= C.lv[l - 1].w && oy[l] + dc_side(N - l) <= C.lv[l - 1].h;
+  if (inside) dc_levels<N, false>(bufA, bufB, bufC, ox, oy, C, tx, ty);
+  else dc_levels<N, true>(bufA, bufB, bufC, ox, oy, C, tx, ty);
 }
 
 // Stand-alone ScaleDown (cuSIFT.h:76): one thread per destination pixel.
@@ -430,52 +591,100 @@ void launch_scale_down(const float *src, int w, int h, int spitch, float *dst, i
   k_scale_down<<<grd, blk, 0, st>>>(src, w, h, spitch, dst, dpitch, dk);
 }
 
-// CSB_K1_SCALAR=1 selects the scalar-fp32 kernels above (debugging aid; same results).
-static bool csb_use_scalar_pyramid() {
-  static const bool v = [] {
-    const char *e = getenv("CSB_K1_SCALAR");
-    return e && e[0] == '1';
-  }();
-  return v;
-}
-
-namespace {
-DogWeights2 dup_weights(const DogWeights &wts) {
-  DogWeights2 w2;
-  for (int s = 0; s < NLEV; s++)
-    for (int j = 0; j < 5; j++) w2.k[s][j] = make_float2(wts.k[s][j], wts.k[s][j]);
-  return w2;
-}
-template <bool kDown, int kRows>
-void launch_blur_dog2(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next, int npitch,
-                      DownK dk, cudaStream_t st) {
-  static_assert(K1V2_SMEM <= 48 * 1024, "needs cudaFuncAttributeMaxDynamicSharedMemorySize above 48 KB");
-  dim3 grd((w + 2 * TW - 1) / (2 * TW), (h + kRows - 1) / kRows);
-  k_blur_dog2<kDown, kRows><<<grd, NT, K1V2_SMEM, st>>>(base, w, h, pitch, dog, dup_weights(wts), next, npitch, dk);
-}
-// fewer than two CTAs per SM with 16-row tiles: use 4-row tiles (the frame's latency, not its SM time)
-inline bool small_octave(int w, int h) { return ((w + 2 * TW - 1) / (2 * TW)) * ((h + ROWS2 - 1) / ROWS2) < 2 * 148; }
-}  // namespace
-
-void launch_blur_dog(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, cudaStream_t st) {
+void launch_blur_dog(const float *base, int w, int h, int spitch, float *dog, int dpitch, const DogWeights &wts,
+                     cudaStream_t st) {
   DownK dk{0.f, 0.f, 0.f};
-  if (csb_use_scalar_pyramid()) {
-    dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
-    k_blur_dog<false><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, nullptr, 0, dk);
-    return;
-  }
-  if (small_octave(w, h)) launch_blur_dog2<false, ROWS2_SMALL>(base, w, h, pitch, dog, wts, nullptr, 0, dk, st);
-  else launch_blur_dog2<false, ROWS2>(base, w, h, pitch, dog, wts, nullptr, 0, dk, st);
+  dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
+  k_blur_dog<false><<<grd, NT, 0, st>>>(base, w, h, spitch, dog, dpitch, wts, nullptr, 0, dk);
 }
 
-void launch_blur_dog_down(const float *base, int w, int h, int pitch, float *dog, const DogWeights &wts, float *next,
-                          int npitch, const float k[3], cudaStream_t st) {
+void launch_blur_dog_down(const float *base, int w, int h, int spitch, float *dog, int dpitch, const DogWeights &wts,
+                          float *next, int npitch, const float k[3], cudaStream_t st) {
   DownK dk{k[0], k[1], k[2]};
-  if (csb_use_scalar_pyramid()) {
-    dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
-    k_blur_dog<true><<<grd, NT, 0, st>>>(base, w, h, pitch, dog, wts, next, npitch, dk);
-    return;
+  dim3 grd((w + TW - 1) / TW, (h + ROWS - 1) / ROWS);
+  k_blur_dog<true><<<grd, NT, 0, st>>>(base, w, h, spitch, dog, dpitch, wts, next, npitch, dk);
+}
+
+// ---- k_pyramid host side ------------------------------------------------------------------------
+int pyramid_source_map(CUtensorMap *out, const float *base, int w, int h, int pitch) {
+  return csb_tmap_2d_f32(out, base, (uint64_t)w, (uint64_t)h, (uint64_t)pitch * sizeof(float), PY_SRC_COLS, BATCH);
+}
+
+bool pyramid_tma_ok(const float *base, int pitch) {
+  return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && (pitch & 3) == 0;
+}
+
+void pyramid_set_weights(PyramidParams *pp, int idx, const DogWeights &wts) {
+  for (int s = 0; s < NLEV; s++)
+    for (int j = 0; j < 5; j++) pp->W[idx].k[s][j] = make_float2(wts.k[s][j], wts.k[s][j]);
+}
+
+// Rows per CTA for every octave of the launch (multiple of 4, <= 16): as large as possible while the whole
+// launch still fits in one wave of K1_MINB CTAs per SM, so that a lone frame fills the GPU and a CTA's
+// serial row loop is as short as the frame allows.
+int plan_pyramid(PyramidParams *pp, int sm_count) {
+  const long long slots = (long long)sm_count * K1_MINB;
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("CSB_K1_ROWS");
+    forced = e ? atoi(e) : 0;
   }
-  if (small_octave(w, h)) launch_blur_dog2<true, ROWS2_SMALL>(base, w, h, pitch, dog, wts, next, npitch, dk, st);
-  else launch_blur_dog2<true, ROWS2>(base, w, h, pitch, dog, wts, next, npitch, dk, st);
+  int rows = 16;
+  for (; rows > 4; rows -= 4) {
+    long long ctas = 0;
+    for (int i = 0; i < pp->n_oct; i++)
+      ctas += (long long)((pp->oct[i].w + 2 * TW - 1) / (2 * TW)) * ((pp->oct[i].h + rows - 1) / rows);
+    if (ctas * 2 > slots) break;          // at least half a wave: do not shrink the tiles any further
+  }
+  if (forced >= 4 && forced <= 16 && forced % 4 == 0) rows = forced;
+  int ctas = 0;
+  for (int i = 0; i < pp->n_oct; i++) {
+    PyramidOctave &o = pp->oct[i];
+    o.rows = rows;
+    o.tiles_x = (o.w + 2 * TW - 1) / (2 * TW);
+    o.cta_begin = ctas;
+    ctas += o.tiles_x * ((o.h + rows - 1) / rows);
+  }
+  return ctas;
+}
+
+void launch_pyramid(const PyramidParams &pp, const PyramidMaps &maps, int n_ctas, bool down, cudaStream_t st) {
+  if (n_ctas <= 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_pyramid<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PY_SMEM);
+    cudaFuncSetAttribute(k_pyramid<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PY_SMEM);
+    cudaFuncSetAttribute(k_pyramid<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PY_SMEM);
+    attr_set = true;
+  }
+  if (pp.n_oct > 1) k_pyramid<false, true><<<n_ctas, NT, PY_SMEM, st>>>(pp, maps);     // (never combined with `down`)
+  else if (down) k_pyramid<true, false><<<n_ctas, NT, PY_SMEM, st>>>(pp, maps);
+  else k_pyramid<false, false><<<n_ctas, NT, PY_SMEM, st>>>(pp, maps);
+}
+
+// dst[0..n-1] = successive half-size levels below `src`; at most 3 levels per launch (the caller's list is cut up)
+void launch_down_chain(const float *src, int sw, int sh, int spitch, float *const *dst, const int *dw, const int *dh,
+                       const int *dpitch, int n, const float k[3], cudaStream_t st) {
+  while (n > 0) {
+    const int m = n < DC_MAXL ? n : DC_MAXL;
+    ChainParams C;
+    C.src = src; C.sw = sw; C.sh = sh; C.spitch = spitch;
+    for (int l = 0; l < DC_MAXL; l++) C.lv[l] = l < m ? ChainLevel{dst[l], dw[l], dh[l], dpitch[l]} : ChainLevel{nullptr, 0, 0, 0};
+    C.dk = DownK{k[0], k[1], k[2]};
+    // tiles of the last level; a finer level with an odd size has one more pixel than twice the next one, so the
+    // grid must also cover every finer level's extent
+    int txn = 1, tyn = 1;
+    for (int l = 0; l < m; l++) {
+      const int own = DC_T << (m - 1 - l);
+      txn = txn > (dw[l] + own - 1) / own ? txn : (dw[l] + own - 1) / own;
+      tyn = tyn > (dh[l] + own - 1) / own ? tyn : (dh[l] + own - 1) / own;
+    }
+    C.tiles_x = txn;
+    if (m == 1) k_down_chain<1><<<txn * tyn, DC_NT, 0, st>>>(C);
+    else if (m == 2) k_down_chain<2><<<txn * tyn, DC_NT, 0, st>>>(C);
+    else k_down_chain<3><<<txn * tyn, DC_NT, 0, st>>>(C);
+    src = dst[m - 1]; sw = dw[m - 1]; sh = dh[m - 1]; spitch = dpitch[m - 1];
+    dst += m; dw += m; dh += m; dpitch += m;
+    n -= m;
+  }
 }

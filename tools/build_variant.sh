@@ -13,4 +13,4 @@ done
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart shared -o build/variants/$name.so build/variants/obj_$name/*.o
 grep -A1 "k_orient_desc\|k_find_points\|k_blur_dog2" build/variants/obj_$name/*.log | grep -E "registers|spill" | head -12
-rm -rf build/variants/obj_$name
+cp build/variants/obj_$name/kernels_pyramid.log build/variants/$name.pyramid.log; rm -rf build/variants/obj_$name

@@ -26,13 +26,13 @@ for k in range(48):
     ctx.extract_batch([dev[k % POOL][0]], W, H, pitch, prm, [ds[0]], [pins[0].ptr], MAXPTS)
 tab = ctx.profile_table()
 ctx.profile(False)
-grp = {"blur_dog": 0.0, "find_points": 0.0, "orient_desc": 0.0, "copy_out": 0.0}
+grp = {"pyramid_o0": 0.0, "down_chain": 0.0, "pyramid_rest": 0.0, "blur_dog": 0.0, "find_points": 0.0, "orient_desc": 0.0, "copy_out": 0.0}
 for name, v in tab.items():
     if v["launches"]:
         for g in grp:
             if name.startswith(g):
                 grp[g] += v["total_ms"] * 1e3 / 48
-o0 = {n: round(v["total_ms"] * 1e3 / max(v["launches"], 1), 1) for n, v in tab.items() if n.endswith("_o0")}
+o0 = {}
 NF = 512
 dl = [dev[k % POOL][0] for k in range(NF)]
 dsl = [ds[k % 16] for k in range(NF)]
