@@ -22,8 +22,12 @@ build/obj/%.o: cusift_b200/csrc/%.cu cusift_b200/csrc/csb_internal.h cusift_b200
 $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -cudart shared -o $@ $(OBJ)
 
-demo: build/csb_demo build/csb_ref_tests
+demo: build/csb_demo build/csb_ref_tests build/csb_improve
 build/csb_demo: tests/cpp/csb_demo.cpp $(LIB)
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O2 -std=c++17 -cudart shared -Iinclude -Iinclude/cusift -o $@ $< -Lcusift_b200 -lcusift_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../cusift_b200'
+
+build/csb_improve: tests/cpp/csb_improve.cpp $(LIB)
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O2 -std=c++17 -cudart shared -Iinclude -Iinclude/cusift -o $@ $< -Lcusift_b200 -lcusift_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../cusift_b200'
 

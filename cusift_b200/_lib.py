@@ -67,10 +67,14 @@ SIGNATURES = {
     "csb_rootsift": (_i, [_vp, _vp, _i]),
     "csb_match": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "csb_match_redo_blocks": (C.c_longlong, [_vp]),
+    "csb_match_domain_fallbacks": (C.c_longlong, [_vp]),
     "csb_find_homography": (_i, [_vp, _vp, _i, _ip, _i, C.c_float, _fp, _ip]),
     "csb_allpairs_match_ransac": (_i, [_vp, _i, C.POINTER(_vp), _ip, _i, _ip, _ip, C.POINTER(C.c_uint), _i, _i, C.c_float,
                                        C.c_float, C.c_float, C.c_uint, _fp, _ip, _ip]),
     "csb_sample_hash": (C.c_uint, [C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]),
+    "csb_allpairs_match_ransac_improve": (_i, [_vp, _i, C.POINTER(_vp), _ip, _i, _ip, _ip, C.POINTER(C.c_uint), _i, _i, C.c_float,
+                                               C.c_float, C.c_float, C.c_uint, _i, C.c_float, _fp, _ip, _ip, _fp, _ip]),
+    "csb_improve_homography": (_i, [_vp, _vp, _i, _fp, _i, C.c_float, C.c_float, C.c_float, _ip, _vp]),
     "csb_debug_octave": (_i, [_vp, _i, _fp, _fp, _ip, _ip]),
     "csb_profile_enable": (_i, [_vp, _i]),
     "csb_profile_reset": (_i, [_vp]),

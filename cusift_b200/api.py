@@ -305,10 +305,26 @@ class Context:
         finally:
             self.free(d)
 
+    def improve_homography(self, pts: np.ndarray, H: np.ndarray, loops: int = 5, min_score: float = 0.0,
+                           max_ambiguity: float = 0.80, thresh: float = 3.0):
+        """csb_improve_homography on a device copy of `pts`: returns (H [9], num_fit, pts with match_error)."""
+        d = self.upload_sift(pts)
+        try:
+            Hc = np.ascontiguousarray(H, np.float32).copy()
+            n = C.c_int(0)
+            out = np.ascontiguousarray(pts.copy())
+            self._check(self._L.csb_improve_homography(self.h, d, len(pts), Hc.ctypes.data_as(C.POINTER(C.c_float)), loops,
+                                                       min_score, max_ambiguity, thresh, C.byref(n), out.ctypes.data),
+                        "csb_improve_homography")
+            return Hc, n.value, out
+        finally:
+            self.free(d)
+
     def allpairs(self, d_sifts, counts, pairs, distance="l2", num_loops=1024, min_score=0.0, max_ambiguity=0.80,
-                 thresh=5.0, seed=1, pair_ids=None):
+                 thresh=5.0, seed=1, pair_ids=None, improve_loops=0, improve_thresh=3.0):
         """csb_allpairs_match_ransac over device SiftPoint arrays (raw pointers).  pairs: [(i, j)].
-        Returns (H [n_pairs, 9], inliers [n_pairs], n_valid [n_pairs])."""
+        Returns (H [n_pairs, 9], inliers [n_pairs], n_valid [n_pairs]); with improve_loops > 0 also
+        (H_improved [n_pairs, 9], num_fit [n_pairs]) from the ImproveHomography step appended to every pair."""
         n_sets, n_pairs = len(d_sifts), len(pairs)
         ptrs = (C.c_void_p * n_sets)(*d_sifts)
         cnts = np.ascontiguousarray(counts, np.int32)
@@ -319,6 +335,16 @@ class Context:
         inl = np.zeros(max(n_pairs, 1), np.int32)
         nv = np.zeros(max(n_pairs, 1), np.int32)
         ip = C.POINTER(C.c_int)
+        if improve_loops > 0:
+            H2 = np.zeros((max(n_pairs, 1), 9), np.float32)
+            nf = np.zeros(max(n_pairs, 1), np.int32)
+            self._check(self._L.csb_allpairs_match_ransac_improve(
+                self.h, n_sets, ptrs, cnts.ctypes.data_as(ip), n_pairs, pi.ctypes.data_as(ip), pj.ctypes.data_as(ip),
+                None if ids is None else ids.ctypes.data_as(C.POINTER(C.c_uint)), 1 if distance == "l2" else 0, num_loops,
+                min_score, max_ambiguity, thresh, seed, improve_loops, improve_thresh, H.ctypes.data_as(C.POINTER(C.c_float)),
+                inl.ctypes.data_as(ip), nv.ctypes.data_as(ip), H2.ctypes.data_as(C.POINTER(C.c_float)), nf.ctypes.data_as(ip)),
+                "csb_allpairs_match_ransac_improve")
+            return H[:n_pairs], inl[:n_pairs], nv[:n_pairs], H2[:n_pairs], nf[:n_pairs]
         self._check(self._L.csb_allpairs_match_ransac(
             self.h, n_sets, ptrs, cnts.ctypes.data_as(ip), n_pairs, pi.ctypes.data_as(ip), pj.ctypes.data_as(ip),
             None if ids is None else ids.ctypes.data_as(C.POINTER(C.c_uint)), 1 if distance == "l2" else 0, num_loops,

@@ -108,11 +108,18 @@ struct csb_ctx {
   size_t tc_sl_cap = 0, tc_blk_cap = 0;
   int *h_tc_count = nullptr;
   long long tc_redo_blocks = 0;      // 16-query blocks redone exactly (diagnostics)
+  long long tc_domain_fallbacks = 0; // calls / pairs routed to the exact kernel because a set violated the fp16 precondition
+  int *ap_flags = nullptr, *h_ap_flags = nullptr;   // per-set out-of-domain flags of the all-pairs path
+  size_t ap_flags_cap = 0;
   // homography scratch
   float *d_coord = nullptr, *d_homo = nullptr;
   int *d_rand = nullptr, *d_counts = nullptr;
   size_t coord_cap = 0, loops_cap = 0;
   int *h_counts = nullptr;
+  // ImproveHomography scratch: device {H_in[9], H_out[9], numfit, job}, pinned host mirror
+  char *ih_dev = nullptr, *ih_host = nullptr;
+  char *ap_jobs = nullptr;           // all-pairs: one ImproveJob per pair
+  size_t ap_jobs_cap = 0;
   // all-pairs scratch (grow-only, csb_allpairs_match_ransac)
   static constexpr int AP_STREAMS = 8;
   cudaStream_t ap_stream[AP_STREAMS] = {};
@@ -666,6 +673,11 @@ void csb_ctx_destroy(csb_ctx *ctx) {
   if (ctx->ap_scratch) cudaFree(ctx->ap_scratch);
   if (ctx->ap_pack) cudaFree(ctx->ap_pack);
   if (ctx->ap_result) cudaFree(ctx->ap_result);
+  if (ctx->ih_dev) cudaFree(ctx->ih_dev);
+  if (ctx->ih_host) cudaFreeHost(ctx->ih_host);
+  if (ctx->ap_jobs) cudaFree(ctx->ap_jobs);
+  if (ctx->ap_flags) cudaFree(ctx->ap_flags);
+  if (ctx->h_ap_flags) cudaFreeHost(ctx->h_ap_flags);
   if (ctx->tc_count) cudaFree(ctx->tc_count);
   if (ctx->h_tc_count) cudaFreeHost(ctx->h_tc_count);
   if (ctx->d_coord) cudaFree(ctx->d_coord);
@@ -1038,11 +1050,12 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
       CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_count, 256));
       CSB_CHECK(ctx, cudaHostAlloc((void **)&ctx->h_tc_count, 256, cudaHostAllocDefault));
     }
+    CSB_CHECK(ctx, cudaMemsetAsync(ctx->tc_count + 4, 0, sizeof(int), s->stream));   // out-of-domain flag of this call
     {
       LaunchScope ls(ctx, s, "match_pack");
       ctx->launches += 1;
-      launch_pack_f16((const csb_sift_point *)sets[0], ns[0], ctx->tc_pack[0], s->stream);
-      launch_pack_f16((const csb_sift_point *)sets[1], ns[1], ctx->tc_pack[1], s->stream);
+      launch_pack_f16((const csb_sift_point *)sets[0], ns[0], ctx->tc_pack[0], ctx->tc_count + 4, s->stream);
+      launch_pack_f16((const csb_sift_point *)sets[1], ns[1], ctx->tc_pack[1], ctx->tc_count + 4, s->stream);
     }
     {
       LaunchScope ls(ctx, s, "match_tc");
@@ -1060,9 +1073,21 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
       launch_match_blocks((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, distance, ctx->tc_list,
                           ctx->tc_count, (int)blk_need, ctx->tc_part, s->stream);
     }
-    CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_tc_count, ctx->tc_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_tc_count, ctx->tc_count, 5 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   }
   CSB_CHECK(ctx, cudaGetLastError());
+  if (use_tc) {
+    CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+    ctx->tc_redo_blocks += ctx->h_tc_count[0];
+    if (ctx->h_tc_count[4]) {
+      // a descriptor set outside the domain in which the fp16 prefilter's error bound holds (not finite in fp16, or
+      // squared norm > 1.002): the short lists prove nothing, so the exact fp32 kernel recomputes every query
+      ctx->tc_domain_fallbacks++;
+      LaunchScope ls(ctx, s, "match");
+      launch_match((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, distance, s->stream);
+      CSB_CHECK(ctx, cudaGetLastError());
+    }
+  }
   if (h_sift1) {   // the five match fields, strided (matching.cu:352-356)
     const csb_sift_point *d = (const csb_sift_point *)d_sift1;
     csb_sift_point *hp = (csb_sift_point *)h_sift1;
@@ -1070,12 +1095,12 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
                                      5 * sizeof(float), n1, cudaMemcpyDeviceToHost, s->stream));
   }
   CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
-  if (use_tc) ctx->tc_redo_blocks += ctx->h_tc_count[0];
   if (ctx->profile) prof_collect(ctx, s);
   return 0;
 }
 
 long long csb_match_redo_blocks(const csb_ctx *ctx) { return ctx ? ctx->tc_redo_blocks : 0; }
+long long csb_match_domain_fallbacks(const csb_ctx *ctx) { return ctx ? ctx->tc_domain_fallbacks : 0; }
 
 int csb_find_homography(csb_ctx *ctx, const void *d_sift, int n, const int *h_rand_pts, int num_loops, float thresh,
                         float *H9, int *num_inliers) {
@@ -1132,6 +1157,44 @@ int csb_find_homography(csb_ctx *ctx, const void *d_sift, int n, const int *h_ra
   return 0;
 }
 
+int csb_improve_homography(csb_ctx *ctx, void *d_sift, int n, float *H9, int num_loops, float min_score, float max_ambiguity,
+                           float thresh, int *num_fit, void *h_sift) {
+  if (!ctx || !H9 || !num_fit || n < 0 || num_loops < 0) return fail(ctx, CSB_E_INVALID, "csb_improve_homography: bad argument");
+  *num_fit = 0;
+  if (n == 0) return 0;
+  if (!d_sift) return fail(ctx, CSB_E_INVALID, "csb_improve_homography: null device data");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  Slot *s = &ctx->slots[0];
+  if (!ctx->ih_dev) {
+    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ih_dev, 512));
+    CSB_CHECK(ctx, cudaHostAlloc((void **)&ctx->ih_host, 512, cudaHostAllocDefault));
+  }
+  // layout (device and pinned mirror): [0,36) H_in, [64,100) H_out, [128,132) numfit, [256,..) job record
+  float *dH_in = (float *)ctx->ih_dev, *dH_out = (float *)(ctx->ih_dev + 64);
+  int *d_nf = (int *)(ctx->ih_dev + 128);
+  memcpy(ctx->ih_host, H9, 9 * sizeof(float));
+  improve_job_fill(ctx->ih_host + 256, d_sift, n, dH_in, dH_out, d_nf);
+  CSB_CHECK(ctx, cudaMemcpyAsync(ctx->ih_dev, ctx->ih_host, 36, cudaMemcpyHostToDevice, s->stream));
+  CSB_CHECK(ctx, cudaMemcpyAsync(ctx->ih_dev + 256, ctx->ih_host + 256, improve_job_bytes(), cudaMemcpyHostToDevice, s->stream));
+  {
+    LaunchScope ls(ctx, s, "improve_homography");
+    launch_improve_homography(ctx->ih_dev + 256, 1, num_loops, min_score, max_ambiguity, thresh * thresh, s->stream);
+  }
+  CSB_CHECK(ctx, cudaGetLastError());
+  CSB_CHECK(ctx, cudaMemcpyAsync(ctx->ih_host + 64, ctx->ih_dev + 64, 68, cudaMemcpyDeviceToHost, s->stream));
+  if (h_sift) {   // match_error is the one field the reference's ImproveHomography writes (homography.cu:339)
+    const csb_sift_point *d = (const csb_sift_point *)d_sift;
+    csb_sift_point *hp = (csb_sift_point *)h_sift;
+    CSB_CHECK(ctx, cudaMemcpy2DAsync(&hp[0].match_error, sizeof(csb_sift_point), &d[0].match_error, sizeof(csb_sift_point),
+                                     sizeof(float), n, cudaMemcpyDeviceToHost, s->stream));
+  }
+  CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
+  memcpy(H9, ctx->ih_host + 64, 9 * sizeof(float));
+  *num_fit = *(int *)(ctx->ih_host + 128);
+  if (ctx->profile) prof_collect(ctx, s);
+  return 0;
+}
+
 unsigned int csb_sample_hash(unsigned int seed, unsigned int pair, unsigned int loop, unsigned int k,
                              unsigned int attempt) {
   return csb_sample_hash_host(seed, pair, loop, k, attempt);
@@ -1141,6 +1204,18 @@ int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, co
                               const int *pair_i, const int *pair_j, const unsigned int *pair_ids, int distance,
                               int num_loops, float min_score, float max_ambiguity, float thresh, unsigned int seed,
                               float *H_out, int *inliers_out, int *nvalid_out) {
+  return csb_allpairs_match_ransac_improve(ctx, n_sets, d_sifts, counts, n_pairs, pair_i, pair_j, pair_ids, distance, num_loops,
+                                           min_score, max_ambiguity, thresh, seed, 0, 0.0f, H_out, inliers_out, nvalid_out,
+                                           nullptr, nullptr);
+}
+
+int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_sifts, const int *counts, int n_pairs,
+                                      const int *pair_i, const int *pair_j, const unsigned int *pair_ids, int distance,
+                                      int num_loops, float min_score, float max_ambiguity, float thresh, unsigned int seed,
+                                      int improve_loops, float improve_thresh, float *H_out, int *inliers_out,
+                                      int *nvalid_out, float *H_improved_out, int *numfit_out) {
+  const bool improve = improve_loops > 0;
+  if (improve && (!H_improved_out || !numfit_out)) return fail(ctx, CSB_E_INVALID, "csb_allpairs: improve outputs missing");
   if (!ctx || n_sets <= 0 || !d_sifts || !counts || n_pairs < 0 || !pair_i || !pair_j || !H_out || !inliers_out ||
       !nvalid_out || num_loops <= 0 || (num_loops % 16) != 0 || (distance != 0 && distance != 1))
     return fail(ctx, CSB_E_INVALID, "csb_allpairs_match_ransac: bad argument");
@@ -1207,7 +1282,7 @@ int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, co
       c.st = ctx->ap_stream[t];
     }
   }
-  const size_t res_need = (size_t)n_pairs * 11 * 4;
+  const size_t res_need = (size_t)n_pairs * 21 * 4;   // H[9], inliers, n_valid, H_improved[9], numfit
   if (ctx->ap_result_cap < res_need) {
     if (ctx->ap_result) cudaFree(ctx->ap_result);
     ctx->ap_result = nullptr; ctx->ap_result_cap = 0;
@@ -1216,8 +1291,38 @@ int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, co
   }
   float *d_H = (float *)ctx->ap_result;
   int *d_inl = (int *)(ctx->ap_result + (size_t)n_pairs * 36), *d_nv = d_inl + n_pairs;
+  float *d_Himp = (float *)(d_nv + n_pairs);
+  int *d_nfit = (int *)(d_Himp + 9 * (size_t)n_pairs);
+  const size_t job_b = improve_job_bytes();
+  if (improve) {
+    if (ctx->ap_jobs_cap < job_b * n_pairs) {
+      if (ctx->ap_jobs) cudaFree(ctx->ap_jobs);
+      ctx->ap_jobs = nullptr; ctx->ap_jobs_cap = 0;
+      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ap_jobs, job_b * n_pairs));
+      ctx->ap_jobs_cap = job_b * n_pairs;
+    }
+    std::vector<char> jobs(job_b * n_pairs);
+    for (int k = 0; k < n_pairs; k++)
+      improve_job_fill(jobs.data() + job_b * k, d_sifts[pair_i[k]], counts[pair_i[k]], d_H + 9 * (size_t)k, d_Himp + 9 * (size_t)k,
+                       d_nfit + k);
+    CSB_CHECK(ctx, cudaMemcpyAsync(ctx->ap_jobs, jobs.data(), jobs.size(), cudaMemcpyHostToDevice, st));
+    CSB_CHECK(ctx, cudaStreamSynchronize(st));      // `jobs` is pageable and goes out of scope
+  }
   std::vector<void *> packed(n_sets, nullptr);
+  if (ctx->ap_flags_cap < (size_t)n_sets) {
+    if (ctx->ih_dev) cudaFree(ctx->ih_dev);
+  if (ctx->ih_host) cudaFreeHost(ctx->ih_host);
+  if (ctx->ap_jobs) cudaFree(ctx->ap_jobs);
+  if (ctx->ap_flags) cudaFree(ctx->ap_flags);
+    if (ctx->h_ap_flags) cudaFreeHost(ctx->h_ap_flags);
+    ctx->ap_flags = nullptr; ctx->h_ap_flags = nullptr; ctx->ap_flags_cap = 0;
+    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ap_flags, sizeof(int) * (size_t)n_sets));
+    CSB_CHECK(ctx, cudaHostAlloc((void **)&ctx->h_ap_flags, sizeof(int) * (size_t)n_sets, cudaHostAllocDefault));
+    ctx->ap_flags_cap = n_sets;
+  }
+  for (int i = 0; i < n_sets; i++) ctx->h_ap_flags[i] = 0;
   if (use_tc) {
+    CSB_CHECK(ctx, cudaMemsetAsync(ctx->ap_flags, 0, sizeof(int) * (size_t)n_sets, st));
     size_t need = 0;
     for (int i = 0; i < n_sets; i++) if (counts[i] >= 256) need += (tc_packed_bytes(counts[i]) + 1023) & ~(size_t)1023;
     if (ctx->ap_pack_cap < need) {
@@ -1231,9 +1336,12 @@ int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, co
       if (counts[i] < 256) continue;
       packed[i] = ctx->ap_pack + off;
       off += (tc_packed_bytes(counts[i]) + 1023) & ~(size_t)1023;
-      launch_pack_f16((const csb_sift_point *)d_sifts[i], counts[i], packed[i], st);
+      launch_pack_f16((const csb_sift_point *)d_sifts[i], counts[i], packed[i], ctx->ap_flags + i, st);
       ctx->launches++;
     }
+    // which sets satisfy the fp16 prefilter's precondition?  (one small read-back per batch of pairs)
+    CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_ap_flags, ctx->ap_flags, sizeof(int) * (size_t)n_sets, cudaMemcpyDeviceToHost, st));
+    CSB_CHECK(ctx, cudaStreamSynchronize(st));
   }
   CSB_CHECK(ctx, cudaEventRecord(ctx->ap_packed, st));
   for (int t = 0; t < n_streams; t++) CSB_CHECK(ctx, cudaStreamWaitEvent(sc[t].st, ctx->ap_packed, 0));
@@ -1245,7 +1353,9 @@ int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, co
     csb_sift_point *s1 = (csb_sift_point *)d_sifts[i];
     const csb_sift_point *s2 = (const csb_sift_point *)d_sifts[j];
     if (n1 > 0 && n2 > 0) {
-      if (use_tc && n1 >= 256 && n2 >= 256) {
+      const bool in_domain = !ctx->h_ap_flags[i] && !ctx->h_ap_flags[j];
+      if (use_tc && n1 >= 256 && n2 >= 256 && !in_domain) ctx->tc_domain_fallbacks++;
+      if (use_tc && n1 >= 256 && n2 >= 256 && in_domain) {
         const int splits = tc_splits(n1, n2, ctx->sm_count);
         launch_match_tc(packed[i], n1, packed[j], n2, splits, c.sl_val, c.sl_idx, c.st);
         launch_rescore(s1, n1, s2, n2, c.sl_val, c.sl_idx, splits, distance, c.flags, c.list, c.cnt, c.st);
@@ -1261,6 +1371,11 @@ int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, co
                        c.d_homo, c.d_counts, num_loops, thresh * thresh, seed, pair_ids ? pair_ids[k] : (unsigned int)k,
                        d_H + 9 * (size_t)k, d_inl + k, d_nv + k, c.st);
     ctx->launches += 6;
+    if (improve && n1 > 0) {   // main.cpp:335: ImproveHomography right after FindHomography
+      launch_improve_homography(ctx->ap_jobs + job_b * k, 1, improve_loops, min_score, max_ambiguity,
+                                improve_thresh * improve_thresh, c.st);
+      ctx->launches += 1;
+    }
   }
   CSB_CHECK(ctx, cudaGetLastError());
   for (int t = 0; t < n_streams; t++) {
@@ -1270,6 +1385,10 @@ int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, co
   CSB_CHECK(ctx, cudaMemcpyAsync(H_out, d_H, sizeof(float) * 9 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
   CSB_CHECK(ctx, cudaMemcpyAsync(inliers_out, d_inl, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
   CSB_CHECK(ctx, cudaMemcpyAsync(nvalid_out, d_nv, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  if (improve) {
+    CSB_CHECK(ctx, cudaMemcpyAsync(H_improved_out, d_Himp, sizeof(float) * 9 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    CSB_CHECK(ctx, cudaMemcpyAsync(numfit_out, d_nfit, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  }
   const double t_issue = now_ms();
   CSB_CHECK(ctx, cudaStreamSynchronize(st));
   if (trace)

@@ -135,7 +135,8 @@ void launch_match_blocks(csb_sift_point *d_sift1, int n1, const csb_sift_point *
 size_t tc_packed_bytes(int n);
 int tc_pad(int n);
 int tc_splits(int n1, int n2, int sm_count);
-void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, cudaStream_t st);
+// *out_of_domain (device int, zeroed by the caller) is set when the set violates the fp16 error bound's precondition
+void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *out_of_domain, cudaStream_t st);
 void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
                      cudaStream_t st);
 void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,
@@ -147,6 +148,11 @@ void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min
                         int *d_nvalid, float *d_coord, int *d_rand, float *d_homo, int *d_counts, int num_loops,
                         float thresh2, unsigned int seed, unsigned int pair, float *H_out, int *inl_out, int *nvalid_out,
                         cudaStream_t st);
+// device ImproveHomography: one CTA per job (kernels_homography.cu); jobs = array of improve_job_bytes() records
+void launch_improve_homography(const void *d_jobs, int n_jobs, int num_loops, float min_score, float max_amb, float limit,
+                               cudaStream_t st);
+size_t improve_job_bytes();
+void improve_job_fill(void *h_job, void *d_pts, int n, const float *d_H_in, float *d_H_out, int *d_numfit);
 // rigid-transform RANSAC (kernels_rigid.cu)
 void launch_rigid_hypotheses(const float *d_coord, int num_pts, int *d_indices, int draw, unsigned int seed, int type3d,
                              int num_loops, float thresh2, float *d_Rt, int *d_counts, cudaStream_t st);

@@ -369,10 +369,11 @@ int make_dog_tensor_map(CUtensorMap *out, const float *dog, int h, int pitch) {
 void launch_find_points(const ExtremaParams &ep, const ExtremaMaps &maps, int n_ctas, KpStage *d_stage,
                         unsigned int *d_counter, int max_pts, cudaStream_t st) {
   if (n_ctas <= 0) return;
-  static int cap = 0;                                  // CSB_XT_CAP: shrink the per-CTA list (tests of the dense fallback)
-  if (!cap) {
-    const char *e = getenv("CSB_XT_CAP");
-    cap = e ? atoi(e) : XT_CAP;
+  // CSB_XT_CAP shrinks the per-CTA list (tests of the dense fallback); read on every launch so that a test can set it
+  // for one context without needing a fresh process
+  int cap = XT_CAP;
+  if (const char *e = getenv("CSB_XT_CAP")) {
+    cap = atoi(e);
     if (cap < 1 || cap > XT_CAP) cap = XT_CAP;
   }
   k_find_points<<<n_ctas, (XT_WARPS + 1) * 32, 0, st>>>(ep, maps, d_stage, d_counter, max_pts, cap);

@@ -6,8 +6,8 @@
 // launches on one stream and no intermediate host synchronisation.
 //   k_gather_coords : AoS SiftPoint -> SoA x1,y1,x2,y2 (pad slots zeroed; the
 //                     reference leaves them uninitialised, homography.cu:215)
-//   k_hypotheses    : one thread per 4-point sample, 8x8 DLT system solved by
-//                     the same Crout LU / implicit pivoting as the reference
+//   k_hypotheses    : eight lanes per 4-point sample, the 8x8 DLT system in registers,
+//                     Crout LU / implicit pivoting in the reference's operation order
 //   k_score         : one warp per hypothesis, inlier test with the reference's
 //                     round-toward-zero products (__fmul_rz), shuffle sum
 #include "csb_internal.h"
@@ -32,104 +32,277 @@ __global__ void k_gather_coords(const csb_sift_point *__restrict__ d_sift, int n
   coord[i + 3 * n_up] = y2;
 }
 
-// Numerical-Recipes style LU inverse, restated from homography.cu:12-96.
-__device__ void invert8(float elem[8][8], float res[8][8]) {
-  const int size = 8;
-  int indx[8];
-  float b[8], vv[8];
-  for (int i = 0; i < size; i++) indx[i] = 0;
-  int imax = 0;
-  for (int i = 0; i < size; i++) {
+// ComputeHomographies + InvertMatrix<8> (homography.cu:98-139, 12-96) as a warp-cooperative kernel:
+// EIGHT LANES PER HYPOTHESIS, lane r owning row r of the 8x8 DLT system in eight registers (the reference
+// gives every hypothesis one thread and two 8x8 matrices in local memory).  All loops are unrolled, every
+// register index is static, rows travel by shuffles: no local memory at all.
+//   * Crout LU, column by column: the finished upper entry of row k is broadcast and rows below it subtract
+//     their multiple - the same fused multiply-adds, in the same order (k ascending), as the reference's
+//     inner loops, so the factors are bit-identical;
+//   * implicit-scaling pivot search = 3-step shuffle arg-max over the group with the reference's tie rule
+//     (">=" while scanning upwards: the LAST maximal row wins; no candidate at all, e.g. NaNs, keeps the
+//     previous column's pivot row); the row swap is one shuffle per register;
+//   * the inverse is never formed row by row: lane j solves L U x = P e_j for ITS column of the inverse (the
+//     reference's "skip leading zeros" rule included), reading the factors by broadcast;
+//   * h = A^-1 b accumulates in the reference's order (i ascending).
+// Numerics that are part of the contract: reciprocals through double ((float)(1.0 / (double)x)), IEEE division
+// in the back substitution, a zero pivot replaced by 1e-16.
+__device__ __forceinline__ float recip_via_double(float x) { return (float)(1.0 / (double)x); }
+
+__global__ void __launch_bounds__(128) k_hypotheses(const float *__restrict__ coord, const int *__restrict__ randPts,
+                                                    float *__restrict__ homo, int numPts, int numLoops) {
+  constexpr unsigned FULLM = 0xffffffffu;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = gtid >> 3;                        // hypothesis
+  const int r = threadIdx.x & 7;                    // row owned by this lane
+  const bool live = idx < numLoops;                 // whole 8-lane groups are live or not; dead groups compute on zeros
+  float e[8];                                       // row r of the system / of its LU factors
+  float rhs = 0.0f;
+  {
+    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+    if (live) {
+      const int pt = randPts[(r >> 1) * numLoops + idx];
+      x1 = coord[pt + 0 * numPts]; y1 = coord[pt + 1 * numPts];
+      x2 = coord[pt + 2 * numPts]; y2 = coord[pt + 3 * numPts];
+    }
+    const bool even = (r & 1) == 0;                 // homography.cu:107-129
+    const float t = even ? x2 : y2;
+    e[0] = even ? x1 : 0.0f; e[1] = even ? y1 : 0.0f; e[2] = even ? 1.0f : 0.0f;
+    e[3] = even ? 0.0f : x1; e[4] = even ? 0.0f : y1; e[5] = even ? 0.0f : 1.0f;
+    e[6] = __fmul_rn(-t, x1);
+    e[7] = __fmul_rn(-t, y1);
+    rhs = t;
+  }
+  // implicit scaling: vv = 1 / max |row|
+  float vv;
+  {
     float big = 0.0f;
-    for (int j = 0; j < size; j++) {
-      const float temp = fabsf(elem[i][j]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float temp = fabsf(e[j]);
       if (temp > big) big = temp;
     }
-    if (big > 0.0f) vv[i] = (float)(1.0 / (double)big);
-    else vv[i] = 1e16f;
+    vv = big > 0.0f ? recip_via_double(big) : 1e16f;
   }
-  for (int j = 0; j < size; j++) {
-    for (int i = 0; i < j; i++) {
-      float sum = elem[i][j];
-      for (int k = 0; k < i; k++) sum -= elem[i][k] * elem[k][j];
-      elem[i][j] = sum;
+  int indx[8];
+  int imax = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    // column j: rows below the finished entry of row k subtract (their entry in column k) * (that entry)
+#pragma unroll
+    for (int k = 0; k < j; k++) {
+      const float u = __shfl_sync(FULLM, e[j], k, 8);
+      if (r > k) e[j] = __fmaf_rn(-e[k], u, e[j]);
     }
-    float big = 0.0f;
-    for (int i = j; i < size; i++) {
-      float sum = elem[i][j];
-      for (int k = 0; k < j; k++) sum -= elem[i][k] * elem[k][j];
-      elem[i][j] = sum;
-      const float dum = vv[i] * fabsf(sum);
-      if (dum >= big) {
-        big = dum;
-        imax = i;
+    // pivot: last row i >= j with the largest vv[i] * |a[i][j]|
+    {
+      float d = vv * fabsf(e[j]);
+      int di = r;
+      if (!(r >= j && d >= 0.0f)) { d = -1.0f; di = -1; }     // not a candidate (row above the diagonal, or NaN)
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(FULLM, d, o, 8);
+        const int oi = __shfl_xor_sync(FULLM, di, o, 8);
+        if (od > d || (od == d && oi > di)) { d = od; di = oi; }
       }
+      if (di >= 0) imax = di;
     }
-    if (j != imax) {
-      for (int k = 0; k < size; k++) {
-        const float dum = elem[imax][k];
-        elem[imax][k] = elem[j][k];
-        elem[j][k] = dum;
-      }
-      vv[imax] = vv[j];
+    {
+      // row swap j <-> imax.  imax differs between the four hypotheses of a warp, so the shuffles are executed
+      // unconditionally (a group that needs no swap reads its own rows back)
+      const int src = (r == j) ? imax : ((r == imax) ? j : r);
+#pragma unroll
+      for (int c = 0; c < 8; c++) e[c] = __shfl_sync(FULLM, e[c], src, 8);
+      const float vj = __shfl_sync(FULLM, vv, j, 8);
+      if (r == imax) vv = vj;                        // vv[imax] = vv[j] (vv[j] itself is not needed again)
     }
     indx[j] = imax;
-    if (elem[j][j] == 0.0f) elem[j][j] = 1e-16f;
-    if (j != (size - 1)) {
-      const float dum = (float)(1.0 / (double)elem[j][j]);
-      for (int i = j + 1; i < size; i++) elem[i][j] *= dum;
+    if (r == j && e[j] == 0.0f) e[j] = 1e-16f;
+    if (j != 7) {
+      const float piv = __shfl_sync(FULLM, e[j], j, 8);
+      const float dum = recip_via_double(piv);
+      if (r > j) e[j] = __fmul_rn(e[j], dum);
     }
   }
-  for (int j = 0; j < size; j++) {
-    for (int k = 0; k < size; k++) b[k] = 0.0f;
-    b[j] = 1.0f;
-    int ii = -1;
-    for (int i = 0; i < size; i++) {
-      const int ip = indx[i];
-      float sum = b[ip];
-      b[ip] = b[i];
-      if (ii != -1) {
-        for (int jj = ii; jj < i; jj++) sum -= elem[i][jj] * b[jj];
-      } else if (sum != 0.0f) {
-        ii = i;
-      }
-      b[i] = sum;
+  // lane r solves for column r of the inverse: b = e_r, permuted by the recorded row swaps
+  int pos = r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int ip = indx[i];
+    if (pos == i) pos = ip;
+    else if (pos == ip) pos = i;
+  }
+  float y[8];
+  int ii = -1;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {                      // forward substitution (unit lower factor)
+    float sum = (pos == i) ? 1.0f : 0.0f;
+#pragma unroll
+    for (int jj = 0; jj < i; jj++) {
+      const float l = __shfl_sync(FULLM, e[jj], i, 8);            // a[i][jj]
+      if (ii != -1 && jj >= ii) sum = __fmaf_rn(-l, y[jj], sum);
     }
-    for (int i = size - 1; i >= 0; i--) {
-      float sum = b[i];
-      for (int jj = i + 1; jj < size; jj++) sum -= elem[i][jj] * b[jj];
-      b[i] = sum / elem[i][i];
+    if (ii == -1 && sum != 0.0f) ii = i;
+    y[i] = sum;
+  }
+#pragma unroll
+  for (int i = 7; i >= 0; i--) {                     // back substitution
+    float sum = y[i];
+#pragma unroll
+    for (int jj = i + 1; jj < 8; jj++) {
+      const float u = __shfl_sync(FULLM, e[jj], i, 8);            // a[i][jj]
+      sum = __fmaf_rn(-u, y[jj], sum);
     }
-    for (int i = 0; i < size; i++) res[i][j] = b[i];
+    const float diag = __shfl_sync(FULLM, e[i], i, 8);
+    y[i] = __fdiv_rn(sum, diag);
+  }
+  // y[i] = inverse[i][r].  h[j] = sum_i inverse[j][i] * b[i], i ascending (homography.cu:133-138)
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float ia = __shfl_sync(FULLM, y[j], i, 8);
+      const float bi = __shfl_sync(FULLM, rhs, i, 8);
+      sum = __fmaf_rn(ia, bi, sum);
+    }
+    if (live && r == j) homo[j * numLoops + idx] = sum;
   }
 }
 
-__global__ void __launch_bounds__(64) k_hypotheses(const float *__restrict__ coord, const int *__restrict__ randPts,
-                                                   float *__restrict__ homo, int numPts, int numLoops) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= numLoops) return;
-  float a[8][8], ia[8][8], b[8];
-  for (int i = 0; i < 4; i++) {
-    const int pt = randPts[i * numLoops + idx];
-    const float x1 = coord[pt + 0 * numPts], y1 = coord[pt + 1 * numPts];
-    const float x2 = coord[pt + 2 * numPts], y2 = coord[pt + 3 * numPts];
-    float *row1 = a[2 * i + 0];
-    row1[0] = x1; row1[1] = y1; row1[2] = 1.0f;
-    row1[3] = row1[4] = row1[5] = 0.0f;
-    row1[6] = -x2 * x1; row1[7] = -x2 * y1;
-    float *row2 = a[2 * i + 1];
-    row2[0] = row2[1] = row2[2] = 0.0f;
-    row2[3] = x1; row2[4] = y1; row2[5] = 1.0f;
-    row2[6] = -y2 * x1; row2[7] = -y2 * y1;
-    b[2 * i + 0] = x2;
-    b[2 * i + 1] = y2;
+// ImproveHomography (homography.cu:280-346) on the device, one CTA per homography: iteratively re-weighted
+// least squares, weights limit / (err + limit), the 8x8 normal equations accumulated in fp64 and solved by
+// Cholesky, then the inlier count and match_error of every point.  Per-point arithmetic follows the reference
+// (projection in double rounded to float, float error and weight); the fp64 sums are formed in a different
+// order (per-thread partial sums, then a tree), so H agrees with the host version to ~1e-12 relative, not bit
+// for bit.  The reference runs this on the host with OpenCV (cv::solve, DECOMP_CHOLESKY).
+struct ImproveJob {
+  csb_sift_point *pts;
+  int n;
+  const float *H_in;        // 9 floats (device)
+  float *H_out;             // 9 floats (device)
+  int *numfit_out;
+};
+#define IH_NT 256
+#define IH_NACC 44          // 36 upper-triangle entries of M + 8 of X
+__device__ __forceinline__ int ih_tri(int r, int c) { return r * 8 - r * (r - 1) / 2 + (c - r); }   // r <= c
+
+__global__ void __launch_bounds__(IH_NT) k_improve_homography(const ImproveJob *__restrict__ jobs, int num_loops,
+                                                              float min_score, float max_amb, float limit) {
+  __shared__ double s_part[IH_NT / 32][IH_NACC];
+  __shared__ double s_A[8];
+  __shared__ int s_cnt[IH_NT / 32];
+  const ImproveJob J = jobs[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 8) s_A[threadIdx.x] = (double)(J.H_in[threadIdx.x] / J.H_in[8]);   // float division, as the reference
+  __syncthreads();
+  for (int loop = 0; loop < num_loops; loop++) {
+    double A[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) A[i] = s_A[i];
+    double acc[IH_NACC];
+#pragma unroll
+    for (int i = 0; i < IH_NACC; i++) acc[i] = 0.0;
+    for (int i = threadIdx.x; i < J.n; i += IH_NT) {
+      const csb_sift_point &pt = J.pts[i];
+      if (pt.score < min_score || pt.ambiguity > max_amb) continue;
+      const float x = pt.coords2D[0], y = pt.coords2D[1], mx = pt.match_xpos, my = pt.match_ypos;
+      const float den = (float)(A[6] * x + A[7] * y + 1.0f);
+      const float dx = (float)((A[0] * x + A[1] * y + A[2]) / den - mx);
+      const float dy = (float)((A[3] * x + A[4] * y + A[5]) / den - my);
+      const float err = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      const double wei = (double)__fdiv_rn(limit, __fadd_rn(err, limit));
+      // two rows of the design matrix: Yx = [x y 1 0 0 0 -x*mx -y*mx], Yy = [0 0 0 x y 1 -x*my -y*my]
+      const double Yx[8] = {x, y, 1.0, 0.0, 0.0, 0.0, (double)__fmul_rn(-x, mx), (double)__fmul_rn(-y, mx)};
+      const double Yy[8] = {0.0, 0.0, 0.0, x, y, 1.0, (double)__fmul_rn(-x, my), (double)__fmul_rn(-y, my)};
+      const double ax = (double)mx * wei, ay = (double)my * wei;
+      // M += (Y Y^T) wei for both rows, upper triangle only; products with a structural zero are skipped (they add 0)
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+#pragma unroll
+        for (int c = r; c < 8; c++) {
+          const bool in_x = (r < 3 || r >= 6) && (c < 3 || c >= 6), in_y = r >= 3 && c >= 3;   // compile-time after unrolling
+          if (in_x) acc[ih_tri(r, c)] += (Yx[c] * Yx[r]) * wei;
+          if (in_y) acc[ih_tri(r, c)] += (Yy[c] * Yy[r]) * wei;
+        }
+        if (r < 3 || r >= 6) acc[36 + r] += Yx[r] * ax;
+        if (r >= 3) acc[36 + r] += Yy[r] * ay;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < IH_NACC; i++) {
+      double v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_part[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double M[8][8], X[8], L[8][8];
+      for (int r = 0; r < 8; r++) {
+        for (int c = r; c < 8; c++) {
+          double v = 0.0;
+          for (int w = 0; w < IH_NT / 32; w++) v += s_part[w][ih_tri(r, c)];
+          M[r][c] = M[c][r] = v;
+        }
+        double v = 0.0;
+        for (int w = 0; w < IH_NT / 32; w++) v += s_part[w][36 + r];
+        X[r] = v;
+      }
+      bool spd = true;
+      for (int i = 0; i < 8 && spd; i++)
+        for (int j = 0; j <= i; j++) {
+          double sacc = M[i][j];
+          for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
+          if (i == j) {
+            if (!(sacc > 0.0)) { spd = false; break; }
+            L[i][i] = sqrt(sacc);
+          } else {
+            L[i][j] = sacc / L[j][j];
+          }
+        }
+      if (spd) {
+        double yv[8], Av[8];
+        for (int i = 0; i < 8; i++) {
+          double sacc = X[i];
+          for (int k = 0; k < i; k++) sacc -= L[i][k] * yv[k];
+          yv[i] = sacc / L[i][i];
+        }
+        for (int i = 7; i >= 0; i--) {
+          double sacc = yv[i];
+          for (int k = i + 1; k < 8; k++) sacc -= L[k][i] * Av[k];
+          Av[i] = sacc / L[i][i];
+        }
+        for (int i = 0; i < 8; i++) s_A[i] = Av[i];
+      }
+    }
+    __syncthreads();
   }
-  invert8(a, ia);
-  for (int j = 0; j < 8; j++) {
-    float sum = 0.0f;
-    for (int i = 0; i < 8; i++) sum += ia[j][i] * b[i];
-    homo[j * numLoops + idx] = sum;
+  double A[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) A[i] = s_A[i];
+  int numfit = 0;
+  for (int i = threadIdx.x; i < J.n; i += IH_NT) {
+    csb_sift_point &pt = J.pts[i];
+    const float x = pt.coords2D[0], y = pt.coords2D[1];
+    const float den = (float)(A[6] * x + A[7] * y + 1.0);
+    const float dx = (float)((A[0] * x + A[1] * y + A[2]) / den - pt.match_xpos);
+    const float dy = (float)((A[3] * x + A[4] * y + A[5]) / den - pt.match_ypos);
+    const float err = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (err < limit) numfit++;
+    pt.match_error = (float)sqrt((double)err);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) numfit += __shfl_xor_sync(0xffffffffu, numfit, o);
+  if (lane == 0) s_cnt[warp] = numfit;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < IH_NT / 32; w++) tot += s_cnt[w];
+    *J.numfit_out = tot;
+  }
+  if (threadIdx.x < 8) J.H_out[threadIdx.x] = (float)A[threadIdx.x];
+  if (threadIdx.x == 8) J.H_out[8] = 1.0f;
 }
 
 // TestHomographies (homography.cu:139-192): inliers of every hypothesis over ALL numPts points.
@@ -298,7 +471,7 @@ void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min
   k_valid_compact<<<1, 1024, 0, st>>>(d_sift, n, min_score, max_amb, d_valid, d_nvalid);
   k_make_samples<<<(num_loops + 127) / 128, 128, 0, st>>>(d_valid, d_nvalid, num_loops, seed, pair, d_rand);
   k_gather_coords<<<((n_up > num_loops ? n_up : num_loops) + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord, d_counts, num_loops);
-  k_hypotheses<<<(num_loops + 63) / 64, 64, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
+  k_hypotheses<<<(num_loops * 8 + 127) / 128, 128, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
   k_score<<<dim3((num_loops + SCORE_HYP - 1) / SCORE_HYP, (n_up + SCORE_PTS - 1) / SCORE_PTS), SCORE_HYP, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
   k_pick_best<<<1, 256, 0, st>>>(d_counts, d_homo, num_loops, d_nvalid, n, H_out, inl_out, nvalid_out);
 }
@@ -306,6 +479,22 @@ void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min
 void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
                        int *d_counts, int num_loops, float thresh2, cudaStream_t st) {
   k_gather_coords<<<((n_up > num_loops ? n_up : num_loops) + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord, d_counts, num_loops);
-  k_hypotheses<<<(num_loops + 63) / 64, 64, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
+  k_hypotheses<<<(num_loops * 8 + 127) / 128, 128, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
   k_score<<<dim3((num_loops + SCORE_HYP - 1) / SCORE_HYP, (n_up + SCORE_PTS - 1) / SCORE_PTS), SCORE_HYP, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
+}
+
+void launch_improve_homography(const void *d_jobs, int n_jobs, int num_loops, float min_score, float max_amb, float limit,
+                               cudaStream_t st) {
+  if (n_jobs <= 0) return;
+  k_improve_homography<<<n_jobs, IH_NT, 0, st>>>(reinterpret_cast<const ImproveJob *>(d_jobs), num_loops, min_score, max_amb,
+                                                 limit);
+}
+size_t improve_job_bytes() { return sizeof(ImproveJob); }
+void improve_job_fill(void *h_job, void *d_pts, int n, const float *d_H_in, float *d_H_out, int *d_numfit) {
+  ImproveJob *j = reinterpret_cast<ImproveJob *>(h_job);
+  j->pts = reinterpret_cast<csb_sift_point *>(d_pts);
+  j->n = n;
+  j->H_in = d_H_in;
+  j->H_out = d_H_out;
+  j->numfit_out = d_numfit;
 }

@@ -36,8 +36,13 @@
 //                    split: massive near-ties) is flagged and redone by the exact fp32 kernel
 //                    (kernels_match.cu).
 //
-// fp16 inputs: descriptors are non-negative, <= 1, unit norm; rounding each element to
-// fp16 perturbs a dot product by < 128 * 2 * 2^-12 * (elementwise products) <= 6.1e-4 * dot.
+// fp16 inputs and the bound TC_EPS: rounding an element to fp16 changes it by a relative 2^-11 at most, so a
+// product of two rounded elements is off by at most (2^-10 + 2^-22) |q_k c_k| and the whole dot product by at most
+// 2^-10 * sum |q_k c_k| <= 2^-10 |q| |c| (Cauchy-Schwarz, any signs) = 9.77e-4 for unit vectors; fp16 subnormals
+// (|v| < 6.1e-5, absolute error 2^-25 each) and the fp32 accumulation add < 2e-6.  TC_EPS = 1e-3 covers that for
+// |q|^2, |c|^2 <= 1.002.  k_pack_f16 CHECKS the precondition (every element finite in fp16, squared norm <= 1.002)
+// and raises a flag otherwise; csb_match / the all-pairs path then route the call to the exact fp32 kernel, so
+// arbitrary SiftPoint.data (un-normalised, 0..255, huge) still gets the reference's exact result.
 #include <cuda_fp16.h>
 
 #include "csb_internal.h"
@@ -56,7 +61,8 @@ constexpr uint32_t SMEM_B_STAGE = 2 * B_HALF_BYTES;                             
 constexpr uint32_t SMEM_TC = SMEM_A + TC_STAGES * SMEM_B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 32 * (2 + 8);
 constexpr int RS_ROWS = 16;        // staged candidate rows per rescoring round (per warp)
-constexpr float TC_EPS = 6.5e-4f;   // bound on |fp16-input dot - exact dot| for unit descriptors
+constexpr float TC_EPS = 1.0e-3f;   // bound on |fp16-input dot - exact dot| for descriptors in the checked domain
+constexpr float TC_MAX_NORM2 = 1.002f;
 
 // ---- PTX wrappers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -139,21 +145,34 @@ constexpr uint32_t IDESC_F16_M128_N256 = (1u << 4)                 // D format =
 // ---- 1. pack ----------------------------------------------------------------------
 // Packed layout (per set): two K-halves; half kb is a [n_pad][64] fp16 matrix (128-byte rows) in
 // which the 16-byte chunk c of row r is stored at chunk position c ^ (r & 7) (128B swizzle).
+// Also validates the domain in which TC_EPS bounds the fp16 error (see the header): *out_of_domain is set when a
+// row has a non-finite / fp16-overflowing element or a squared norm above TC_MAX_NORM2.
 __global__ void __launch_bounds__(256) k_pack_f16(const csb_sift_point *__restrict__ pts, int n, int n_pad,
-                                                  __half *__restrict__ packed) {
+                                                  __half *__restrict__ packed, int *__restrict__ out_of_domain) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 16-byte chunk): 16 chunks/row
   const int r = gid >> 4, c16 = gid & 15;
-  if (r >= n_pad) return;
+  const bool live = r < n_pad;                             // n_pad * 16 is a multiple of 32: whole warps are live or not
   const int kb = c16 >> 3, c = c16 & 7;
   __align__(16) __half v[8];
-  if (r < n) {
+  float ss = 0.0f;
+  bool bad = false;
+  if (live && r < n) {
     const float *d = pts[r].data + 8 * c16;
 #pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = __float2half_rn(d[i]);
+    for (int i = 0; i < 8; i++) {
+      const float f = d[i];
+      v[i] = __float2half_rn(f);
+      ss = __fmaf_rn(f, f, ss);
+      bad = bad || !(fabsf(f) <= 65504.0f);               // NaN, inf, or beyond the fp16 range
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = __float2half_rn(0.0f);
   }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o, 16);   // the row's 16 threads are adjacent lanes
+  if (bad || !(ss <= TC_MAX_NORM2)) *out_of_domain = 1;
+  if (!live) return;
   char *dst = reinterpret_cast<char *>(packed) + (size_t)kb * n_pad * KHALF_BYTES_PER_ROW +
               (size_t)r * KHALF_BYTES_PER_ROW + ((c ^ (r & 7)) << 4);
   *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(v);
@@ -510,10 +529,10 @@ int tc_splits(int n1, int n2, int sm_count) {
   return s;
 }
 
-void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, cudaStream_t st) {
+void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *out_of_domain, cudaStream_t st) {
   const int n_pad = tc_pad(n);
   const int threads = n_pad * 16;
-  k_pack_f16<<<(threads + 255) / 256, 256, 0, st>>>(pts, n, n_pad, reinterpret_cast<__half *>(packed));
+  k_pack_f16<<<(threads + 255) / 256, 256, 0, st>>>(pts, n, n_pad, reinterpret_cast<__half *>(packed), out_of_domain);
 }
 
 void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,

@@ -165,6 +165,11 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
  * to force the fp32 CUDA-core kernel): number of 16-query blocks whose short list could not be
  * proven complete and were redone exactly, accumulated since the context was created. */
 long long csb_match_redo_blocks(const csb_ctx *ctx);
+/* The tensor-core path prefilters with fp16 dot products whose error bound (1e-3) holds for descriptors that are
+ * finite in fp16 with squared norm <= 1.002 (SIFT / RootSIFT descriptors are unit vectors).  The packing kernel
+ * checks this; calls whose sets fall outside are computed by the exact fp32 kernel instead, so csb_match equals the
+ * reference for ANY SiftPoint.data.  Number of calls / pairs that took that route since the context was created: */
+long long csb_match_domain_fallbacks(const csb_ctx *ctx);
 
 /* ---- homography -------------------------------------------------------------
  * FindHomography (extras/homography.h:8, homography.cu:191-278).  Valid points
@@ -193,6 +198,23 @@ int csb_allpairs_match_ransac(csb_ctx *ctx, int n_sets, void *const *d_sifts, co
                               float *H_out, int *inliers_out, int *nvalid_out);
 unsigned int csb_sample_hash(unsigned int seed, unsigned int pair, unsigned int loop, unsigned int k,
                              unsigned int attempt);
+/* The same with ImproveHomography(set_i, H, improve_loops, min_score, max_ambiguity, improve_thresh) appended to every
+ * pair (main.cpp:334-335), on the device: H_improved_out gets the refined homography, numfit_out its inlier count. */
+int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_sifts, const int *counts, int n_pairs,
+                                      const int *pair_i, const int *pair_j, const unsigned int *pair_ids, int distance,
+                                      int num_loops, float min_score, float max_ambiguity, float thresh, unsigned int seed,
+                                      int improve_loops, float improve_thresh, float *H_out, int *inliers_out,
+                                      int *nvalid_out, float *H_improved_out, int *numfit_out);
+
+/* ImproveHomography (extras/homography.cu:271-337; declared in main.cpp:19) on the DEVICE copy of the points:
+ * `num_loops` rounds of re-weighted least squares (weights thresh^2 / (err + thresh^2), points with
+ * score < min_score || ambiguity > max_ambiguity skipped, 8x8 normal equations in fp64, Cholesky), then the number of
+ * points with err < thresh^2 (over ALL points, like the reference) and match_error = sqrt(err) of every point, written
+ * to d_sift and, when h_sift is given, to the host records.  H9 is read (divided by H9[8]) and overwritten.
+ * The reference does this on the host with OpenCV's cv::solve; the C++ shim keeps a host version for callers that
+ * only have host data. */
+int csb_improve_homography(csb_ctx *ctx, void *d_sift, int n, float *H9, int num_loops, float min_score, float max_ambiguity,
+                           float thresh, int *num_fit, void *h_sift);
 
 /* ---- debugging / measurement --------------------------------------------------
  * csb_debug_octave: after a csb_extract* call on slot 0, copies octave `oct`'s

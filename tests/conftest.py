@@ -24,6 +24,17 @@ def _has_gpu() -> bool:
         return False
 
 
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests are skipped (not errored) on a box without a GPU, unless they were asked for with -m gpu."""
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if gpu_items and not _has_gpu():
+        skip = pytest.mark.skip(reason="no CUDA GPU on this box (run with -m gpu on the B200)")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def gpu_ctx():
     """One product-library context for the whole GPU session (fails loudly without a GPU)."""

@@ -139,14 +139,17 @@ def test_extract_vs_reference(gpu_ctx, frames, synth1080, workdir, case):
         img, prm = PU.preblur(frames[1]), (6, 0.0, 0.1)          # main.cpp:308-309 pre-blur
     elif case == "synth_1080p":
         img, prm = synth1080, (5, 0.0, 1.0)
-    elif case == "synth_4k_rootsift":                            # BASELINE config 3
-        img, prm, root = csb.synth(3840, 2160, 2000), (5, 0.0, 2.0), True
+    elif case == "synth_4k_rootsift":                            # BASELINE config 3 at its own parameters:
+        img, prm, root = csb.synth(3840, 2160, 2000), (5, 0.0, 0.1), True   # thresh 0.1 -> ~94.6 k keypoints, maxPts 131072
     elif case == "initblur_odd_size":
         img, prm = csb.synth(517, 389, 91), (4, 0.5, 0.3)
     else:
         img, prm, root = csb.synth(640, 480, 33), (5, 0.0, 0.5), True
-    ours = gpu_ctx.extract(img, csb.make_params(*prm, 10.0, 0.0, rootsift=root), max_pts=65536)
-    ref = O.ref_extract(img, workdir, prm[0], prm[1], prm[2], 10.0, 0.0, root, 65536, safe=True, tag=case)
+    max_pts = 131072 if case == "synth_4k_rootsift" else 65536
+    ours = gpu_ctx.extract(img, csb.make_params(*prm, 10.0, 0.0, rootsift=root), max_pts=max_pts)
+    ref = O.ref_extract(img, workdir, prm[0], prm[1], prm[2], 10.0, 0.0, root, max_pts, safe=True, tag=case)
+    if case == "synth_4k_rootsift":
+        assert 90000 < len(ref) < 100000, len(ref)                # survey emulator: 94 585
     r = PU.compare_keypoints(ours, ref)
     assert r["n_ours"] == r["n_ref"] == r["matched"] and r["only_ours"] == 0 and r["only_ref"] == 0, r
     assert r["pos_exact"] == r["matched"], r                  # bit-exact positions and scales
@@ -156,14 +159,58 @@ def test_extract_vs_reference(gpu_ctx, frames, synth1080, workdir, case):
     assert PU.per_octave_counts(ours) == PU.per_octave_counts(ref)
 
 
+DESC_Q = (0.5, 0.9, 0.99, 0.999, 1.0)
+
+
+def _desc_err(a, b):
+    ia, ib, oa, ob = PU.match_sets(a, b)
+    assert len(oa) == 0 and len(ob) == 0
+    return PU.desc_rel_l2(a["data"][ia], b["data"][ib]), PU.ang_diff_deg(a["orientation"][ia], b["orientation"][ib])
+
+
 @needs_ref
-def test_reference_self_consistency(frames, workdir):
-    """Documents the reference's own run-to-run spread (the bound our tolerances inherit)."""
-    a = O.ref_extract(frames[0], workdir, 6, 0.0, 0.1, 10.0, 0.0, False, 32768, safe=True, tag="selfa")
-    b = O.ref_extract(frames[0], workdir, 6, 0.0, 0.1, 10.0, 0.0, False, 32768, safe=True, tag="selfb")
-    r = PU.compare_keypoints(a, b)
-    assert r["matched"] == len(a) == len(b) and r["pos_exact"] == r["matched"]
-    assert r["desc_max"] < 1e-3
+@pytest.mark.parametrize("case", ["gray1", "synth_1080p"])
+def test_descriptor_error_is_within_the_reference_own_spread(gpu_ctx, frames, synth1080, workdir, case):
+    """north_star asks for descriptors within 1e-4 relative L2 of the reference.  The reference does not meet that
+    against ITSELF: its descriptor votes are shared-memory float atomicAdds (cuSIFT_D.cu:234-253) and its orientation
+    histogram too (:343), so two runs of the unmodified binary on the same frame differ.  This test MEASURES that
+    spread (three reference runs, all three pairs pooled) next to ours-vs-reference (our deterministic result against
+    each of the three runs, pooled) and asserts, quantile by quantile:
+      * maximum: ours-vs-ref <= 1.05 x ref-vs-ref (measured on the B200: 3.7745e-4 both - the same keypoint);
+      * median / p90 / p99 / p99.9: within a factor 2.5 (+1e-7).  Measured (gray1, 9508 keypoints): ref-vs-ref
+        4.8e-8 / 9.9e-8 / 2.5e-5 / 2.0e-4, ours-vs-ref 8.2e-8 / 1.2e-7 / 5.3e-5 / 2.2e-4.  The reference's atomics
+        mostly land in the same order run to run, so it agrees with itself a little more often than with any other
+        summation order; ours sums in a fixed tree order;
+      * fraction within 1e-4: at most 0.5 % below the reference's own (measured 99.43 % vs 99.66 %);
+      * p99 below north_star's 1e-4 in absolute terms.
+    Both rows are printed (pytest -s) and written to gpurun_out/desc_spread_<case>.json."""
+    import json
+    img, prm = (frames[0], (6, 0.0, 0.1)) if case == "gray1" else (synth1080, (5, 0.0, 1.0))
+    refs = [O.ref_extract(img, workdir, prm[0], prm[1], prm[2], 10.0, 0.0, False, 65536, safe=True, tag=f"spread{case}{k}")
+            for k in range(3)]
+    ours = gpu_ctx.extract(img, csb.make_params(*prm, 10.0, 0.0), max_pts=65536)
+    rr = [_desc_err(refs[i], refs[j]) for i, j in ((0, 1), (0, 2), (1, 2))]
+    orr = [_desc_err(ours, r) for r in refs]
+    d_rr, d_or = np.concatenate([x[0] for x in rr]), np.concatenate([x[0] for x in orr])
+    a_rr, a_or = np.concatenate([x[1] for x in rr]), np.concatenate([x[1] for x in orr])
+    q_rr, q_or = np.quantile(d_rr, DESC_Q), np.quantile(d_or, DESC_Q)
+    rec = {"case": case, "keypoints": int(len(ours)), "quantiles": list(DESC_Q),
+           "ref_vs_ref": [float(x) for x in q_rr], "ours_vs_ref": [float(x) for x in q_or],
+           "ref_vs_ref_within_1e-4": float(np.mean(d_rr <= 1e-4)), "ours_vs_ref_within_1e-4": float(np.mean(d_or <= 1e-4)),
+           "ori_max_deg_ref_vs_ref": float(a_rr.max()), "ori_max_deg_ours_vs_ref": float(a_or.max())}
+    print("\ndescriptor relative-L2 error, quantiles", DESC_Q, "\n  ref vs ref :", q_rr, "\n  ours vs ref:", q_or, "\n ", rec)
+    try:
+        out = PU.ROOT / "gpurun_out"
+        out.mkdir(exist_ok=True)
+        (out / f"desc_spread_{case}.json").write_text(json.dumps(rec))
+    except OSError:
+        pass
+    for q, a, b in zip(DESC_Q[:-1], q_or[:-1], q_rr[:-1]):
+        assert a <= 2.5 * b + 1e-7, (q, a, b, rec)
+    assert q_or[-1] <= 1.05 * q_rr[-1] + 1e-7, rec
+    assert q_or[2] < PU.DESC_TOL, rec
+    assert rec["ours_vs_ref_within_1e-4"] >= rec["ref_vs_ref_within_1e-4"] - 0.005, rec
+    assert a_or.max() <= max(2.0 * a_rr.max(), 1e-4) and a_or.max() < PU.ORI_TOL_DEG, rec
 
 
 def test_host_entry_equals_device_entry(gpu_ctx, frames):
@@ -659,3 +706,190 @@ def test_rigid_transform_device_sampling_and_edges(gpu_ctx):
     # fewer than 3 points: identity, no inliers (nothing to fit)
     Rt0, n0, _ = gpu_ctx.rigid_transform(coord[:2], None, 16, 1.0, True)
     assert n0 == 0 and np.array_equal(Rt0.reshape(3, 4), np.eye(3, 4, dtype=np.float32))
+
+
+# ------------------------------------------------------- verdict r1: parity gaps ---
+def _c1_matched(gpu_ctx, frames):
+    a, b = PU.preblur(frames[0]), PU.preblur(frames[1])
+    p = csb.make_params(6, 0.0, 0.1)
+    k1 = gpu_ctx.extract(a, p, max_pts=32768)
+    k2 = gpu_ctx.extract(b, p, max_pts=32768)
+    return gpu_ctx.match(k1, k2, "l2")
+
+
+def test_improve_homography_host_shim_device_oracle_reference(gpu_ctx, frames, workdir):
+    """ImproveHomography (extras/homography.cu:271-337, main.cpp:335): the drop-in C++ function (host, OpenCV-free), the
+    device version behind csb_improve_homography, the CPU oracle and - where built - the UNMODIFIED reference, all
+    started from the same H on the same matched points: numFit equal, H within 1e-6, match_error within 1e-5."""
+    import json
+    import subprocess
+    m = _c1_matched(gpu_ctx, frames)
+    valid = O.valid_points(m, 0.0, 0.80)
+    if O.ref_available():
+        refh = O.ref_homography(m, workdir, 2048, 0.0, 0.80, 5.0, 5, 3.0, tag="imp")
+        H0 = refh["H"].astype(np.float32)
+    else:
+        rp = glibc_rand_samples(valid, 2048)
+        H0, _ = gpu_ctx.find_homography(m, rp, 5.0)
+    H_o, nfit_o, pts_o = O.improve_homography(m, H0, 5, 0.0, 0.80, 3.0)
+    assert nfit_o > 1500
+    # device
+    H_d, nfit_d, pts_d = gpu_ctx.improve_homography(m, H0, 5, 0.0, 0.80, 3.0)
+    assert nfit_d == nfit_o, (nfit_d, nfit_o)
+    assert np.allclose(H_d, H_o, rtol=1e-6, atol=1e-6), (H_d, H_o)
+    assert np.allclose(pts_d["match_error"], pts_o["match_error"], rtol=1e-5, atol=1e-5)
+    # C++ shim (host path)
+    exe = PU.ROOT / "build" / "csb_improve"
+    assert exe.exists(), "build/csb_improve missing: run make demo"
+    fin, fout = workdir / "imp_in.sift", workdir / "imp_out.sift"
+    O.write_sift_file(fin, m)
+    res = subprocess.run([str(exe), str(fin), str(fout), "5", "0.0", "0.80", "3.0"] + ["%.9g" % v for v in H0],
+                         capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    js = json.loads(res.stdout.strip().splitlines()[-1])
+    assert js["numFit"] == nfit_o
+    assert np.allclose(np.array(js["H"], np.float32), H_o, rtol=1e-6, atol=1e-6)
+    pts_s = O.read_sift_file(fout)
+    assert np.allclose(pts_s["match_error"], pts_o["match_error"], rtol=1e-5, atol=1e-5)
+    if O.ref_available():
+        assert refh["num_fit"] == nfit_o, (refh["num_fit"], nfit_o)
+        assert np.allclose(refh["H_improved"], H_o, rtol=1e-6, atol=1e-6), (refh["H_improved"], H_o)
+    # no loops: only the inlier count / match_error pass
+    H_z, nfit_z, _ = gpu_ctx.improve_homography(m, H0, 0, 0.0, 0.80, 3.0)
+    H_zo, nfit_zo, _ = O.improve_homography(m, H0, 0, 0.0, 0.80, 3.0)
+    assert nfit_z == nfit_zo and np.allclose(H_z, H_zo, rtol=1e-6, atol=1e-7)
+
+
+def test_allpairs_with_improve_vs_oracle(gpu_ctx):
+    """The batched pipeline with ImproveHomography appended to every pair (device IRLS, one CTA per pair)."""
+    imgs = [csb.synth(640, 480, 3100 + i) for i in range(3)]
+    p = csb.make_params(5, 0.0, 0.5)
+    sets = []
+    for im in imgs:
+        k = gpu_ctx.extract(im, p, max_pts=8192)
+        sets.append(np.ascontiguousarray(PU.canonical_sort(k)[:1280]))
+    # make set 1 a warped copy of set 0 so that one pair has a real homography to refine
+    sets[1] = sets[0].copy()
+    x, y = sets[0]["coords2D"][:, 0].astype(np.float64), sets[0]["coords2D"][:, 1].astype(np.float64)
+    den = 1e-5 * x - 2e-5 * y + 1.0
+    sets[1]["coords2D"][:, 0] = ((1.02 * x + 0.01 * y + 3.0) / den).astype(np.float32)
+    sets[1]["coords2D"][:, 1] = ((-0.015 * x + 0.98 * y - 2.0) / den).astype(np.float32)
+    dptrs = [gpu_ctx.upload_sift(s) for s in sets]
+    pairs = csb.all_pairs(len(sets))
+    loops, seed = 256, 11
+    try:
+        H, inl, nv, H2, nf = gpu_ctx.allpairs(dptrs, [len(s) for s in sets], pairs, "l2", loops, 0.0, 0.80, 5.0, seed,
+                                              improve_loops=5, improve_thresh=3.0)
+        for k, (i, j) in enumerate(pairs):
+            m = O.match(sets[i], sets[j], "l2")
+            valid = O.valid_points(m, 0.0, 0.80)
+            rp = gpu_ctx.sample_points(valid, loops, seed, k)
+            Ho, cnto = O.find_homography(m, rp, 5.0)
+            assert inl[k] == cnto and nv[k] == len(valid)
+            H2o, nfo, _ = O.improve_homography(m, H[k], 5, 0.0, 0.80, 3.0)
+            assert nf[k] == nfo, (k, nf[k], nfo)
+            assert np.allclose(H2[k], H2o, rtol=1e-5, atol=1e-5), (k, H2[k], H2o)
+        k01 = pairs.index((0, 1))
+        assert nf[k01] > 1000 and abs(H2[k01][0] - 1.02) < 1e-3 and abs(H2[k01][2] - 3.0) < 5e-2, (nf[k01], H2[k01])
+    finally:
+        for d in dptrs:
+            gpu_ctx.free(d)
+
+
+@pytest.mark.parametrize("kind", ["scaled_x10", "signed", "range_0_255", "huge", "norm_1p01"])
+def test_match_descriptors_outside_the_fp16_domain_use_the_exact_kernel(gpu_ctx, kind):
+    """MatchSiftData accepts ANY SiftPoint.data (extras/matching.cu:232-362 is plain fp32).  The tensor-core prefilter's
+    error bound needs descriptors that are finite in fp16 with squared norm <= 1.002; k_pack_f16 checks that and the
+    call falls back to the exact fp32 kernel otherwise.  Results must equal the oracle bit for bit either way."""
+    n1, n2 = 700, 1500
+    a, b = _rand_set(n1, 501), _rand_set(n2, 502)
+    r = np.random.default_rng(9)
+    expect_fallback = True
+    if kind == "scaled_x10":
+        a["data"] *= 10.0
+        b["data"] *= 10.0
+    elif kind == "signed":                                    # unit norm, mixed signs: still inside the domain
+        b["data"] *= r.choice([-1.0, 1.0], b["data"].shape).astype(np.float32)
+        expect_fallback = False
+    elif kind == "range_0_255":
+        a["data"] = np.round(a["data"] * 512).clip(0, 255)
+        b["data"] = np.round(b["data"] * 512).clip(0, 255)
+    elif kind == "huge":
+        b["data"][77, 5] = 1.0e6                              # > 65504: inf in fp16
+    else:
+        a["data"] *= np.float32(1.01)                         # |q|^2 = 1.02 > 1.002
+    L = csb.lib()
+    for dist in ("l2", "dot"):
+        before = L.csb_match_domain_fallbacks(gpu_ctx.h)
+        ours, orc = gpu_ctx.match(a, b, dist), O.match(a, b, dist)
+        took = L.csb_match_domain_fallbacks(gpu_ctx.h) - before
+        assert took == (1 if expect_fallback else 0), (kind, dist, took)
+        for f in ("score", "ambiguity", "match", "match_xpos", "match_ypos"):
+            assert np.array_equal(ours[f], orc[f]), (kind, dist, f)
+
+
+def test_allpairs_out_of_domain_set_falls_back(gpu_ctx):
+    sets = [_rand_set(512, 601), _rand_set(512, 602), _rand_set(512, 603)]
+    sets[1]["data"] *= 3.0
+    dptrs = [gpu_ctx.upload_sift(s) for s in sets]
+    pairs = csb.all_pairs(3)
+    try:
+        before = csb.lib().csb_match_domain_fallbacks(gpu_ctx.h)
+        gpu_ctx.allpairs(dptrs, [512] * 3, pairs, "l2", 64, 0.0, 0.80, 5.0, 3)
+        assert csb.lib().csb_match_domain_fallbacks(gpu_ctx.h) - before == 2        # pairs (0,1) and (1,2)
+        last = {}
+        for (i, j) in pairs:
+            last[i] = j
+        for i, j in last.items():
+            dev = gpu_ctx.download_sift(dptrs[i], 512)
+            ref = O.match(sets[i], sets[j], "l2")
+            for f in ("score", "ambiguity", "match"):
+                assert np.array_equal(dev[f], ref[f]), (i, j, f)
+    finally:
+        for d in dptrs:
+            gpu_ctx.free(d)
+
+
+@pytest.mark.parametrize("pitch", [640, 648, 768, 1024])
+def test_extract_with_noncanonical_source_pitch(gpu_ctx, frames, pitch):
+    """cuImage::Allocate takes any pitch (cuImage.cu:16-45); only the SOURCE image uses it - the DoG stack and its TMA
+    descriptors keep the slot's own pitch.  A pitch must still satisfy cudaCreateTextureObject (32-byte row alignment =
+    multiple of 8 floats; the reference binds the same texture, cuSIFT.cu:218-236): anything else is rejected with the
+    CUDA error as status (test below)."""
+    img = frames[0]
+    h, w = img.shape
+    want = PU.canonical_sort(gpu_ctx.extract(img, csb.make_params(5, 0.0, 0.5), max_pts=32768))
+    padded = np.full((h, pitch), -1.0e6, np.float32)            # poison between width and pitch
+    padded[:, :w] = img
+    d_img = gpu_ctx.alloc(padded.nbytes)
+    d_sift = gpu_ctx.alloc(588 * 32768)
+    pin = csb.PinnedArray(32768)
+    try:
+        gpu_ctx.h2d(d_img, padded)
+        cnt = gpu_ctx.extract_batch([d_img], w, h, pitch, csb.make_params(5, 0.0, 0.5), [d_sift], [pin.ptr], 32768)
+        got = PU.canonical_sort(pin.array[: cnt[0]].copy())
+        assert len(got) == len(want) > 1000
+        for f in ("coords2D", "scale", "sharpness", "edgeness", "orientation", "data", "subsampling"):
+            assert np.array_equal(got[f], want[f]), (pitch, f)
+    finally:
+        gpu_ctx.free(d_img)
+        gpu_ctx.free(d_sift)
+        pin.free()
+
+
+def test_unbindable_pitch_is_an_error_status(gpu_ctx, frames):
+    """A source pitch the texture unit cannot bind (644 floats = 2576 bytes, not a multiple of 32) comes back as a CUDA
+    status from csb_extract (the reference would print the CUDA error and exit, cutils.h:24-48); the context stays usable."""
+    img = frames[0]
+    h, w = img.shape
+    d_img = gpu_ctx.alloc(644 * h * 4)
+    d_sift = gpu_ctx.alloc(588 * 1024)
+    try:
+        n = ctypes.c_int(0)
+        p = csb.make_params(5, 0.0, 0.5)
+        rc = csb.lib().csb_extract(gpu_ctx.h, d_img, w, h, 644, ctypes.byref(p), d_sift, 1024, None, ctypes.byref(n))
+        assert rc != 0 and b"cudaCreateTextureObject" in csb.lib().csb_last_error(gpu_ctx.h)
+        assert len(gpu_ctx.extract(img, p, max_pts=32768)) > 1000
+    finally:
+        gpu_ctx.free(d_img)
+        gpu_ctx.free(d_sift)
