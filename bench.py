@@ -11,21 +11,25 @@ A step is one pass of the hot path over `frames_per_step` frames per GPU (512 = 
 4096 frames / 8 GPUs); frames are sharded cyclically over ranks, no data-path
 collective (weak scaling: per-GPU work is fixed).
 
-  value : frames/s, frame already in HBM -> SiftPoint array in HBM + count on the host
-          (SiftData(dev=true, host=false); the reference downloads the array only when
-          h_data != NULL, cuSIFT.cu:55-58,113)
-  value_host_results : same + every SiftPoint array downloaded into pinned host memory —
-          the legacy ExtractSift contract with host=true (main.cpp:317-328)
+  value : frames/s, frame already in HBM -> SiftPoint array in pinned HOST memory and numPts
+          known on the host: the legacy ExtractSift contract with host=true (main.cpp:317-328,
+          cuSIFT.cu:113) and SURVEY.md 8d's timed region
+  value_hbm_results : the same with the SiftPoint arrays left in HBM and only the count read back
+          (SiftData(dev=true, host=false): the reference downloads only when h_data != NULL,
+          cuSIFT.cu:55-58) - what the GPU does when the host link is not in the way
   e2e   : the same through csb_extract_batch with HOST frames: pinned-host upload of
           every frame and result download inside the timed region
           (HEAD SiftData::Extract(float*) contract, cuSIFT.cu:61-120).  8.3 MB up and
-          ~4.5 MB down per frame: bound by the box's host<->GPU bandwidth, which at 8 GPUs
-          is ~94 GB/s D2H in aggregate (tools/pcie_probe.py), i.e. 11.8 GB/s per GPU
-  e2e_u8: extension — frames uploaded as 8-bit and converted on the device
+          ~4.5 MB down per frame: bound by the box's host<->GPU bandwidth (profiles/r02_pcie_probe.json)
+  e2e_u8: extension - frames uploaded as 8-bit and converted on the device
+Extra keys (N = 1): per-kernel CUDA-event times and roofline fractions (`kernels`, `k1_pyramid_all`,
+`roofline_match`, `k3_orient_desc`), BASELINE configs 1-3 (`c1_demo_pipeline`, `c2` = latency,
+`c3_4k_rootsift`), config 5 sample / full (`allpairs_c5_*`).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -55,6 +59,23 @@ def peaks():
         d = json.loads(p.read_text())
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def tex_peak():
+    """Bilinear tex2D<float> fetch peak measured with tools/ubench_tex.cu on this pool's B200 (committed record)."""
+    p = ROOT / "profiles" / "r02_tex_peak.json"
+    try:
+        return float(json.loads(p.read_text())["gfetch_per_s"])
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 class ClockSampler:
@@ -180,6 +201,7 @@ def main():
     ap.add_argument("--pool", type=int, default=32)
     ap.add_argument("--slots", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the extra N=1 arms (matcher roofline, configs 1 and 3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -275,18 +297,18 @@ def main():
         return float(t[0]), float(t[1]), launches, counts
 
     for _ in range(args.warmup):
-        step_device()
+        step_device_host_results()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, wall_ms, launches, counts = timed(step_device, args.steps)
+    ms, wall_ms, launches, counts = timed(step_device_host_results, args.steps)
     clocks = sampler.stop()
     frames_total = F * world * args.steps
     value = frames_total / (ms / 1e3)
 
     for _ in range(args.warmup):
-        step_device_host_results()
-    ms_h, _, _, _ = timed(step_device_host_results, args.steps)
-    value_host_results = frames_total / (ms_h / 1e3)
+        step_device()
+    ms_h, _, _, _ = timed(step_device, args.steps)
+    value_hbm_results = frames_total / (ms_h / 1e3)
 
     for _ in range(args.warmup):
         step_host()
@@ -320,31 +342,52 @@ def main():
     ctx.profile(False)
     peak, peak_src = peaks()
     kernels = {}
+    # algorithmic HBM bytes per launch (4 B read + 28 B DoG written (+ 1 B next base) per octave pixel for
+    # the pyramid, 28 B read per octave pixel for the extrema scan)
+    alg_bytes = {"pyramid_o0": OCT_PX[0] * BYTES_PYR,                      # octave 0 incl. the octave-1 base it writes
+                 "pyramid_rest": sum(OCT_PX[1:]) * BYTES_PYR_LAST,         # octaves 1..4: base read + 7 DoG planes
+                 "down_chain": OCT_PX[1] * 4.0 + sum(OCT_PX[2:]) * 4.0,    # reads base 1, writes bases 2..4
+                 "find_points": sum(OCT_PX) * BYTES_EXT}
     for name, v in tab.items():
         if not v["launches"]:
             continue
         avg_ms = v["total_ms"] / v["launches"]
         ent = {"avg_us": round(avg_ms * 1e3, 2), "launches_per_frame": v["launches"] / nprof,
                "us_per_frame": round(v["total_ms"] * 1e3 / nprof, 2)}
-        alg = None
-        if name.startswith("blur_dog") and name[-1].isdigit():
-            o = int(name[-1])
-            alg = OCT_PX[o] * (BYTES_PYR if name.startswith("blur_dog_down") else BYTES_PYR_LAST)
-        elif name == "find_points":       # one launch covers every octave
-            alg = sum(OCT_PX) * BYTES_EXT
+        alg = alg_bytes.get(name)
         if alg:
             ent["alg_bytes"] = alg
             ent["achieved_gbs"] = round(alg / (avg_ms * 1e-3) / 1e9, 1)
             ent["frac"] = round(ent["achieved_gbs"] / peak, 4)
         kernels[name] = ent
-    hbm_kernels = {k: v for k, v in kernels.items() if "alg_bytes" in v}
+    hbm_kernels = {k: v for k, v in kernels.items() if k in ("pyramid_o0", "find_points")}
     dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["us_per_frame"]) if hbm_kernels else None
     roofline = None
     if dom:
         d = hbm_kernels[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": d["frac"], "traffic": ncu_traffic(dom), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": d["alg_bytes"], "avg_launch_us": d["avg_us"]}
+                    "algorithmic_bytes_per_launch": d["alg_bytes"], "avg_launch_us": d["avg_us"],
+                    "timing": "CUDA events around every launch on its own stream, one frame in flight, the stream held by a "
+                              "150 us spin kernel while the frame's launches are queued (no host enqueue gaps inside the brackets)"}
+    # the whole pyramid (K1 = 91.1 MB per 1080p frame) = three launches
+    k1_names = [k for k in ("pyramid_o0", "down_chain", "pyramid_rest") if k in kernels]
+    k1_all = None
+    if k1_names:
+        us = sum(kernels[k]["us_per_frame"] for k in k1_names)
+        alg = OCT_PX[0] * BYTES_PYR + sum(OCT_PX[1:-1]) * BYTES_PYR + OCT_PX[-1] * BYTES_PYR_LAST
+        k1_all = {"launches": k1_names, "us_per_frame": round(us, 2), "alg_bytes": alg,
+                  "achieved_gbs": round(alg / (us * 1e-6) / 1e9, 1), "frac": round(alg / (us * 1e-6) / 1e9 / peak, 4)}
+    # orientation + descriptor kernel: keypoints/s and fraction of the measured bilinear-fetch peak
+    k3 = None
+    if "orient_desc" in kernels:
+        kp = float(np.mean(counts))
+        us = kernels["orient_desc"]["us_per_frame"]
+        fetches = 1508.0 * kp                      # 121 x 4 (orientation) + 256 x 4 (descriptor) bilinear fetches per keypoint
+        tp = tex_peak()
+        k3 = {"us_per_frame": us, "keypoints_per_s": round(kp / (us * 1e-6), 0), "gfetch_per_s": round(fetches / (us * 1e-6) / 1e9, 1),
+              "tex_peak_gfetch_per_s": tp, "tex_frac": round(fetches / (us * 1e-6) / 1e9 / tp, 4) if tp else None,
+              "bytes_written_per_keypoint": 588}
 
     # BASELINE config 5 in miniature (informational): all-pairs MatchSiftData + 1024-hypothesis RANSAC over
     # 8 keypoint sets of 8192 points per GPU; the sets are exchanged with ONE NCCL all-gather, the unordered
@@ -391,6 +434,138 @@ def main():
     except Exception as e:  # noqa: BLE001  (informational arm: never fail the headline line)
         allpairs = {"unavailable": repr(e)}
 
+    # ---- extra arms at N = 1: matcher tensor-pipe roofline, BASELINE configs 1 and 3 ---------------------------------
+    roofline_match = c1 = c3 = None
+    if rank == 0 and world == 1 and not args.quick:
+        L = csb.lib()
+
+        def rand_set(n, seed):
+            r = np.random.default_rng(seed)
+            sset = np.zeros(n, csb.SIFT_DTYPE)
+            d = np.abs(r.standard_normal((n, 128))).astype(np.float32)
+            sset["data"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+            sset["coords2D"] = r.uniform(0, 1000, (n, 2)).astype(np.float32)
+            return sset
+
+        try:   # 8192 x 8192 MatchSiftData (BASELINE config 5's pair size), kernels timed with CUDA events
+            n = 8192
+            sa, sb = rand_set(n, 1), rand_set(n, 2)
+            d1, d2 = ctx.upload_sift(sa), ctx.upload_sift(sb)
+            for _ in range(3):
+                L.csb_match(ctx.h, d1, n, d2, n, 1, None)
+            reps = 20
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                L.csb_match(ctx.h, d1, n, d2, n, 1, None)
+            wall_us = (time.perf_counter() - t0) / reps * 1e6
+            ctx.profile(True)
+            ctx.profile_reset()
+            for _ in range(reps):
+                L.csb_match(ctx.h, d1, n, d2, n, 1, None)
+            mt = ctx.profile_table()
+            ctx.profile(False)
+            us = {k: mt[k]["total_ms"] * 1e3 / reps for k in ("match_pack", "match_tc", "match_rescore", "match_redo") if k in mt}
+            flop = 2.0 * 128 * n * n
+            burst, sustained, tsrc = tensor_peaks()
+            scan = us.get("match_tc", float("nan"))
+            scored = scan + us.get("match_rescore", 0.0) + us.get("match_redo", 0.0)
+            roofline_match = {"bound": "tensor", "n1": n, "n2": n, "flop": flop, "us": {k: round(v, 2) for k, v in us.items()},
+                              "achieved": round(flop / (scan * 1e-6) / 1e12, 1), "peak": burst, "unit": "TFLOP/s",
+                              "frac": round(flop / (scan * 1e-6) / 1e12 / burst, 4),
+                              "frac_incl_rescoring": round(flop / (scored * 1e-6) / 1e12 / burst, 4),
+                              "peak_source": tsrc + " bf16_tflops (burst; the scan is timed alone)",
+                              "input_type": "fp16 operands, fp32 accumulation in TMEM, exact fp32 rescoring of the short lists",
+                              "call_wall_us": round(wall_us, 1), "Mmatches_per_s_one_pair_at_a_time": round(n / wall_us, 2)}
+            from oracle import oracle as O
+            if O.ref_available():
+                work = ROOT / "gpurun_out"
+                work.mkdir(exist_ok=True)
+                fa, fb = work / "bench_a.sift", work / "bench_b.sift"
+                O.write_sift_file(fa, sa)
+                O.write_sift_file(fb, sb)
+                out = subprocess.run([str(O.REF_DRIVER), "benchmatch", str(fa), str(fb), "2", "5"], capture_output=True,
+                                     text=True, timeout=300)
+                fa.unlink(missing_ok=True)
+                fb.unlink(missing_ok=True)
+                if out.returncode == 0:
+                    roofline_match["reference_ms_per_pair"] = json.loads(out.stdout.strip().splitlines()[-1])["ms_per_pair"]
+            ctx.free(d1)
+            ctx.free(d2)
+        except Exception as e:  # noqa: BLE001
+            roofline_match = {"unavailable": repr(e)}
+
+        try:   # BASELINE config 1: main.cpp's demo on the reference's own image pair (tests/golden/frames.npz)
+            import cv2
+            z = np.load(ROOT / "tests" / "golden" / "frames.npz")
+            g = [cv2.GaussianBlur(z[k].astype(np.float32), (3, 3), 0.5) for k in ("gray1", "gray2")]   # main.cpp:308-309
+            p1 = csb.make_params(6, 0.0, 0.1, 10.0, 0.0)
+            dimg = [ctx.upload_image(x) for x in g]
+            dsf = [ctx.alloc(588 * 4096) for _ in range(2)]
+            pin = [csb.PinnedArray(4096) for _ in range(2)]
+            H9 = np.zeros(9, np.float32)
+            nin, nfit = C.c_int(0), C.c_int(0)
+            rngs = np.random.default_rng(1)
+            stages = {"extract_x2": [], "match": [], "find_homography_10000": [], "improve_homography_5": []}
+            for it in range(12):
+                t0 = time.perf_counter()
+                cnt = [int(ctx.extract_batch([dimg[k][0]], 640, 480, dimg[k][1], p1, [dsf[k]], [pin[k].ptr], 4096)[0]) for k in range(2)]
+                t1 = time.perf_counter()
+                L.csb_match(ctx.h, dsf[0], cnt[0], dsf[1], cnt[1], 1, pin[0].ptr)
+                t2 = time.perf_counter()
+                mm = pin[0].array[: cnt[0]]
+                valid = np.nonzero((mm["score"] > 0.0) & (mm["ambiguity"] < 0.80))[0].astype(np.int32)
+                rp = np.ascontiguousarray(valid[rngs.integers(0, len(valid), (4, 10000))], np.int32)
+                t3 = time.perf_counter()
+                ctx._check(L.csb_find_homography(ctx.h, dsf[0], cnt[0], rp.ctypes.data_as(C.POINTER(C.c_int)), 10000, 5.0,
+                                                 H9.ctypes.data_as(C.POINTER(C.c_float)), C.byref(nin)), "csb_find_homography")
+                t4 = time.perf_counter()
+                ctx._check(L.csb_improve_homography(ctx.h, dsf[0], cnt[0], H9.ctypes.data_as(C.POINTER(C.c_float)), 5, 0.0, 0.80, 3.0,
+                                                    C.byref(nfit), None), "csb_improve_homography")
+                t5 = time.perf_counter()
+                if it >= 2:
+                    for k, v in zip(stages, (t1 - t0, t2 - t1, t4 - t3, t5 - t4)):
+                        stages[k].append(v * 1e3)
+            c1 = {"workload": "C1: main.cpp demo on test/data/color1+2 (640x480, 3x3 pre-blur, 6 octaves, thresh 0.1, maxPts 4096), "
+                              "MatchSiftData L2, FindHomography(10000, 0.0, 0.80, 5.0), ImproveHomography(5, 0.0, 0.80, 3.0)",
+                  "ms_per_stage_median": {k: round(statistics.median(v), 4) for k, v in stages.items()},
+                  "ms_total_median": round(sum(statistics.median(v) for v in stages.values()), 4),
+                  "num_pts": cnt, "num_matches": int(nin.value), "num_fit": int(nfit.value)}
+            for d_, _ in dimg:
+                ctx.free(d_)
+            for d_ in dsf:
+                ctx.free(d_)
+        except Exception as e:  # noqa: BLE001
+            c1 = {"unavailable": repr(e)}
+
+        try:   # BASELINE config 3: one 3840x2160 frame, ExtractRootSift, thresh 0.1 (~95 k keypoints)
+            img4k = csb.synth(3840, 2160, 2000)
+            p3 = csb.make_params(5, 0.0, 0.1, 10.0, 0.0, rootsift=True)
+            d4k, pitch4k = ctx.upload_image(img4k)
+            ds4k = ctx.alloc(588 * 131072)
+            pin4k = csb.PinnedArray(131072)
+            ts = []
+            for it in range(13):
+                t0 = time.perf_counter()
+                c4k = ctx.extract_batch([d4k], 3840, 2160, pitch4k, p3, [ds4k], [pin4k.ptr], 131072)
+                if it >= 3:
+                    ts.append((time.perf_counter() - t0) * 1e3)
+            ms3 = statistics.median(ts)
+            ctx.profile(True)
+            ctx.profile_reset()
+            for _ in range(4):
+                ctx.extract_batch([d4k], 3840, 2160, pitch4k, p3, [ds4k], [pin4k.ptr], 131072)
+            t3 = ctx.profile_table()
+            ctx.profile(False)
+            c3 = {"workload": "C3: synth(3840,2160,2000), ExtractRootSift, 5 octaves, thresh 0.1, maxPts 131072; device frame -> "
+                              "SiftPoint array in pinned host memory", "ms_per_frame_median": round(ms3, 3),
+                  "keypoints": int(c4k[0]), "keypoints_per_s": round(int(c4k[0]) / (ms3 * 1e-3), 0),
+                  "kernel_us": {k: round(v["total_ms"] * 1e3 / 4, 1) for k, v in t3.items() if v["launches"]}}
+            ctx.free(d4k)
+            ctx.free(ds4k)
+            pin4k.free()
+        except Exception as e:  # noqa: BLE001
+            c3 = {"unavailable": repr(e)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
@@ -428,11 +603,10 @@ def main():
                        "frames_per_step_per_gpu": F, "frames_per_step": F * world, "slots_per_gpu": args.slots,
                        "l2": f"inputs larger than L2: {len(pool_ids)} x 8.3 MB frame pool + {args.slots} x 90 MB pyramid "
                              "workspaces cycle through HBM between reuses",
-                       "timed_region": "device frame -> SiftPoint array in HBM + count on the host (SiftData(dev=true, "
-                                       "host=false): the reference downloads only when h_data != NULL, cuSIFT.cu:55-58,113); "
-                                       "value_host_results adds the download of every SiftPoint array into pinned host "
-                                       "memory; e2e adds the upload of every frame as well"},
-            "value_host_results": value_host_results,
+                       "timed_region": "device frame -> SiftPoint array in pinned host memory + count on the host (legacy "
+                                       "ExtractSift contract, SURVEY.md 8d); value_hbm_results leaves the arrays in HBM "
+                                       "(SiftData(dev=true, host=false)); e2e adds the upload of every frame as well"},
+            "value_hbm_results": value_hbm_results,
             "ms_per_frame": ms / args.steps / (F * world), "wall_ms_per_step": wall_ms / args.steps,
             "latency_ms_single_frame": {"median": statistics.median(lat), "p99": sorted(lat)[int(len(lat) * 0.99) - 1]},
             "keypoints_per_frame": float(np.mean(counts)),
@@ -441,7 +615,8 @@ def main():
             "e2e_u8": e2e_u8,
             "gpu_launches": int(launches) * world, "gpu_launches_e2e": int(launches_e) * world,
             "allpairs_c5_sample": allpairs,
-            "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "roofline": roofline, "kernels": kernels, "k1_pyramid_all": k1_all, "k3_orient_desc": k3,
+            "roofline_match": roofline_match, "c1_demo_pipeline": c1, "c3_4k_rootsift": c3, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
     barrier()

@@ -395,6 +395,9 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
   s->user_h = h_sift;
   s->user_num = num_pts;
 
+  // profiling: hold the stream while the frame's launches and their event pairs are being queued, so that the events
+  // measure device execution back to back rather than the host's enqueue pace
+  if (ctx->profile) launch_delay(150000ull, st);
   CSB_CHECK(ctx, cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int) * (1 + CSB_MAX_OCTAVES), st));   // count + run ends
 
   // octave geometry, blur schedule (cuSIFT.cu:188) and per-octave constants.  The DoG stack always uses the
@@ -1008,6 +1011,7 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
   if (!d_sift1 || !d_sift2) return fail(ctx, CSB_E_INVALID, "csb_match: null device data");
   CSB_CHECK(ctx, cudaSetDevice(ctx->device));
   Slot *s = &ctx->slots[0];
+  if (ctx->profile) launch_delay(150000ull, s->stream);   // see enqueue_frame
   const bool use_tc = !ctx->match_exact && n1 >= 256 && n2 >= 256;
   if (!use_tc) {
     LaunchScope ls(ctx, s, "match");
@@ -1048,18 +1052,20 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
     }
     if (!ctx->tc_count) {
       CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_count, 256));
+      CSB_CHECK(ctx, cudaMemset(ctx->tc_count, 0, 256));
       CSB_CHECK(ctx, cudaHostAlloc((void **)&ctx->h_tc_count, 256, cudaHostAllocDefault));
     }
-    CSB_CHECK(ctx, cudaMemsetAsync(ctx->tc_count + 4, 0, sizeof(int), s->stream));   // out-of-domain flag of this call
+    CSB_CHECK(ctx, cudaMemsetAsync(ctx->tc_count + 4, 0, 4 * sizeof(int), s->stream));   // {out-of-domain, err^2} x 2 sets
     {
       LaunchScope ls(ctx, s, "match_pack");
       ctx->launches += 1;
       launch_pack_f16((const csb_sift_point *)sets[0], ns[0], ctx->tc_pack[0], ctx->tc_count + 4, s->stream);
-      launch_pack_f16((const csb_sift_point *)sets[1], ns[1], ctx->tc_pack[1], ctx->tc_count + 4, s->stream);
+      launch_pack_f16((const csb_sift_point *)sets[1], ns[1], ctx->tc_pack[1], ctx->tc_count + 6, s->stream);
     }
     {
       LaunchScope ls(ctx, s, "match_tc");
-      launch_match_tc(ctx->tc_pack[0], n1, ctx->tc_pack[1], n2, splits, ctx->tc_val, ctx->tc_idx, s->stream);
+      launch_match_tc(ctx->tc_pack[0], n1, ctx->tc_pack[1], n2, splits, ctx->tc_val, ctx->tc_idx, ctx->tc_count + 4,
+                      ctx->tc_count + 6, s->stream);
     }
     {
       LaunchScope ls(ctx, s, "match_rescore");
@@ -1073,13 +1079,13 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
       launch_match_blocks((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, distance, ctx->tc_list,
                           ctx->tc_count, (int)blk_need, ctx->tc_part, s->stream);
     }
-    CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_tc_count, ctx->tc_count, 5 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_tc_count, ctx->tc_count, 8 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   }
   CSB_CHECK(ctx, cudaGetLastError());
   if (use_tc) {
     CSB_CHECK(ctx, cudaStreamSynchronize(s->stream));
     ctx->tc_redo_blocks += ctx->h_tc_count[0];
-    if (ctx->h_tc_count[4]) {
+    if (ctx->h_tc_count[4] || ctx->h_tc_count[6]) {
       // a descriptor set outside the domain in which the fp16 prefilter's error bound holds (not finite in fp16, or
       // squared norm > 1.002): the short lists prove nothing, so the exact fp32 kernel recomputes every query
       ctx->tc_domain_fallbacks++;
@@ -1167,7 +1173,9 @@ int csb_improve_homography(csb_ctx *ctx, void *d_sift, int n, float *H9, int num
   Slot *s = &ctx->slots[0];
   if (!ctx->ih_dev) {
     CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ih_dev, 512));
+    CSB_CHECK(ctx, cudaMemset(ctx->ih_dev, 0, 512));
     CSB_CHECK(ctx, cudaHostAlloc((void **)&ctx->ih_host, 512, cudaHostAllocDefault));
+    memset(ctx->ih_host, 0, 512);
   }
   // layout (device and pinned mirror): [0,36) H_in, [64,100) H_out, [128,132) numfit, [256,..) job record
   float *dH_in = (float *)ctx->ih_dev, *dH_out = (float *)(ctx->ih_dev + 64);
@@ -1316,13 +1324,13 @@ int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_s
   if (ctx->ap_flags) cudaFree(ctx->ap_flags);
     if (ctx->h_ap_flags) cudaFreeHost(ctx->h_ap_flags);
     ctx->ap_flags = nullptr; ctx->h_ap_flags = nullptr; ctx->ap_flags_cap = 0;
-    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ap_flags, sizeof(int) * (size_t)n_sets));
-    CSB_CHECK(ctx, cudaHostAlloc((void **)&ctx->h_ap_flags, sizeof(int) * (size_t)n_sets, cudaHostAllocDefault));
+    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ap_flags, 2 * sizeof(int) * (size_t)n_sets));
+    CSB_CHECK(ctx, cudaHostAlloc((void **)&ctx->h_ap_flags, 2 * sizeof(int) * (size_t)n_sets, cudaHostAllocDefault));
     ctx->ap_flags_cap = n_sets;
   }
-  for (int i = 0; i < n_sets; i++) ctx->h_ap_flags[i] = 0;
+  for (int i = 0; i < 2 * n_sets; i++) ctx->h_ap_flags[i] = 0;
   if (use_tc) {
-    CSB_CHECK(ctx, cudaMemsetAsync(ctx->ap_flags, 0, sizeof(int) * (size_t)n_sets, st));
+    CSB_CHECK(ctx, cudaMemsetAsync(ctx->ap_flags, 0, 2 * sizeof(int) * (size_t)n_sets, st));
     size_t need = 0;
     for (int i = 0; i < n_sets; i++) if (counts[i] >= 256) need += (tc_packed_bytes(counts[i]) + 1023) & ~(size_t)1023;
     if (ctx->ap_pack_cap < need) {
@@ -1336,11 +1344,11 @@ int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_s
       if (counts[i] < 256) continue;
       packed[i] = ctx->ap_pack + off;
       off += (tc_packed_bytes(counts[i]) + 1023) & ~(size_t)1023;
-      launch_pack_f16((const csb_sift_point *)d_sifts[i], counts[i], packed[i], ctx->ap_flags + i, st);
+      launch_pack_f16((const csb_sift_point *)d_sifts[i], counts[i], packed[i], ctx->ap_flags + 2 * i, st);
       ctx->launches++;
     }
     // which sets satisfy the fp16 prefilter's precondition?  (one small read-back per batch of pairs)
-    CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_ap_flags, ctx->ap_flags, sizeof(int) * (size_t)n_sets, cudaMemcpyDeviceToHost, st));
+    CSB_CHECK(ctx, cudaMemcpyAsync(ctx->h_ap_flags, ctx->ap_flags, 2 * sizeof(int) * (size_t)n_sets, cudaMemcpyDeviceToHost, st));
     CSB_CHECK(ctx, cudaStreamSynchronize(st));
   }
   CSB_CHECK(ctx, cudaEventRecord(ctx->ap_packed, st));
@@ -1353,11 +1361,11 @@ int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_s
     csb_sift_point *s1 = (csb_sift_point *)d_sifts[i];
     const csb_sift_point *s2 = (const csb_sift_point *)d_sifts[j];
     if (n1 > 0 && n2 > 0) {
-      const bool in_domain = !ctx->h_ap_flags[i] && !ctx->h_ap_flags[j];
+      const bool in_domain = !ctx->h_ap_flags[2 * i] && !ctx->h_ap_flags[2 * j];
       if (use_tc && n1 >= 256 && n2 >= 256 && !in_domain) ctx->tc_domain_fallbacks++;
       if (use_tc && n1 >= 256 && n2 >= 256 && in_domain) {
         const int splits = tc_splits(n1, n2, ctx->sm_count);
-        launch_match_tc(packed[i], n1, packed[j], n2, splits, c.sl_val, c.sl_idx, c.st);
+        launch_match_tc(packed[i], n1, packed[j], n2, splits, c.sl_val, c.sl_idx, ctx->ap_flags + 2 * i, ctx->ap_flags + 2 * j, c.st);
         launch_rescore(s1, n1, s2, n2, c.sl_val, c.sl_idx, splits, distance, c.flags, c.list, c.cnt, c.st);
         launch_match_blocks(s1, n1, s2, n2, distance, c.list, c.cnt, (n1 + 15) / 16, c.part, c.st);
         ctx->launches += 5;

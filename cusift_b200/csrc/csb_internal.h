@@ -124,6 +124,7 @@ void launch_orient_desc(const OctaveTexSet &texs, int n_oct, const float *subs, 
                         unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st);
 void launch_ingest_u8(const unsigned char *d_src, int stride, int w, int h, float *d_dst, int pitch, int preblur, float k0,
                       float k1, cudaStream_t st);
+void launch_delay(unsigned long long ns, cudaStream_t st);   // measurement aid (profiling mode only)
 void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st);
 void launch_match(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
                   cudaStream_t st);
@@ -135,10 +136,11 @@ void launch_match_blocks(csb_sift_point *d_sift1, int n1, const csb_sift_point *
 size_t tc_packed_bytes(int n);
 int tc_pad(int n);
 int tc_splits(int n1, int n2, int sm_count);
-// *out_of_domain (device int, zeroed by the caller) is set when the set violates the fp16 error bound's precondition
-void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *out_of_domain, cudaStream_t st);
+// info = 2 device ints zeroed by the caller: [0] set when the set violates the fp16 error bound's precondition,
+// [1] = float bits of the largest squared fp16 rounding-error norm of a row (the pair's eps is derived from it)
+void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *info, cudaStream_t st);
 void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
-                     cudaStream_t st);
+                     const int *q_info, const int *c_info, cudaStream_t st);
 void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,
                     int n_splits, int distance, int *redo_flags, int *redo_list, int *redo_count, cudaStream_t st);
 void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,

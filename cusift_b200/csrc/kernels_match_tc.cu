@@ -36,13 +36,15 @@
 //                    split: massive near-ties) is flagged and redone by the exact fp32 kernel
 //                    (kernels_match.cu).
 //
-// fp16 inputs and the bound TC_EPS: rounding an element to fp16 changes it by a relative 2^-11 at most, so a
-// product of two rounded elements is off by at most (2^-10 + 2^-22) |q_k c_k| and the whole dot product by at most
-// 2^-10 * sum |q_k c_k| <= 2^-10 |q| |c| (Cauchy-Schwarz, any signs) = 9.77e-4 for unit vectors; fp16 subnormals
-// (|v| < 6.1e-5, absolute error 2^-25 each) and the fp32 accumulation add < 2e-6.  TC_EPS = 1e-3 covers that for
-// |q|^2, |c|^2 <= 1.002.  k_pack_f16 CHECKS the precondition (every element finite in fp16, squared norm <= 1.002)
-// and raises a flag otherwise; csb_match / the all-pairs path then route the call to the exact fp32 kernel, so
-// arbitrary SiftPoint.data (un-normalised, 0..255, huge) still gets the reference's exact result.
+// fp16 inputs and the error bound eps.  With q^ = fp16(q), dq = q - q^ (same for c):
+//   |q.c - q^.c^| = |dq.c + q^.dc| <= |dq| |c| + |q^| |dc|            (Cauchy-Schwarz, any signs)
+// k_pack_f16 MEASURES |dq| of every row while it packs (the rounding errors are known exactly there) and keeps the
+// maximum over the set, E; it also checks that every element is finite in fp16 and that no squared norm exceeds
+// 1.002.  A pair of sets (i, j) then uses eps = 1.002 (E_i + E_j) + 2e-5 (the last term covers the tensor core's
+// fp32 accumulation of 128 products <= 1): a rigorous bound, ~6e-4 for unit SIFT / RootSIFT descriptors instead of
+// the worst case 2^-10 = 9.8e-4.  Sets outside the checked domain (un-normalised, 0..255, huge values) raise a flag
+// and csb_match / the all-pairs path route the call to the exact fp32 kernel, so arbitrary SiftPoint.data still gets
+// the reference's exact result.
 #include <cuda_fp16.h>
 
 #include "csb_internal.h"
@@ -61,8 +63,7 @@ constexpr uint32_t SMEM_B_STAGE = 2 * B_HALF_BYTES;                             
 constexpr uint32_t SMEM_TC = SMEM_A + TC_STAGES * SMEM_B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 32 * (2 + 8);
 constexpr int RS_ROWS = 16;        // staged candidate rows per rescoring round (per warp)
-constexpr float TC_EPS = 1.0e-3f;   // bound on |fp16-input dot - exact dot| for descriptors in the checked domain
-constexpr float TC_MAX_NORM2 = 1.002f;
+constexpr float TC_MAX_NORM2 = 1.002f;   // squared-norm limit of the domain in which the error bound is derived
 
 // ---- PTX wrappers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -145,16 +146,17 @@ constexpr uint32_t IDESC_F16_M128_N256 = (1u << 4)                 // D format =
 // ---- 1. pack ----------------------------------------------------------------------
 // Packed layout (per set): two K-halves; half kb is a [n_pad][64] fp16 matrix (128-byte rows) in
 // which the 16-byte chunk c of row r is stored at chunk position c ^ (r & 7) (128B swizzle).
-// Also validates the domain in which TC_EPS bounds the fp16 error (see the header): *out_of_domain is set when a
-// row has a non-finite / fp16-overflowing element or a squared norm above TC_MAX_NORM2.
+// Also validates the domain of the error bound and measures its ingredients (see the header): info[0] is set when a
+// row has a non-finite / fp16-overflowing element or a squared norm above TC_MAX_NORM2; info[1] receives (as float
+// bits) the largest squared rounding-error norm |q - fp16(q)|^2 over the rows.  The caller zeroes info[0..1].
 __global__ void __launch_bounds__(256) k_pack_f16(const csb_sift_point *__restrict__ pts, int n, int n_pad,
-                                                  __half *__restrict__ packed, int *__restrict__ out_of_domain) {
+                                                  __half *__restrict__ packed, int *__restrict__ info) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 16-byte chunk): 16 chunks/row
   const int r = gid >> 4, c16 = gid & 15;
   const bool live = r < n_pad;                             // n_pad * 16 is a multiple of 32: whole warps are live or not
   const int kb = c16 >> 3, c = c16 & 7;
   __align__(16) __half v[8];
-  float ss = 0.0f;
+  float ss = 0.0f, es = 0.0f;
   bool bad = false;
   if (live && r < n) {
     const float *d = pts[r].data + 8 * c16;
@@ -163,6 +165,8 @@ __global__ void __launch_bounds__(256) k_pack_f16(const csb_sift_point *__restri
       const float f = d[i];
       v[i] = __float2half_rn(f);
       ss = __fmaf_rn(f, f, ss);
+      const float de = f - __half2float(v[i]);             // exact (Sterbenz / representable difference)
+      es = __fmaf_rn(de, de, es);
       bad = bad || !(fabsf(f) <= 65504.0f);               // NaN, inf, or beyond the fp16 range
     }
   } else {
@@ -170,8 +174,12 @@ __global__ void __launch_bounds__(256) k_pack_f16(const csb_sift_point *__restri
     for (int i = 0; i < 8; i++) v[i] = __float2half_rn(0.0f);
   }
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o, 16);   // the row's 16 threads are adjacent lanes
-  if (bad || !(ss <= TC_MAX_NORM2)) *out_of_domain = 1;
+  for (int o = 8; o > 0; o >>= 1) {                        // the row's 16 threads are adjacent lanes
+    ss += __shfl_xor_sync(0xffffffffu, ss, o, 16);
+    es += __shfl_xor_sync(0xffffffffu, es, o, 16);
+  }
+  if (bad || !(ss <= TC_MAX_NORM2)) info[0] = 1;
+  else if (c16 == 0 && es > 0.0f) atomicMax(info + 1, __float_as_int(es * 1.0001f));   // non-negative floats order like ints
   if (!live) return;
   char *dst = reinterpret_cast<char *>(packed) + (size_t)kb * n_pad * KHALF_BYTES_PER_ROW +
               (size_t)r * KHALF_BYTES_PER_ROW + ((c ^ (r & 7)) << 4);
@@ -182,7 +190,8 @@ __global__ void __launch_bounds__(256) k_pack_f16(const csb_sift_point *__restri
 __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__restrict__ q_packed, int nq_pad,
                                                             const __half *__restrict__ c_packed, int nc, int nc_pad,
                                                             int tiles_per_split, float *__restrict__ out_val,
-                                                            int *__restrict__ out_idx, int n_splits) {
+                                                            int *__restrict__ out_idx, int n_splits,
+                                                            const int *__restrict__ q_info, const int *__restrict__ c_info) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment for the swizzle atoms
   unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -339,7 +348,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
       reduce64(rb, qb);
     }
     // ---- sweep 2: list every candidate with approximate dot >= m2 - 2 eps ----
-    const float thr = m2 - 2.0f * TC_EPS;
+    // eps of this pair of sets from the rounding-error norms measured at pack time (header comment)
+    const float eps = 1.002f * (sqrtf(__int_as_float(q_info[1])) + sqrtf(__int_as_float(c_info[1]))) + 2.0e-5f;
+    const float thr = m2 - 2.0f * eps;
     // Hits (about 2 per query and split) are appended straight to the global short list.  The append path
     // runs for the whole warp whenever ANY lane has a hit in an 8-column group (about a quarter of the
     // groups), so it must be short: a bit mask of the group's hits, then one iteration per set bit.
@@ -529,14 +540,14 @@ int tc_splits(int n1, int n2, int sm_count) {
   return s;
 }
 
-void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *out_of_domain, cudaStream_t st) {
+void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *info, cudaStream_t st) {
   const int n_pad = tc_pad(n);
   const int threads = n_pad * 16;
-  k_pack_f16<<<(threads + 255) / 256, 256, 0, st>>>(pts, n, n_pad, reinterpret_cast<__half *>(packed), out_of_domain);
+  k_pack_f16<<<(threads + 255) / 256, 256, 0, st>>>(pts, n, n_pad, reinterpret_cast<__half *>(packed), info);
 }
 
 void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
-                     cudaStream_t st) {
+                     const int *q_info, const int *c_info, cudaStream_t st) {
   const int nq_pad = tc_pad(n1), nc_pad = tc_pad(n2);
   const int ctiles = nc_pad / TC_CT;
   const int tiles_per_split = (ctiles + n_splits - 1) / n_splits;
@@ -552,7 +563,7 @@ void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2,
   dim3 grd(nq_pad / TC_QT, n_splits);
   k_match_tc<<<grd, TC_THREADS, SMEM_TC, st>>>(reinterpret_cast<const __half *>(q_packed), nq_pad,
                                                reinterpret_cast<const __half *>(c_packed), n2, nc_pad, tiles_per_split,
-                                               sl_val, sl_idx, n_splits);
+                                               sl_val, sl_idx, n_splits, q_info, c_info);
 }
 
 void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,
