@@ -20,7 +20,7 @@ build/obj/%.o: cusift_b200/csrc/%.cu cusift_b200/csrc/csb_internal.h cusift_b200
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/obj/$*.ptxas.log || (cat build/obj/$*.ptxas.log; exit 1)
 
 $(LIB): $(OBJ)
-	$(NVCC) $(ARCH) -shared -cudart shared -o $@ $(OBJ)
+	$(NVCC) $(ARCH) -shared -cudart shared -o $@ $(OBJ) -ldl
 
 demo: build/csb_demo build/csb_ref_tests build/csb_improve
 build/csb_demo: tests/cpp/csb_demo.cpp $(LIB)

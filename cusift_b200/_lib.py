@@ -74,6 +74,11 @@ SIGNATURES = {
     "csb_sample_hash": (C.c_uint, [C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]),
     "csb_allpairs_match_ransac_improve": (_i, [_vp, _i, C.POINTER(_vp), _ip, _i, _ip, _ip, C.POINTER(C.c_uint), _i, _i, C.c_float,
                                                C.c_float, C.c_float, C.c_uint, _i, C.c_float, _fp, _ip, _ip, _fp, _ip]),
+    "csb_nccl_unique_id": (_i, [_vp]),
+    "csb_nccl_comm_create": (_i, [_vp, _i, _i, _vp, C.POINTER(_vp)]),
+    "csb_nccl_comm_destroy": (_i, [_vp]),
+    "csb_allpairs_distributed": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(_vp), _ip, _i, _i, _i, C.c_float, C.c_float, C.c_float,
+                                      C.c_uint, _i, C.c_float, _fp, _ip, _ip, _fp, _ip, C.POINTER(C.c_double)]),
     "csb_improve_homography": (_i, [_vp, _vp, _i, _fp, _i, C.c_float, C.c_float, C.c_float, _ip, _vp]),
     "csb_debug_octave": (_i, [_vp, _i, _fp, _fp, _ip, _ip]),
     "csb_profile_enable": (_i, [_vp, _i]),

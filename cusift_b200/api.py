@@ -352,6 +352,49 @@ class Context:
             nv.ctypes.data_as(ip)), "csb_allpairs_match_ransac")
         return H[:n_pairs], inl[:n_pairs], nv[:n_pairs]
 
+    # ---- multi-GPU all-pairs (one process per GPU) -------------------------
+    def nccl_comm(self, rank: int, world: int, broadcast_bytes):
+        """Creates the library's NCCL communicator.  broadcast_bytes(buf: bytes | None) -> bytes must return rank 0's
+        128-byte id on every rank (e.g. via torch.distributed.broadcast_object_list)."""
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            self._check(self._L.csb_nccl_unique_id(idbuf), "csb_nccl_unique_id")
+        raw = broadcast_bytes(idbuf.raw if rank == 0 else None)
+        idbuf = C.create_string_buffer(raw, 128)
+        comm = C.c_void_p()
+        self._check(self._L.csb_nccl_comm_create(self.h, rank, world, idbuf, C.byref(comm)), "csb_nccl_comm_create")
+        return comm
+
+    def nccl_comm_destroy(self, comm):
+        self._L.csb_nccl_comm_destroy(comm)
+
+    def allpairs_distributed(self, comm, rank: int, world: int, d_local_sifts, local_counts, cap: int, distance="l2",
+                             num_loops=1024, min_score=0.0, max_ambiguity=0.80, thresh=5.0, seed=1, improve_loops=0,
+                             improve_thresh=3.0):
+        """csb_allpairs_distributed: returns dict(H, inliers, n_valid[, H_improved, num_fit], timings_ms) for ALL pairs."""
+        spr = len(d_local_sifts)
+        n_sets = spr * world
+        n_pairs = n_sets * (n_sets - 1) // 2
+        ptrs = (C.c_void_p * spr)(*d_local_sifts)
+        cnts = np.ascontiguousarray(local_counts, np.int32)
+        H = np.zeros((max(n_pairs, 1), 9), np.float32)
+        inl = np.zeros(max(n_pairs, 1), np.int32)
+        nv = np.zeros(max(n_pairs, 1), np.int32)
+        H2 = np.zeros((max(n_pairs, 1), 9), np.float32)
+        nf = np.zeros(max(n_pairs, 1), np.int32)
+        tm = np.zeros(4, np.float64)
+        ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+        self._check(self._L.csb_allpairs_distributed(
+            self.h, comm, rank, world, spr, ptrs, cnts.ctypes.data_as(ip), cap, 1 if distance == "l2" else 0, num_loops,
+            min_score, max_ambiguity, thresh, seed, improve_loops, improve_thresh, H.ctypes.data_as(fp), inl.ctypes.data_as(ip),
+            nv.ctypes.data_as(ip), H2.ctypes.data_as(fp) if improve_loops > 0 else None,
+            nf.ctypes.data_as(ip) if improve_loops > 0 else None, tm.ctypes.data_as(C.POINTER(C.c_double))),
+            "csb_allpairs_distributed")
+        out = {"H": H[:n_pairs], "inliers": inl[:n_pairs], "n_valid": nv[:n_pairs], "timings_ms": tm}
+        if improve_loops > 0:
+            out["H_improved"], out["num_fit"] = H2[:n_pairs], nf[:n_pairs]
+        return out
+
     def sample_points(self, valid: np.ndarray, num_loops: int, seed: int, pair_id: int) -> np.ndarray:
         """Host restatement of the device sample generator (k_make_samples): int32 [4][num_loops]."""
         nv = len(valid)

@@ -643,6 +643,7 @@ bad:
 void csb_ctx_destroy(csb_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  csb_dist_release(ctx);
   if (ctx->trace && ctx->frames)
     fprintf(stderr, "[csb] %lld frames on %d slots: host queueing %.1f us/frame, host waiting %.1f us/frame\n", ctx->frames,
             ctx->n_slots, ctx->host_enqueue_ms * 1e3 / ctx->frames, ctx->host_wait_ms * 1e3 / ctx->frames);
@@ -1318,10 +1319,7 @@ int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_s
   }
   std::vector<void *> packed(n_sets, nullptr);
   if (ctx->ap_flags_cap < (size_t)n_sets) {
-    if (ctx->ih_dev) cudaFree(ctx->ih_dev);
-  if (ctx->ih_host) cudaFreeHost(ctx->ih_host);
-  if (ctx->ap_jobs) cudaFree(ctx->ap_jobs);
-  if (ctx->ap_flags) cudaFree(ctx->ap_flags);
+    if (ctx->ap_flags) cudaFree(ctx->ap_flags);
     if (ctx->h_ap_flags) cudaFreeHost(ctx->h_ap_flags);
     ctx->ap_flags = nullptr; ctx->h_ap_flags = nullptr; ctx->ap_flags_cap = 0;
     CSB_CHECK(ctx, cudaMalloc((void **)&ctx->ap_flags, 2 * sizeof(int) * (size_t)n_sets));

@@ -155,6 +155,8 @@ void launch_improve_homography(const void *d_jobs, int n_jobs, int num_loops, fl
                                cudaStream_t st);
 size_t improve_job_bytes();
 void improve_job_fill(void *h_job, void *d_pts, int n, const float *d_H_in, float *d_H_out, int *d_numfit);
+// frees the multi-GPU exchange buffers of a context (csb_dist.cu); called by csb_ctx_destroy
+void csb_dist_release(csb_ctx *ctx);
 // rigid-transform RANSAC (kernels_rigid.cu)
 void launch_rigid_hypotheses(const float *d_coord, int num_pts, int *d_indices, int draw, unsigned int seed, int type3d,
                              int num_loops, float thresh2, float *d_Rt, int *d_counts, cudaStream_t st);

@@ -207,6 +207,27 @@ int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_s
                                       int improve_loops, float improve_thresh, float *H_out, int *inliers_out,
                                       int *nvalid_out, float *H_improved_out, int *numfit_out);
 
+/* ---- multi-GPU all-pairs (BASELINE config 5; the reference is single-GPU) ------------------------------------
+ * One process per GPU.  Every rank owns `sets_per_rank` keypoint sets (device SiftPoint arrays of at most `cap`
+ * points); global set g = rank * sets_per_rank + local index.  csb_allpairs_distributed all-gathers the sets with NCCL
+ * (one ncclAllGather per local set index, on its own stream, underneath the pairs whose two sets are local),
+ * partitions the n(n-1)/2 unordered pairs (i < j, query = i) cyclically by flattened pair index, runs
+ * csb_allpairs_match_ransac_improve on the rank's share and all-gathers the per-pair results: on return EVERY rank
+ * holds H / inliers / n_valid (/ H_improved / numfit) of ALL pairs in flattened (i-major) order; the sample generator
+ * is fed the flattened pair index, so results do not depend on the number of ranks.
+ * `comm` is an ncclComm_t over the same ranks (NCCL is bound at run time with dlopen("libnccl.so.2"), the library has
+ * no link-time dependency on it).  Callers without an NCCL binding of their own create it here: rank 0 fills a
+ * 128-byte id with csb_nccl_unique_id and distributes it by any means, every rank calls csb_nccl_comm_create.
+ * world == 1 works without NCCL (comm may be NULL).  timings_ms (optional, 4 doubles): local pairs + queueing the
+ * exchange, waiting for the exchange, remaining pairs, result exchange. */
+int csb_nccl_unique_id(void *id128);
+int csb_nccl_comm_create(csb_ctx *ctx, int rank, int world, const void *id128, void **comm_out);
+int csb_nccl_comm_destroy(void *comm);
+int csb_allpairs_distributed(csb_ctx *ctx, void *comm, int rank, int world, int sets_per_rank, void *const *d_local_sifts,
+                             const int *local_counts, int cap, int distance, int num_loops, float min_score, float max_ambiguity,
+                             float thresh, unsigned int seed, int improve_loops, float improve_thresh, float *H_out,
+                             int *inliers_out, int *nvalid_out, float *H_improved_out, int *numfit_out, double *timings_ms);
+
 /* ImproveHomography (extras/homography.cu:271-337; declared in main.cpp:19) on the DEVICE copy of the points:
  * `num_loops` rounds of re-weighted least squares (weights thresh^2 / (err + thresh^2), points with
  * score < min_score || ambiguity > max_ambiguity skipped, 8x8 normal equations in fp64, Cholesky), then the number of

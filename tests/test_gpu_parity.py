@@ -893,3 +893,26 @@ def test_unbindable_pitch_is_an_error_status(gpu_ctx, frames):
     finally:
         gpu_ctx.free(d_img)
         gpu_ctx.free(d_sift)
+
+
+def test_allpairs_distributed_single_rank_equals_batched_call(gpu_ctx):
+    """csb_allpairs_distributed with world = 1 (no NCCL needed): same pairs, same flattened order, same results as
+    csb_allpairs_match_ransac_improve.  The multi-rank exchange itself is exercised by tools/allpairs_bench.py --check
+    under torchrun (2+ GPUs): every rank ends with the results of a single-rank run."""
+    sets = [_rand_set(600 + 10 * k, 700 + k) for k in range(4)]
+    for s in sets:
+        s["match_xpos"] = 0
+    dptrs = [gpu_ctx.upload_sift(s) for s in sets]
+    cnts = [len(s) for s in sets]
+    pairs = csb.all_pairs(4)
+    try:
+        ref = gpu_ctx.allpairs(dptrs, cnts, pairs, "l2", 128, 0.0, 0.80, 5.0, 5, None, improve_loops=2, improve_thresh=3.0)
+        for d, s in zip(dptrs, sets):
+            gpu_ctx.h2d(d, s)                                         # the call above wrote match fields: restore
+        out = gpu_ctx.allpairs_distributed(None, 0, 1, dptrs, cnts, 640, "l2", 128, 0.0, 0.80, 5.0, 5, 2, 3.0)
+        assert np.array_equal(out["inliers"], ref[1]) and np.array_equal(out["n_valid"], ref[2])
+        assert np.array_equal(out["H"], ref[0]) and np.array_equal(out["num_fit"], ref[4])
+        assert np.allclose(out["H_improved"], ref[3], rtol=1e-6, atol=1e-6)
+    finally:
+        for d in dptrs:
+            gpu_ctx.free(d)
