@@ -10,8 +10,8 @@ SRC     := $(wildcard cusift_b200/csrc/*.cu)
 OBJ     := $(patsubst cusift_b200/csrc/%.cu,build/obj/%.o,$(SRC))
 LIB     := cusift_b200/libcusift_b200.so
 
-.PHONY: all lib demo oracle ref clean
-all: lib demo oracle ref
+.PHONY: all lib demo oracle ref refharness clean
+all: lib demo oracle ref refharness
 
 lib: $(LIB)
 
@@ -34,6 +34,21 @@ build/csb_improve: tests/cpp/csb_improve.cpp $(LIB)
 build/csb_ref_tests: tests/cpp/ref_tests.cpp $(LIB)
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O2 -std=c++17 -cudart shared -Iinclude -Iinclude/cusift -o $@ $< -Lcusift_b200 -lcusift_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../cusift_b200'
+
+# the reference's OWN main.cpp and test/test.cpp, compiled UNCHANGED against the drop-in headers
+# (include/cusift/) + the harness compatibility pack (tests/compat/: opencv2 / gtest / vl subsets) and linked with
+# libcusift_b200.so.  The sources are copied into build/_refsrc (git-ignored build scratch) only because a quoted
+# #include searches the including file's own directory first, which would pick up the reference's headers instead.
+# Only where /root/reference exists; the GPU box runs the prebuilt binaries.
+REF ?= /root/reference
+COMPAT_FLAGS := $(ARCH) -O2 -std=c++17 -cudart shared -w -Itests/compat -Iinclude/cusift -Iinclude
+refharness: $(LIB)
+	@if [ ! -d $(REF) ]; then echo "reference not present at $(REF): keeping prebuilt build/ref_*"; exit 0; fi; \
+	mkdir -p build/_refsrc/test && cp $(REF)/main.cpp build/_refsrc/main.cpp && cp $(REF)/test/test.cpp build/_refsrc/test/test.cpp && \
+	cmp -s $(REF)/main.cpp build/_refsrc/main.cpp && cmp -s $(REF)/test/test.cpp build/_refsrc/test/test.cpp && \
+	$(NVCC) $(COMPAT_FLAGS) -o build/ref_main_demo build/_refsrc/main.cpp -Lcusift_b200 -lcusift_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../cusift_b200' && \
+	$(NVCC) $(COMPAT_FLAGS) -o build/ref_test_suite build/_refsrc/test/test.cpp tests/compat/gtest_main.cpp -Lcusift_b200 -lcusift_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../cusift_b200' && \
+	rm -rf build/_refsrc
 
 oracle:
 	$(MAKE) -C oracle oracle
