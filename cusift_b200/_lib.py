@@ -50,6 +50,7 @@ SIGNATURES = {
     "csb_host_free": (_i, [_vp]),
     "csb_device_alloc": (_i, [_vp, C.POINTER(_vp), _ull]),
     "csb_device_free": (_i, [_vp, _vp]),
+    "csb_forget_image": (_i, [_vp, _vp]),
     "csb_memcpy_h2d": (_i, [_vp, _vp, _vp, _ull]),
     "csb_memcpy_d2h": (_i, [_vp, _vp, _vp, _ull]),
     "csb_upload_image": (_i, [_vp, _vp, _i, _vp, _i, _i]),
@@ -64,6 +65,7 @@ SIGNATURES = {
     "csb_extract_batch_u8": (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i, _i, C.POINTER(CsbParams), C.POINTER(_vp),
                                    C.POINTER(_vp), _i, _ip]),
     "csb_scale_down": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    "csb_scale_down_var": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, C.c_float]),
     "csb_rootsift": (_i, [_vp, _vp, _i]),
     "csb_match": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "csb_match_redo_blocks": (C.c_longlong, [_vp]),

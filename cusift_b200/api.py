@@ -243,14 +243,14 @@ class Context:
         finally:
             self.free(d_dst)
 
-    def scale_down(self, img: np.ndarray) -> np.ndarray:
+    def scale_down(self, img: np.ndarray, variance: float = 0.5) -> np.ndarray:
         img = np.ascontiguousarray(img, np.float32)
         h, w = img.shape
         d_src, sp = self.upload_image(img)
         dp = align_up(w // 2, 128)
         d_dst = self.alloc(4 * dp * (h // 2))
         try:
-            self._check(self._L.csb_scale_down(self.h, d_src, w, h, sp, d_dst, dp), "csb_scale_down")
+            self._check(self._L.csb_scale_down_var(self.h, d_src, w, h, sp, d_dst, dp, variance), "csb_scale_down_var")
             return self.download_image(d_dst, dp, w // 2, h // 2)
         finally:
             self.free(d_src)

@@ -314,8 +314,7 @@ void preblur_kernel(float *k0, float *k1) {
 }
 
 // ---- host-side constants, restated verbatim from the reference -----------------
-void scale_down_kernel(float k3[3]) {     // cuSIFT.cu:320-338 with variance = 0.5f (cuSIFT.cu:185)
-  const float variance = 0.5f;
+void scale_down_kernel(float k3[3], float variance = 0.5f) {     // cuSIFT.cu:320-338; ExtractSiftLoop passes 0.5f (cuSIFT.cu:185)
   float h_Kernel[5], kernelSum = 0.0f;
   for (int j = 0; j < 5; j++) {
     h_Kernel[j] = (float)expf(-(double)(j - 2) * (j - 2) / 2.0 / variance);
@@ -708,6 +707,24 @@ int csb_device_alloc(csb_ctx *ctx, void **d_ptr, unsigned long long bytes) {
   CSB_CHECK(ctx, cudaMalloc(d_ptr, (size_t)bytes));
   return 0;
 }
+int csb_forget_image(csb_ctx *ctx, const void *d_ptr) {
+  if (!ctx) return CSB_E_INVALID;
+  if (!d_ptr) return 0;
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  for (int i = 0; i < ctx->n_slots; i++) {   // drop cached textures / TMA descriptors over this buffer
+    Slot *s = &ctx->slots[i];
+    for (size_t k = 0; k < s->tex_cache.size();) {
+      if (s->tex_cache[k].ptr == d_ptr) {
+        cudaStreamSynchronize(s->stream);
+        cudaDestroyTextureObject(s->tex_cache[k].tex);
+        s->tex_cache.erase(s->tex_cache.begin() + k);
+      } else {
+        k++;
+      }
+    }
+  }
+  return 0;
+}
 int csb_device_free(csb_ctx *ctx, void *d_ptr) {
   if (!ctx) return CSB_E_INVALID;
   if (!d_ptr) return 0;
@@ -977,11 +994,17 @@ int csb_extract_batch_u8(csb_ctx *ctx, int n_frames, const unsigned char *const 
 }
 
 int csb_scale_down(csb_ctx *ctx, const float *d_src, int w, int h, int src_pitch, float *d_dst, int dst_pitch) {
-  if (!ctx || !d_src || !d_dst || w < 2 || h < 2) return fail(ctx, CSB_E_INVALID, "csb_scale_down: bad argument");
+  return csb_scale_down_var(ctx, d_src, w, h, src_pitch, d_dst, dst_pitch, 0.5f);
+}
+
+int csb_scale_down_var(csb_ctx *ctx, const float *d_src, int w, int h, int src_pitch, float *d_dst, int dst_pitch,
+                       float variance) {
+  if (!ctx || !d_src || !d_dst || w < 2 || h < 2 || !(variance > 0.0f))
+    return fail(ctx, CSB_E_INVALID, "csb_scale_down: bad argument");
   CSB_CHECK(ctx, cudaSetDevice(ctx->device));
   Slot *s = &ctx->slots[0];
   float k3[3];
-  scale_down_kernel(k3);
+  scale_down_kernel(k3, variance);
   {
     LaunchScope ls(ctx, s, "scale_down");
     launch_scale_down(d_src, w, h, src_pitch, d_dst, dst_pitch, k3, s->stream);

@@ -36,9 +36,18 @@ static_assert(sizeof(cuImage) == 48, "cuImage must be 48 bytes (cuImage.h:8-26)"
 namespace {
 
 // One lazily created context per device, shared by every shim object of the process.
+std::mutex &shim_mu() { static std::mutex mu; return mu; }
+std::map<int, csb_ctx *> &shim_ctxs() { static std::map<int, csb_ctx *> ctxs; return ctxs; }
+csb_ctx *shim_ctx_if_exists() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(shim_mu());
+  auto it = shim_ctxs().find(dev);
+  return it != shim_ctxs().end() ? it->second : nullptr;
+}
 csb_ctx *shim_ctx() {
-  static std::mutex mu;
-  static std::map<int, csb_ctx *> ctxs;
+  std::mutex &mu = shim_mu();
+  std::map<int, csb_ctx *> &ctxs = shim_ctxs();
   int dev = 0;
   safeCall(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(mu);
@@ -79,6 +88,9 @@ cuImage::cuImage(int width_, int height_, float *h_data_, bool download)
 }
 
 cuImage::~cuImage() {
+  // the context caches a texture object / TMA descriptor per frame it has seen: drop them before the memory goes away
+  if (d_data != NULL)
+    if (csb_ctx *ctx = shim_ctx_if_exists()) csb_forget_image(ctx, d_data);
   if (d_internalAlloc && d_data != NULL) safeCall(cudaFree(d_data));
   d_data = NULL;
   if (h_internalAlloc && h_data != NULL) free(h_data);
@@ -226,12 +238,8 @@ double ScaleDown(cuImage &res, cuImage &src, float variance) {
     printf("ScaleDown: missing data\n");
     return 0.0;
   }
-  if (variance != 0.5f) {
-    fprintf(stderr, "ScaleDown: only variance 0.5f is supported (the reference's sole call site, cuSIFT.cu:185)\n");
-    exit(-1);
-  }
   csb_ctx *ctx = shim_ctx();
-  shim_check(ctx, csb_scale_down(ctx, src.d_data, src.width, src.height, src.pitch, res.d_data, res.pitch),
+  shim_check(ctx, csb_scale_down_var(ctx, src.d_data, src.width, src.height, src.pitch, res.d_data, res.pitch, variance),
              "ScaleDown");
   return 0.0;
 }

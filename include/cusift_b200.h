@@ -88,6 +88,9 @@ int  csb_host_free(void *ptr);
  * to / from a pitched device image (pitch in floats). */
 int  csb_device_alloc(csb_ctx *ctx, void **d_ptr, unsigned long long bytes);
 int  csb_device_free(csb_ctx *ctx, void *d_ptr);
+/* A caller that frees a frame it allocated itself (cudaFree) tells the context, which caches a texture object and a
+ * TMA descriptor per caller-owned frame (keyed by pointer and geometry); csb_device_free does this implicitly. */
+int  csb_forget_image(csb_ctx *ctx, const void *d_ptr);
 int  csb_memcpy_h2d(csb_ctx *ctx, void *d_dst, const void *h_src, unsigned long long bytes);
 int  csb_memcpy_d2h(csb_ctx *ctx, void *h_dst, const void *d_src, unsigned long long bytes);
 int  csb_upload_image(csb_ctx *ctx, float *d_img, int pitch_floats, const float *h_img, int w, int h);
@@ -149,6 +152,9 @@ int csb_extract_batch_u8(csb_ctx *ctx, int n_frames, const unsigned char *const 
 /* ScaleDown(cuImage &res, cuImage &src, 0.5f) (cuSIFT.h:76, cuSIFT.cu:313-353):
  * dst is (w/2) x (h/2).  Stores are guarded (the reference's are not). */
 int csb_scale_down(csb_ctx *ctx, const float *d_src, int w, int h, int src_pitch, float *d_dst, int dst_pitch);
+/* the same with the caller's variance (cuSIFT.cu:313-338 builds the 5 taps from it; csb_scale_down uses 0.5f) */
+int csb_scale_down_var(csb_ctx *ctx, const float *d_src, int w, int h, int src_pitch, float *d_dst, int dst_pitch,
+                       float variance);
 
 /* SiftData::ConvertSiftToRootSift (cuSIFT.cu:383-395) on n device points. */
 int csb_rootsift(csb_ctx *ctx, void *d_sift, int n);

@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
         vp = C.c_void_p
         L.orc_sizeof_point.restype = C.c_int
         L.orc_scale_down.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp, C.c_int]
+        L.orc_scale_down_var.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_float]
         L.orc_next_init_blur.argtypes = [C.c_double]
         L.orc_next_init_blur.restype = C.c_double
         L.orc_laplace_weights.argtypes = [C.c_double, fp]
@@ -100,11 +101,11 @@ def _i(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
 
-def scale_down(img: np.ndarray) -> np.ndarray:
+def scale_down(img: np.ndarray, variance: float = 0.5) -> np.ndarray:
     img = np.ascontiguousarray(img, np.float32)
     h, w = img.shape
     out = np.zeros((h // 2, w // 2), np.float32)
-    lib().orc_scale_down(_f(img), w, h, w, _f(out), w // 2)
+    lib().orc_scale_down_var(_f(img), w, h, w, _f(out), w // 2, variance)
     return out
 
 

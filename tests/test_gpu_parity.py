@@ -39,6 +39,8 @@ def synth1080():
 def test_scale_down_bit_exact(gpu_ctx, frames, shape, seed):
     img = frames[0] if seed is None else csb.synth(shape[1], shape[0], seed)
     assert np.array_equal(gpu_ctx.scale_down(img), O.scale_down(img))
+    for variance in (0.3, 1.0, 2.5):                          # ScaleDown(res, src, variance) takes any variance (cuSIFT.cu:313-338)
+        assert np.array_equal(gpu_ctx.scale_down(img, variance), O.scale_down(img, variance)), variance
 
 
 @pytest.mark.parametrize("case", ["gray1", "synth_500x300", "synth_odd_173x131", "initblur"])
