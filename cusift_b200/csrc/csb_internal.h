@@ -73,9 +73,6 @@ struct OctaveTexSet {
 };
 
 // ---- k_pyramid (kernels_pyramid.cu): blur + DoG (+ downsample) of any set of octaves in ONE launch ----
-struct DogWeights2 {
-  float2 k[CSB_NUM_LEVELS][5];     // each tap duplicated {k, k} (operands of the packed f32x2 instructions)
-};
 struct DownK {
   float k0, k1, k2;                // ScaleDown taps (cuSIFT.cu:320-338): k0 = outer, k1 = inner, k2 = centre
 };
@@ -91,7 +88,7 @@ struct PyramidParams {
   int n_oct;
   DownK dk;
   PyramidOctave oct[CSB_MAX_OCTAVES];
-  DogWeights2 W[CSB_MAX_OCTAVES];  // index = oct[] index (the weights depend on the octave's initBlur)
+  DogWeights W[CSB_MAX_OCTAVES];   // index = oct[] index (the weights depend on the octave's initBlur)
 };
 // one 2-D TMA descriptor per octave over its BASE image (w x h floats, row pitch in bytes): box = 248 x 4
 struct alignas(64) PyramidMaps {

@@ -229,6 +229,18 @@ void ReadMATLABRt(double *Rt_relative, const char *filename) {
 void AddSiftData(SiftData &data, SiftPoint *h_data, int numPts) {
   if (numPts <= 0 || h_data == NULL) return;
   const int total = data.numPts + numPts;
+  if (data.h_data == NULL && data.d_data == NULL) {
+    // A default-constructed SiftData owns no storage (cuSIFT.h:57: host = dev = false), and the InitSiftData call the
+    // reference's reader used to make is commented out (debug.cpp:128) - at the reference's HEAD its own
+    // test/test.cpp:26-40 therefore reads nothing and indexes an empty match vector.  Deviation:
+    // give such an object host + device storage here, so that the reference's tests run as written.
+    int cap = data.maxPts > 0 ? data.maxPts : 1024;
+    while (cap < total) cap *= 2;
+    data.numPts = 0;
+    data.h_data = host_points((size_t)cap);
+    safeCall(cudaMalloc((void **)&data.d_data, sizeof(SiftPoint) * (size_t)cap));
+    data.maxPts = cap;
+  }
   if (data.maxPts < total) {
     int cap = data.maxPts > 0 ? 2 * data.maxPts : 1024;
     while (cap < total) cap *= 2;

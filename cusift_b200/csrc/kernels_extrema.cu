@@ -37,10 +37,13 @@
 namespace {
 
 constexpr int XT_COLS = 30;          // output columns per warp
-constexpr int XT_WARPS = 4;
-constexpr int XT_TW = XT_COLS * XT_WARPS;   // 120 output columns per CTA
+#ifndef K2_WARPS
+#define K2_WARPS 4          // scanning warps per CTA (4: 120-column tiles, 512-byte TMA rows; 8: 240 columns, 1 KB rows)
+#endif
+constexpr int XT_WARPS = K2_WARPS;
+constexpr int XT_TW = XT_COLS * XT_WARPS;   // output columns per CTA
 #ifndef K2_MINB
-#define K2_MINB 6           // resident CTAs per SM (35 KB of shared memory each)
+#define K2_MINB (K2_WARPS == 4 ? 6 : 3)     // resident CTAs per SM (35 KB / 67 KB of shared memory each)
 #endif
 #ifndef K2_WAVES
 #define K2_WAVES 1          // CTAs launched per resident slot
@@ -53,7 +56,8 @@ constexpr int ST_ROWS = 3;           // source rows per pipeline stage (one turn
 #define K2_STAGES 3
 #endif
 constexpr int ST_N = K2_STAGES;      // stages: 9 rows x 7 planes of loads in flight per CTA
-constexpr int ST_COLS = 128;         // columns staged per row: the 120 output columns + halo, 512 bytes
+constexpr int ST_COLS = (XT_TW + 8 + 31) / 32 * 32;   // columns staged per row: output columns + halo, rounded so that a stage
+                                                      // is a multiple of 128 bytes (TMA destination alignment): 128 or 256
 constexpr uint32_t ST_BYTES = ST_ROWS * NPL * ST_COLS * sizeof(float);
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -192,10 +196,11 @@ __global__ void __launch_bounds__((XT_WARPS + 1) * 32, K2_MINB) k_find_points(co
   // they only ever feed border pixels, which cannot be extrema.
   // With loads issued by the scanning warps themselves the kernel ran at 3.2 TB/s although the same access
   // pattern alone reaches about 5 TB/s: the memory pipeline only moved when the compute warps got round to it.
-  __shared__ __align__(128) float s_tile[ST_N][ST_ROWS][NPL][ST_COLS];
+  extern __shared__ __align__(128) unsigned char xt_smem[];   // the ring: ST_N stages of ST_BYTES (dynamic: > 48 KB for wide tiles)
+  float(*s_tile)[ST_ROWS][NPL][ST_COLS] = reinterpret_cast<float(*)[ST_ROWS][NPL][ST_COLS]>(xt_smem);
   __shared__ __align__(8) uint64_t s_full[ST_N], s_empty[ST_N];
   __shared__ unsigned int s_cnt;
-  __shared__ unsigned short s_list[XT_CAP];   // local column | local row << 7 | scale << 13
+  __shared__ unsigned int s_list[XT_CAP];     // local column | local row << 8 | scale << 14
 
   // which octave does this CTA belong to?  (octave 0 owns the first, and by far the most, CTAs)
   int oi = 0;
@@ -275,12 +280,12 @@ __global__ void __launch_bounds__((XT_WARPS + 1) * 32, K2_MINB) k_find_points(co
     const unsigned int big = hmax3(hmax3(c3[1][M], c3[2][M], c3[3][M]), c3[4][M], c3[5][M]);
     const bool rowOK = colOK && (y >= y0) && (y >= 1) && (y <= h - 2) && (y < y0 + rows);
     if (rowOK && (eq & ge_pm(big, tp))) {                    // rare
-      const unsigned int loc = (unsigned int)(x - bx * XT_TW) | ((unsigned int)(y - y0) << 7);
+      const unsigned int loc = (unsigned int)(x - bx * XT_TW) | ((unsigned int)(y - y0) << 8);
 #pragma unroll
       for (int sc = 0; sc < CSB_NUM_SCALES; sc++)
         if (flag_pm(c3[sc + 1][M], mx[sc], tp)) {
           const unsigned int slot = atomicAdd(&s_cnt, 1u);
-          if (slot < (unsigned int)cap) s_list[slot] = (unsigned short)(loc | ((unsigned int)sc << 13));
+          if (slot < (unsigned int)cap) s_list[slot] = loc | ((unsigned int)sc << 14);
         }
     }
   };
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__((XT_WARPS + 1) * 32, K2_MINB) k_find_points(co
           ey = y0 + (int)((i / CSB_NUM_SCALES) / (unsigned int)tile_w);
         } else {
           const unsigned int en = s_list[i];
-          ex = bx * XT_TW + (int)(en & 0x7fu), ey = y0 + (int)((en >> 7) & 0x3fu), es = (int)(en >> 13);
+          ex = bx * XT_TW + (int)(en & 0xffu), ey = y0 + (int)((en >> 8) & 0x3fu), es = (int)(en >> 14);
         }
         const bool inner = ex >= 1 && ex <= w - 2 && ey >= 1 && ey <= h - 2;
         if (inner) emit = verify_refine(dog, plane, drow, P, ex, ey, es, r);
@@ -376,5 +381,11 @@ void launch_find_points(const ExtremaParams &ep, const ExtremaMaps &maps, int n_
     cap = atoi(e);
     if (cap < 1 || cap > XT_CAP) cap = XT_CAP;
   }
-  k_find_points<<<n_ctas, (XT_WARPS + 1) * 32, 0, st>>>(ep, maps, d_stage, d_counter, max_pts, cap);
+  constexpr size_t ring_bytes = (size_t)ST_N * ST_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_find_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+    attr_set = true;
+  }
+  k_find_points<<<n_ctas, (XT_WARPS + 1) * 32, ring_bytes, st>>>(ep, maps, d_stage, d_counter, max_pts, cap);
 }

@@ -12,9 +12,8 @@
 // Kernels in this file:
 //   k_pyramid      the production kernel: ONE launch covers any set of octaves (a CTA looks its octave and
 //                  tile up in a table).  The octave base reaches shared memory through 2-D tiled TMA loads
-//                  (cp.async.bulk.tensor.2d -> UTMALDG, completion on mbarriers) into a 3-slot ring of
-//                  4-row chunks that runs ahead of the arithmetic; out-of-image parts of a box are
-//                  zero-filled by the TMA unit and never read (clamp-to-edge is applied to the indices).
+//                  (cp.async.bulk.tensor.2d -> UTMALDG, completion on mbarriers); the four warps of a CTA then
+//                  run vertical pass, shared-memory exchange and horizontal pass + DoG autonomously.
 //   k_down_chain   octave bases k+1 .. k+3 from base k in one launch (tile-local recomputation of the
 //                  intermediate levels), so that all coarse octaves can then go through ONE k_pyramid launch.
 //   k_blur_dog     scalar fallback (source image not 16-byte aligned / pitch not a multiple of 4 floats:
@@ -203,12 +202,17 @@ constexpr int PY_SLOTS = 3;                     // ring of 4-row chunks
 constexpr uint32_t PY_CHUNK_BYTES = PY_SRC_COLS * BATCH * sizeof(float);   // 3968 = 31 * 128
 constexpr size_t PY_SMEM = sizeof(float2) * BATCH * NLEV * V2_ROW + PY_SLOTS * PY_CHUNK_BYTES + 64;
 
-__device__ __forceinline__ float2 tap9x2(const float2 (&k)[5], float2 c, float2 s1, float2 s2, float2 s3, float2 s4) {
-  float2 t = __fmul2_rn(k[3], s1);
-  t = __ffma2_rn(c, k[4], t);
-  t = __ffma2_rn(k[2], s2, t);
-  t = __ffma2_rn(k[1], s3, t);
-  t = __ffma2_rn(k[0], s4, t);
+// The taps are SCALARS: written as {k, k} they compile to the scalar-broadcast operand form of the packed instructions
+// (FFMA2 Rd, Ra.F32x2, URb.F32, Rc.F32x2), i.e. all 40 taps live in uniform registers and every packed operation reads
+// two register pairs + one uniform register.  (Taps passed as pre-duplicated float2 pairs - the first version - occupy
+// 80 uniform registers, more than there are, so half of them ended up in ordinary registers: a packed operation with
+// three register-pair sources reads three registers from one bank and issues every 3 cycles instead of every 2.)
+__device__ __forceinline__ float2 tap9x2(const float (&k)[5], float2 c, float2 s1, float2 s2, float2 s3, float2 s4) {
+  float2 t = __fmul2_rn(make_float2(k[3], k[3]), s1);
+  t = __ffma2_rn(c, make_float2(k[4], k[4]), t);
+  t = __ffma2_rn(make_float2(k[2], k[2]), s2, t);
+  t = __ffma2_rn(make_float2(k[1], k[1]), s3, t);
+  t = __ffma2_rn(make_float2(k[0], k[0]), s4, t);
   return t;
 }
 __device__ __forceinline__ float2 down_h2(float2 c0, float2 c1, float2 c2, float2 c3, float2 c4, float2 k0, float2 k1,
@@ -233,7 +237,7 @@ template <int PH, bool kDown>
 __device__ __forceinline__ void py_vertical(float2 (&P)[12], float2 &last, const float *__restrict__ chunk,
                                             const float *__restrict__ row0, float *chunk_w, float *row0_w, int r0, int h,
                                             int colA, int colB, bool patchA, bool patchB, int pos, bool hasOut,
-                                            const DogWeights2 &W, float2 *__restrict__ V, int vslot) {
+                                            const DogWeights &W, float2 *__restrict__ V, int vslot) {
 #define PYWIN(i) P[((i) + 4 * PH) % 12]
 #pragma unroll
   for (int b = 0; b < BATCH; b++) {
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(NT, K1_MINB) k_pyramid(const __grid_constant__
       if ((int)blockIdx.x >= P.oct[i].cta_begin) oi = i;
   }
   const PyramidOctave &O = P.oct[oi];
-  const DogWeights2 &W = P.W[oi];
+  const DogWeights &W = P.W[oi];
   const int w = O.w, h = O.h, rows = O.rows;
   const int local = (int)blockIdx.x - O.cta_begin;
   const int bx = local % O.tiles_x, by = local / O.tiles_x;
@@ -614,10 +618,7 @@ bool pyramid_tma_ok(const float *base, int pitch) {
   return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && (pitch & 3) == 0;
 }
 
-void pyramid_set_weights(PyramidParams *pp, int idx, const DogWeights &wts) {
-  for (int s = 0; s < NLEV; s++)
-    for (int j = 0; j < 5; j++) pp->W[idx].k[s][j] = make_float2(wts.k[s][j], wts.k[s][j]);
-}
+void pyramid_set_weights(PyramidParams *pp, int idx, const DogWeights &wts) { pp->W[idx] = wts; }
 
 // Rows per CTA for every octave of the launch (multiple of 4, <= 16): as large as possible while the whole
 // launch still fits in one wave of K1_MINB CTAs per SM, so that a lone frame fills the GPU and a CTA's

@@ -157,7 +157,10 @@ def test_extract_vs_reference(gpu_ctx, frames, synth1080, workdir, case):
     assert r["pos_exact"] == r["matched"], r                  # bit-exact positions and scales
     assert r["sharp_max"] == 0.0 and r["edge_rel_max"] == 0.0 and r["subs_equal"], r
     assert r["ori_max_deg"] < PU.ORI_TOL_DEG, r
-    assert r["desc_within_tol"] >= 0.99 and r["desc_max"] < 1e-3, r
+    # the reference's descriptors vary run to run (float atomics): >= 99 % within 1e-4; the maximum over ~95 k RootSIFT
+    # descriptors (sqrt amplifies differences in near-zero bins) reaches 1e-3 in some runs of the reference itself -
+    # test_descriptor_error_is_within_the_reference_own_spread measures that spread
+    assert r["desc_within_tol"] >= 0.99 and r["desc_max"] < (2e-3 if root else 1e-3), r
     assert PU.per_octave_counts(ours) == PU.per_octave_counts(ref)
 
 
