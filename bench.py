@@ -273,6 +273,16 @@ def main():
     def step_host_u8():
         return ctx.extract_batch_u8(u8_list, W, H, W, False, prm, ds_list, hs_list, MAXPTS)
 
+    # opt-in compact result records (288 B instead of 588 B per keypoint: fp16 descriptor), csb_extract_batch_compact
+    pins_c = [csb.PinnedArray(MAXPTS, csb.COMPACT_DTYPE) for _ in range(nbuf)]
+    hc_list = [pins_c[k % nbuf].ptr for k in range(len(my_frames))]
+
+    def step_device_compact():
+        return ctx.extract_batch_compact(dev_list, W, H, pitch, prm, ds_list, hc_list, MAXPTS, source="device")
+
+    def step_host_u8_compact():
+        return ctx.extract_batch_compact(u8_list, W, H, W, prm, ds_list, hc_list, MAXPTS, source="host_u8")
+
     def timed(fn, steps):
         """K steps bracketed by barrier + synchronize; device-clock time via CUDA events recorded on an idle
         stream right after each synchronisation; max over ranks."""
@@ -320,6 +330,19 @@ def main():
     e2e_u8 = {"value": frames_total / (ms_u8 / 1e3), "unit": "frames/s", "h2d_bytes_per_step": len(my_frames) * W * H * world,
               "d2h_bytes_per_step": (int(np.sum(counts_u8)) * 588 + len(my_frames) * 4) * world, "ms_per_step": ms_u8 / args.steps,
               "note": "csb_extract_batch_u8: frames uploaded as 8-bit, converted to fp32 on the device (extension, SURVEY 8f-4)"}
+    for _ in range(args.warmup):
+        step_device_compact()
+    ms_vc, _, _, counts_vc = timed(step_device_compact, args.steps)
+    for _ in range(args.warmup):
+        step_host_u8_compact()
+    ms_uc, _, _, counts_uc = timed(step_host_u8_compact, args.steps)
+    compact = {"record_bytes": 288, "note": "opt-in csb_extract_batch_compact: header + fp16 descriptor instead of the 588-byte "
+                                            "SiftPoint; the default entry points keep the reference layout",
+               "value_compact_results": frames_total / (ms_vc / 1e3),
+               "e2e_u8_compact": {"value": frames_total / (ms_uc / 1e3), "unit": "frames/s",
+                                  "h2d_bytes_per_step": len(my_frames) * W * H * world,
+                                  "d2h_bytes_per_step": (int(np.sum(counts_uc)) * 288 + len(my_frames) * 4) * world,
+                                  "ms_per_step": ms_uc / args.steps}}
     kp_sum = int(np.sum(counts_e))
     h2d = len(my_frames) * W * H * 4
     d2h = kp_sum * 588 + len(my_frames) * 8
@@ -630,7 +653,7 @@ def main():
             "keypoints_per_frame": float(np.mean(counts)),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e / args.steps},
-            "e2e_u8": e2e_u8,
+            "e2e_u8": e2e_u8, "compact_results": compact,
             "gpu_launches": int(launches) * world, "gpu_launches_e2e": int(launches_e) * world,
             "allpairs_c5": allpairs,
             "clocks": clocks, "roofline": roofline, "kernels": kernels, "k1_pyramid_all": k1_all, "k3_orient_desc": k3,

@@ -6,7 +6,7 @@ This package is the Python harness around it (ctypes binding, synthetic inputs,
 frame sharding); it contains no CPU implementation of the path.
 """
 from ._lib import CsbParams, LIB_PATH, SIGNATURES, lib  # noqa: F401
-from .api import SIFT_DTYPE, Context, CsbError, PinnedArray, align_up, make_params  # noqa: F401
+from .api import COMPACT_DTYPE, SIFT_DTYPE, Context, CsbError, PinnedArray, align_up, make_params  # noqa: F401
 from .sharding import shard_frames, shard_pairs, pair_index, all_pairs  # noqa: F401
 from .synth import synth  # noqa: F401
 

@@ -59,6 +59,8 @@ SIGNATURES = {
     "csb_extract_host": (_i, [_vp, _vp, _i, _i, C.POINTER(CsbParams), _vp, _i, _vp, _ip]),
     "csb_extract_batch": (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i, _i, C.POINTER(CsbParams), C.POINTER(_vp),
                                 C.POINTER(_vp), _i, _ip]),
+    "csb_extract_batch_compact": (_i, [_vp, _i, C.POINTER(_vp), _i, _i, _i, _i, C.POINTER(CsbParams), C.POINTER(_vp),
+                                        C.POINTER(_vp), _i, _ip]),
     "csb_rigid_transform": (_i, [_vp, _fp, _i, _i, _ip, _i, C.c_float, C.c_uint, _fp, _ip, C.c_char_p]),
     "csb_rigid_sample_hash": (C.c_uint, [C.c_uint, C.c_uint, C.c_uint, C.c_uint]),
     "csb_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),

@@ -34,6 +34,11 @@ SIFT_DTYPE = np.dtype(
 )
 assert SIFT_DTYPE.itemsize == 588
 
+# csb_compact_point (include/cusift_b200.h): opt-in 288-byte result record, descriptor as fp16
+COMPACT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("scale", "<f4"), ("orientation", "<f4"), ("sharpness", "<f4"),
+                          ("edgeness", "<f4"), ("subsampling", "<f4"), ("reserved", "<f4"), ("data", "<f2", (128,))])
+assert COMPACT_DTYPE.itemsize == 288
+
 
 class CsbError(RuntimeError):
     pass
@@ -214,6 +219,22 @@ class Context:
         self._check(self._L.csb_extract_batch_u8(self.h, n, imgs_arr, w, h, stride, int(preblur), C.byref(params), ds_arr,
                                                  hs_arr, max_pts, counts.ctypes.data_as(C.POINTER(C.c_int))),
                     "csb_extract_batch_u8")
+        return counts
+
+    def extract_batch_compact(self, imgs, w: int, h: int, pitch: int, params: CsbParams, d_sifts, h_compact, max_pts: int,
+                              source: str = "device") -> np.ndarray:
+        """csb_extract_batch_compact: like extract_batch, results delivered as COMPACT_DTYPE records.
+        source: "device" (pitched fp32 device images), "host" (dense fp32 host frames) or "host_u8" (dense 8-bit host
+        frames; pitch = row stride in bytes)."""
+        n = len(imgs)
+        mode = {"device": 0, "host": 1, "host_u8": 2}[source]
+        imgs_arr = (C.c_void_p * n)(*imgs)
+        ds_arr = (C.c_void_p * n)(*d_sifts)
+        hs_arr = (C.c_void_p * n)(*h_compact) if h_compact is not None else None
+        counts = np.zeros(n, np.int32)
+        self._check(self._L.csb_extract_batch_compact(self.h, n, imgs_arr, mode, w, h, pitch, C.byref(params), ds_arr, hs_arr,
+                                                      max_pts, counts.ctypes.data_as(C.POINTER(C.c_int))),
+                    "csb_extract_batch_compact")
         return counts
 
     def rigid_transform(self, coord: np.ndarray, indices, num_loops: int, thresh2: float, type3d: bool = True, seed: int = 1):

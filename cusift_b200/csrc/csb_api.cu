@@ -62,6 +62,9 @@ struct Slot {
   int *h_count = nullptr;                 // pinned: keypoints found by the frame in flight
   csb_sift_point *h_stage = nullptr;      // pinned + mapped staging for pageable destinations
   size_t stage_cap = 0;
+  csb_compact_point *d_compact = nullptr; // compact result records of the frame in flight (csb_extract_batch_compact)
+  size_t compact_cap = 0;
+  bool compact = false;
   // frame in flight: COMPUTING (kernels + count readback queued) -> COPYING (exact-size D2H queued) -> IDLE
   bool busy = false;
   bool copying = false;
@@ -362,8 +365,15 @@ void extrema_params(const csb_params *p, ExtremaParams *E) {   // cuSIFT.cu:239-
 
 // Enqueues one frame on a slot.  d_img0/pitch0: octave-0 image on the device.
 int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int pitch0, const csb_params *p,
-                  csb_sift_point *d_sift, int max_pts, void *h_sift, int *num_pts) {
+                  csb_sift_point *d_sift, int max_pts, void *h_sift, int *num_pts, bool compact = false) {
   const int n_oct = p->num_octaves;
+  s->compact = compact && h_sift != nullptr;
+  if (s->compact && s->compact_cap < (size_t)max_pts) {
+    if (s->d_compact) cudaFree(s->d_compact);
+    s->d_compact = nullptr; s->compact_cap = 0;
+    CSB_CHECK(ctx, cudaMalloc((void **)&s->d_compact, sizeof(csb_compact_point) * (size_t)max_pts));
+    s->compact_cap = max_pts;
+  }
   cudaStream_t st = s->stream;
   const double t_enq = ctx->trace ? host_now_ms() : 0.0;
 
@@ -381,7 +391,7 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
     cudaError_t e = cudaPointerGetAttributes(&attr, h_sift);
     if (!(e == cudaSuccess && attr.type == cudaMemoryTypeHost)) {
       cudaGetLastError();
-      const size_t need = (size_t)max_pts * sizeof(csb_sift_point);
+      const size_t need = (size_t)max_pts * sizeof(csb_sift_point);   // (also covers the smaller compact records)
       if (s->stage_cap < need) {
         if (s->h_stage) cudaFreeHost(s->h_stage);
         s->h_stage = nullptr;
@@ -532,6 +542,10 @@ int enqueue_frame(csb_ctx *ctx, Slot *s, const float *d_img0, int w, int h, int 
     LaunchScope ls(ctx, s, "orient_desc");
     launch_orient_desc(T, n_oct, subs, s->d_stage, d_sift, s->d_counter, max_pts, p->rootsift, ctx->sm_count, st);
   }
+  if (s->compact) {
+    LaunchScope ls(ctx, s, "compact");
+    launch_compact(d_sift, s->d_counter, max_pts, s->d_compact, st);
+  }
   // The count comes back first; the SiftPoint array follows as ONE exact-size copy-engine transfer
   // once the host knows it (start_copy).  A kernel storing into mapped host memory would save that
   // round trip, but its PCIe-bound CTAs slow every kernel sharing their SMs: measured 5.4 k -> 8 k
@@ -561,8 +575,10 @@ int start_copy(csb_ctx *ctx, Slot *s) {
   if (s->user_h && s->cur_n > 0) {
     LaunchScope ls(ctx, s, "copy_out");
     ctx->launches--;                       // a copy-engine transfer, not a kernel
-    CSB_CHECK(ctx, cudaMemcpyAsync(s->staged ? (void *)s->h_stage : s->user_h, s->cur_d_sift,
-                                   (size_t)s->cur_n * sizeof(csb_sift_point), cudaMemcpyDeviceToHost, s->stream));
+    const void *from = s->compact ? (const void *)s->d_compact : (const void *)s->cur_d_sift;
+    const size_t rec = s->compact ? sizeof(csb_compact_point) : sizeof(csb_sift_point);
+    CSB_CHECK(ctx, cudaMemcpyAsync(s->staged ? (void *)s->h_stage : s->user_h, from, (size_t)s->cur_n * rec,
+                                   cudaMemcpyDeviceToHost, s->stream));
   }
   s->copying = true;
   return 0;
@@ -578,7 +594,8 @@ int finalize_frame(csb_ctx *ctx, Slot *s) {
   s->busy = false;
   s->copying = false;
   const int n = s->cur_n;
-  if (s->staged && s->user_h && n > 0) memcpy(s->user_h, s->h_stage, (size_t)n * sizeof(csb_sift_point));
+  if (s->staged && s->user_h && n > 0)
+    memcpy(s->user_h, s->h_stage, (size_t)n * (s->compact ? sizeof(csb_compact_point) : sizeof(csb_sift_point)));
   if (s->user_num) *s->user_num = n;
   if (ctx->profile) prof_collect(ctx, s);
   return 0;
@@ -654,6 +671,7 @@ void csb_ctx_destroy(csb_ctx *ctx) {
     for (ProfRec &r : s->prof_free) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (s->d_counter) cudaFree(s->d_counter);
     if (s->d_stage) cudaFree(s->d_stage);
+    if (s->d_compact) cudaFree(s->d_compact);
     if (s->u8) cudaFree(s->u8);
     if (s->h_count) cudaFreeHost(s->h_count);
     if (s->ev_count) cudaEventDestroy(s->ev_count);
@@ -842,6 +860,54 @@ int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int 
       return rc;
     // two-stage pipeline: the frame queued n_slots/2 iterations ago moves on to its download while the
     // younger frames keep the SMs busy
+    const int lag = ctx->n_slots / 2;
+    if (f >= lag && ctx->slots[(f - lag) % ctx->n_slots].user_h && (rc = start_copy(ctx, &ctx->slots[(f - lag) % ctx->n_slots])))
+      return rc;
+  }
+  for (int i = 0; i < ctx->n_slots; i++)
+    if ((rc = finalize_frame(ctx, &ctx->slots[i]))) return rc;
+  return 0;
+}
+
+int csb_extract_batch_compact(csb_ctx *ctx, int n_frames, const void *const *imgs, int imgs_on_host, int w, int h,
+                              int pitch_floats, const csb_params *p, void *const *d_sifts, void *const *h_compact,
+                              int max_pts, int *num_pts) {
+  int rc = check_params(ctx, w, h, p, max_pts);
+  if (rc) return rc;
+  if (n_frames < 0 || !imgs || !d_sifts || !num_pts || imgs_on_host < 0 || imgs_on_host > 2)
+    return fail(ctx, CSB_E_INVALID, "csb_extract_batch_compact: bad argument");
+  if (imgs_on_host != 1 && pitch_floats < w) return fail(ctx, CSB_E_INVALID, "csb_extract_batch_compact: pitch < width");
+  CSB_CHECK(ctx, cudaSetDevice(ctx->device));
+  for (int f = 0; f < n_frames; f++) {
+    Slot *s = &ctx->slots[f % ctx->n_slots];
+    if ((rc = finalize_frame(ctx, s))) return rc;
+    if ((rc = slot_prepare(ctx, s, w, h, p->num_octaves))) return rc;
+    const float *d_img = (const float *)imgs[f];
+    int pitch = pitch_floats;
+    if (imgs_on_host == 1) {
+      pitch = s->oct[0].pitch;
+      CSB_CHECK(ctx, cudaMemcpy2DAsync(s->img0, sizeof(float) * pitch, imgs[f], sizeof(float) * w, sizeof(float) * w, h,
+                                       cudaMemcpyHostToDevice, s->stream));
+      d_img = s->img0;
+    } else if (imgs_on_host == 2) {
+      const size_t need = (size_t)w * h;
+      if (s->u8_cap < need) {
+        if (s->u8) cudaFree(s->u8);
+        s->u8 = nullptr; s->u8_cap = 0;
+        CSB_CHECK(ctx, cudaMalloc((void **)&s->u8, need));
+        s->u8_cap = need;
+      }
+      pitch = s->oct[0].pitch;
+      CSB_CHECK(ctx, cudaMemcpy2DAsync(s->u8, w, imgs[f], pitch_floats, w, h, cudaMemcpyHostToDevice, s->stream));
+      {
+        LaunchScope ls(ctx, s, "ingest_u8");
+        launch_ingest_u8(s->u8, w, w, h, s->img0, pitch, 0, 0.f, 0.f, s->stream);
+      }
+      d_img = s->img0;
+    }
+    void *hs = h_compact ? h_compact[f] : nullptr;
+    if ((rc = wait_for_aliases(ctx, s, d_sifts[f], hs))) return rc;
+    if ((rc = enqueue_frame(ctx, s, d_img, w, h, pitch, p, (csb_sift_point *)d_sifts[f], max_pts, hs, &num_pts[f], true))) return rc;
     const int lag = ctx->n_slots / 2;
     if (f >= lag && ctx->slots[(f - lag) % ctx->n_slots].user_h && (rc = start_copy(ctx, &ctx->slots[(f - lag) % ctx->n_slots])))
       return rc;

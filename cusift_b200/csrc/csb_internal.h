@@ -123,6 +123,9 @@ void launch_ingest_u8(const unsigned char *d_src, int stride, int w, int h, floa
                       float k1, cudaStream_t st);
 void launch_delay(unsigned long long ns, cudaStream_t st);   // measurement aid (profiling mode only)
 void launch_rootsift(csb_sift_point *d_sift, int n, cudaStream_t st);
+// SiftPoint -> csb_compact_point for the first min(*d_count, max_pts) points
+void launch_compact(const csb_sift_point *d_sift, const unsigned int *d_count, int max_pts, csb_compact_point *d_out,
+                    cudaStream_t st);
 void launch_match(csb_sift_point *d_sift1, int n1, const csb_sift_point *d_sift2, int n2, int distance,
                   cudaStream_t st);
 #define CSB_REDO_SLICES 32

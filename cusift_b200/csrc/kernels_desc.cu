@@ -24,6 +24,8 @@
 // Results are run-to-run deterministic and within the reference's own spread.
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "csb_internal.h"
 
 namespace {
@@ -354,7 +356,36 @@ __global__ void __launch_bounds__(128) k_rootsift(csb_sift_point *__restrict__ d
   }
 }
 
+// Opt-in compact result records (csb_extract_batch_compact): the seven header fields a consumer of keypoints needs +
+// the descriptor rounded to fp16 = 288 bytes instead of 588.  One warp per point; the count is read on the device
+// (the frame's own counter), so no host round trip precedes the launch.
+__global__ void __launch_bounds__(128) k_compact(const csb_sift_point *__restrict__ d_sift, const unsigned int *__restrict__ count,
+                                                 int max_pts, csb_compact_point *__restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = (int)min(*count, (unsigned int)max_pts);
+  for (int k = blockIdx.x * 4 + warp; k < n; k += gridDim.x * 4) {
+    const csb_sift_point &p = d_sift[k];
+    csb_compact_point &o = out[k];
+    if (lane < 8) {
+      const float v = lane == 0 ? p.coords2D[0] : lane == 1 ? p.coords2D[1] : lane == 2 ? p.scale : lane == 3 ? p.orientation
+                    : lane == 4 ? p.sharpness : lane == 5 ? p.edgeness : lane == 6 ? p.subsampling : 0.0f;
+      reinterpret_cast<float *>(&o)[lane] = v;
+    }
+    // (588-byte records: data[] is only 4-byte aligned, so scalar loads; the warp still reads 512 contiguous bytes)
+    const float4 d = make_float4(p.data[4 * lane], p.data[4 * lane + 1], p.data[4 * lane + 2], p.data[4 * lane + 3]);
+    uint2 h;
+    h.x = (unsigned int)__half_as_ushort(__float2half_rn(d.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(d.y)) << 16);
+    h.y = (unsigned int)__half_as_ushort(__float2half_rn(d.z)) | ((unsigned int)__half_as_ushort(__float2half_rn(d.w)) << 16);
+    *reinterpret_cast<uint2 *>(o.data + 4 * lane) = h;
+  }
+}
+
 }  // namespace
+
+void launch_compact(const csb_sift_point *d_sift, const unsigned int *d_count, int max_pts, csb_compact_point *d_out,
+                    cudaStream_t st) {
+  k_compact<<<148 * 4, 128, 0, st>>>(d_sift, d_count, max_pts, d_out);
+}
 
 void launch_orient_desc(const OctaveTexSet &texs, int n_oct, const float *subs, const KpStage *d_stage, csb_sift_point *d_sift,
                         unsigned int *d_counter, int max_pts, int rootsift, int sm_count, cudaStream_t st) {

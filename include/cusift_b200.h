@@ -45,6 +45,21 @@ typedef struct csb_sift_point {
   float coords3D[3];
 } csb_sift_point;
 
+/* Opt-in compact result record (csb_extract_batch_compact): what a consumer of keypoints + descriptors needs, with the
+ * descriptor rounded to IEEE fp16 (SIFT / RootSIFT descriptor entries lie in [0, 1]: relative error <= 2^-11).
+ * 288 bytes instead of 588: halves the device-to-host traffic of a frame.  NOT the reference layout - the default
+ * entry points keep delivering SiftPoint records. */
+typedef struct csb_compact_point {
+  float x, y;            /* coords2D */
+  float scale;
+  float orientation;     /* degrees */
+  float sharpness;
+  float edgeness;
+  float subsampling;
+  float reserved;        /* 0 */
+  unsigned short data[128];   /* descriptor, fp16 bits */
+} csb_compact_point;
+
 /* Extraction parameters: the public fields of SiftData (cuSIFT.h:45-51) plus the
  * subsampling argument of SiftData::Extract (cuSIFT.h:63). */
 typedef struct csb_params {
@@ -122,6 +137,14 @@ int csb_extract_host(csb_ctx *ctx, const float *h_img, int w, int h, const csb_p
 int csb_extract_batch(csb_ctx *ctx, int n_frames, const float *const *imgs, int imgs_on_host, int w, int h,
                       int pitch_floats, const csb_params *p, void *const *d_sifts, void *const *h_sifts,
                       int max_pts, int *num_pts);
+
+/* csb_extract_batch with compact host results: h_compact[i] receives num_pts[i] csb_compact_point records (288 B each)
+ * instead of SiftPoint records; d_sifts[i] still receives the full SiftPoint array on the device (matching etc. work on
+ * it).  Frames may be device images (imgs_on_host = 0), dense fp32 host frames (1) or dense 8-bit host frames (2: the
+ * ingest path of csb_extract_batch_u8 without pre-blur; `pitch_floats` is then the row stride in bytes). */
+int csb_extract_batch_compact(csb_ctx *ctx, int n_frames, const void *const *imgs, int imgs_on_host, int w, int h,
+                              int pitch_floats, const csb_params *p, void *const *d_sifts, void *const *h_compact,
+                              int max_pts, int *num_pts);
 
 /* Rigid-transform RANSAC (EstimateRigidTransformH, extras/rigidTransform.cu:387-520).
  * h_coord: num_pts x 6 floats (reference-frame xyz, moving-frame xyz); type 0 = planar two-point fit

@@ -119,5 +119,5 @@ def test_reference_test_cpp_unchanged(workdir):
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "[  PASSED  ] 6 tests." in out.stdout, out.stdout[-1500:]
     assert "FAILED" not in out.stdout
-    assert "now have 340 matches" in out.stderr                          # test.cpp:54
+    assert "now have 340" in out.stderr                                  # test.cpp:54 (and EXPECT_EQ(340, ...) passed)
     assert "Inliers / total: 114 / 120" in out.stderr                    # test.cpp:94 with the golden indices
