@@ -46,6 +46,7 @@
 // and csb_match / the all-pairs path route the call to the exact fp32 kernel, so arbitrary SiftPoint.data still gets
 // the reference's exact result.
 #include <cuda_fp16.h>
+#include <cuda_pipeline.h>
 
 #include "csb_internal.h"
 
@@ -456,9 +457,14 @@ __global__ void __launch_bounds__(128) k_rescore(csb_sift_point *__restrict__ s1
       if (r < r0 || r >= r0 + RS_ROWS) continue;
       const int c = __shfl_sync(0xffffffffu, ci, src);
       const float *pb = s2[c].data;
+      // asynchronous global -> shared copies (LDGSTS): the rows of ALL listed candidates are in flight at once;
+      // with ordinary loads every row waited for the previous row's data (load -> store dependency in a loop of
+      // unknown length), i.e. one L2 round trip per candidate.  4-byte copies: data[] is only 4-byte aligned.
 #pragma unroll
-      for (int j = 0; j < 4; j++) sc[(r - r0) * 129 + lane + 32 * j] = pb[lane + 32 * j];
+      for (int j = 0; j < 4; j++) __pipeline_memcpy_async(&sc[(r - r0) * 129 + lane + 32 * j], &pb[lane + 32 * j], 4);
     }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
     __syncwarp();
     if (ci >= 0 && my_row >= r0 && my_row < r0 + RS_ROWS) {
       const float *pb = sc + (my_row - r0) * 129;

@@ -239,6 +239,20 @@ __device__ __forceinline__ void py_vertical(float2 (&P)[12], float2 &last, const
                                             int colA, int colB, bool patchA, bool patchB, int pos, bool hasOut,
                                             const DogWeights &W, float2 *__restrict__ V, int vslot) {
 #define PYWIN(i) P[((i) + 4 * PH) % 12]
+  if (r0 >= 0 && r0 + BATCH - 1 <= h - 1) {    // CTA-uniform: all four rows inside the image (all but the first / last batch
+                                               // of tiles on the top / bottom border): no row clamping
+#pragma unroll
+    for (int b = 0; b < BATCH; b++) {
+      const float *src = chunk + b * PY_SRC_COLS;
+      const float2 v = make_float2(src[colA], src[colB]);
+      if constexpr (kDown) {
+        if (patchA) chunk_w[b * PY_SRC_COLS + pos] = v.x;
+        if (patchB) chunk_w[b * PY_SRC_COLS + pos + TW] = v.y;
+      }
+      PYWIN(8 + b) = v;
+    }
+    last = PYWIN(8 + BATCH - 1);
+  } else
 #pragma unroll
   for (int b = 0; b < BATCH; b++) {
     const int r = r0 + b;
@@ -418,6 +432,15 @@ __global__ void __launch_bounds__(NT, K1_MINB) k_pyramid(const __grid_constant__
       // three rows carried over, output rows (r0-2)/2 [rows r0-3..r0+1] and r0/2 [rows r0-1..r0+3] follow.
       if (t < TW / 2) {
         float2 hv[BATCH];
+        if (r0 >= 0 && r0 + BATCH - 1 <= h - 1) {
+#pragma unroll
+          for (int b = 0; b < BATCH; b++) {
+            const float *rw = chunk + b * PY_SRC_COLS + 2 * t + 2;
+            hv[b] = down_h2(make_float2(rw[0], rw[TW]), make_float2(rw[1], rw[TW + 1]), make_float2(rw[2], rw[TW + 2]),
+                            make_float2(rw[3], rw[TW + 3]), make_float2(rw[4], rw[TW + 4]), dk0, dk1, dk2);
+          }
+          hlast = hv[BATCH - 1];
+        } else
 #pragma unroll
         for (int b = 0; b < BATCH; b++) {
           const int r = r0 + b;
