@@ -163,6 +163,16 @@ def reference_arm(args, rank: int, world: int):
                                                 "(CUDA library: 1 host thread + the box's GPU 0)"},
                      "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                      "keypoints_per_frame": res["keypoints"]})
+        # the wall-clock number above is dominated by the reference's per-frame cudaMallocPitch / cudaFree / symbol
+        # copies and swings several-fold between boxes; its KERNELS take a stable ~0.5 ms per frame (committed ncu
+        # launch list of this same command on a B200)
+        try:
+            rk = json.loads((ROOT / "profiles" / "r02_reference_kernels.json").read_text())["extract_1080p_frame"]
+            line["reference_device_time"] = {"us_per_frame": rk["device_us_per_frame"], "launches_per_frame": rk["launches_per_frame"],
+                                             "frames_per_s_if_only_kernels": 1e6 / rk["device_us_per_frame"],
+                                             "source": "profiles/r02_reference_kernels.json (ncu launch list, not measured in this run)"}
+        except (OSError, ValueError, KeyError):
+            pass
     else:
         t0 = time.perf_counter()
         n = 0

@@ -119,6 +119,9 @@ struct csb_ctx {
   int *d_rand = nullptr, *d_counts = nullptr;
   size_t coord_cap = 0, loops_cap = 0;
   int *h_counts = nullptr;
+  // rigid-transform scratch (grow-only): coords | indices | Rt | counts | mask
+  char *rt_dev = nullptr;
+  size_t rt_cap = 0;
   // ImproveHomography scratch: device {H_in[9], H_out[9], numfit, job}, pinned host mirror
   char *ih_dev = nullptr, *ih_host = nullptr;
   char *ap_jobs = nullptr;           // all-pairs: one ImproveJob per pair
@@ -694,6 +697,7 @@ void csb_ctx_destroy(csb_ctx *ctx) {
   if (ctx->ap_scratch) cudaFree(ctx->ap_scratch);
   if (ctx->ap_pack) cudaFree(ctx->ap_pack);
   if (ctx->ap_result) cudaFree(ctx->ap_result);
+  if (ctx->rt_dev) cudaFree(ctx->rt_dev);
   if (ctx->ih_dev) cudaFree(ctx->ih_dev);
   if (ctx->ih_host) cudaFreeHost(ctx->ih_host);
   if (ctx->ap_jobs) cudaFree(ctx->ap_jobs);
@@ -936,8 +940,15 @@ int csb_rigid_transform(csb_ctx *ctx, const float *h_coord, int num_pts, int typ
   const size_t b_coord = ((size_t)num_pts * 6 * 4 + 255) & ~(size_t)255, b_idx = ((size_t)num_loops * 12 + 255) & ~(size_t)255,
                b_rt = ((size_t)num_loops * 48 + 255) & ~(size_t)255, b_cnt = ((size_t)num_loops * 4 + 255) & ~(size_t)255,
                b_mask = ((size_t)num_pts + 255) & ~(size_t)255;
-  char *d = nullptr;
-  CSB_CHECK(ctx, cudaMalloc((void **)&d, b_coord + b_idx + b_rt + b_cnt + b_mask));
+  // the scratch lives in the context and only grows (no cudaMalloc / cudaFree per call)
+  const size_t need = b_coord + b_idx + b_rt + b_cnt + b_mask;
+  if (ctx->rt_cap < need) {
+    if (ctx->rt_dev) cudaFree(ctx->rt_dev);
+    ctx->rt_dev = nullptr; ctx->rt_cap = 0;
+    CSB_CHECK(ctx, cudaMalloc((void **)&ctx->rt_dev, need));
+    ctx->rt_cap = need;
+  }
+  char *d = ctx->rt_dev;
   float *d_coord = (float *)d;
   int *d_idx = (int *)(d + b_coord);
   float *d_rt = (float *)(d + b_coord + b_idx);
@@ -965,7 +976,6 @@ int csb_rigid_transform(csb_ctx *ctx, const float *h_coord, int num_pts, int typ
   if (e == cudaSuccess) e = cudaMemcpyAsync(mask.data(), d_mask, (size_t)num_pts, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(Rt12, d_rt + 12 * (size_t)best, 48, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d);
   if (e != cudaSuccess) {
     ctx->err = std::string("csb_rigid_transform: ") + cudaGetErrorString(e);
     return (int)e;
