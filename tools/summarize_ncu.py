@@ -35,13 +35,13 @@ def to_bytes(val, unit):
 
 
 # bench.py kernel name of each capture (bench.py reads <tag>_traffic.json for roofline.traffic)
-BENCH_NAME = {"blur_dog_o0": "blur_dog_down_o0", "find_points": "find_points", "orient_desc": "orient_desc",
-              "match_tc": "match_tc"}
+BENCH_NAME = {"blur_dog_o0": "blur_dog_down_o0", "pyramid_o0": "pyramid_o0", "pyramid_rest": "pyramid_rest",
+              "down_chain": "down_chain", "find_points": "find_points", "orient_desc": "orient_desc", "match_tc": "match_tc"}
 traffic = {}
 PROF.mkdir(exist_ok=True)
 lines = [f"# ncu summaries, tag {tag}", "",
          "Captured on a B200 with `ncu --set full --clock-control none --import-source on` (one launch per kernel,",
-         "a 1080p frame of the bench workload — blur_dog: octave 0; cold caches, serialised) and",
+         "a 1080p frame of the bench workload; cold caches, serialised) and",
          "`ncu --metrics gpu__time_duration.sum --clock-control none` (launch list).  Numbers taken under a profiler are",
          "not bench values; they explain them.", ""]
 for rep in sorted(OUT.glob(f"prof_{tag}_*.ncu-rep")):
@@ -96,7 +96,8 @@ if lf.exists():
         data = rows[start + 1:]
         for r in data:
             wr.writerow([r[ik].split("(")[0], r[ig], r[ib], r[iv]])
-    frame = data[-7:]     # 5 blur_dog + find_points (all octaves) + orient_desc (the result download is a copy-engine transfer)
+    per_frame = 5 if any("k_pyramid" in r[ik] for r in data) else 7   # r02: pyramid_o0, down_chain, pyramid_rest, find_points, orient_desc
+    frame = data[-per_frame:]
     tot = sum(float(r[iv].replace(",", "")) for r in frame)
     lines += ["## launch list (last frame of the capture)", "", "| kernel | grid | ns | share |", "|---|---|---|---|"]
     for r in frame:
