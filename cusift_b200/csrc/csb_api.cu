@@ -1135,7 +1135,7 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
       if (ctx->tc_val) cudaFree(ctx->tc_val);
       if (ctx->tc_idx) cudaFree(ctx->tc_idx);
       ctx->tc_val = nullptr; ctx->tc_idx = nullptr;
-      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_val, sizeof(float) * sl_need));
+      CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_val, sizeof(float) * tc_shortlist_floats(n1)));
       CSB_CHECK(ctx, cudaMalloc((void **)&ctx->tc_idx, sizeof(int) * sl_need));
       ctx->tc_sl_cap = sl_need;
     }
@@ -1171,7 +1171,7 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
       LaunchScope ls(ctx, s, "match_rescore");
       ctx->launches += 1;
       launch_rescore((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, ctx->tc_val, ctx->tc_idx, splits,
-                     distance, ctx->tc_flags, ctx->tc_list, ctx->tc_count, s->stream);
+                     distance, ctx->tc_count + 4, ctx->tc_count + 6, ctx->tc_flags, ctx->tc_list, ctx->tc_count, s->stream);
     }
     {
       LaunchScope ls(ctx, s, "match_redo");
@@ -1370,7 +1370,7 @@ int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_s
     const size_t nblk = (size_t)max_n / 16 + 2;
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_slv = carve(4 * sl_need), o_sli = carve(4 * sl_need), o_flags = carve(4 * nblk), o_list = carve(4 * nblk),
+    const size_t o_slv = carve(4 * tc_shortlist_floats(max_n > 0 ? max_n : 1)), o_sli = carve(4 * sl_need), o_flags = carve(4 * nblk), o_list = carve(4 * nblk),
                  o_cnt = carve(256), o_part = carve(match_redo_scratch_bytes((int)nblk)), o_valid = carve(4 * (size_t)(max_n + 1)),
                  o_nvalid = carve(256), o_coord = carve(16 * (size_t)(n_up + 16)), o_rand = carve(16 * (size_t)num_loops),
                  o_homo = carve(32 * (size_t)num_loops), o_counts = carve(4 * (size_t)num_loops);
@@ -1463,7 +1463,8 @@ int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_s
       if (use_tc && n1 >= 256 && n2 >= 256 && in_domain) {
         const int splits = tc_splits(n1, n2, ctx->sm_count);
         launch_match_tc(packed[i], n1, packed[j], n2, splits, c.sl_val, c.sl_idx, ctx->ap_flags + 2 * i, ctx->ap_flags + 2 * j, c.st);
-        launch_rescore(s1, n1, s2, n2, c.sl_val, c.sl_idx, splits, distance, c.flags, c.list, c.cnt, c.st);
+        launch_rescore(s1, n1, s2, n2, c.sl_val, c.sl_idx, splits, distance, ctx->ap_flags + 2 * i, ctx->ap_flags + 2 * j, c.flags,
+                       c.list, c.cnt, c.st);
         launch_match_blocks(s1, n1, s2, n2, distance, c.list, c.cnt, (n1 + 15) / 16, c.part, c.st);
         ctx->launches += 5;
       } else {

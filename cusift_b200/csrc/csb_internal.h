@@ -142,7 +142,9 @@ void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *info, 
 void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
                      const int *q_info, const int *c_info, cudaStream_t st);
 void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,
-                    int n_splits, int distance, int *redo_flags, int *redo_list, int *redo_count, cudaStream_t st);
+                    int n_splits, int distance, const int *q_info, const int *c_info, int *redo_flags, int *redo_list,
+                    int *redo_count, cudaStream_t st);
+size_t tc_shortlist_floats(int n);   // floats of short-list scratch (sl_val) a query set of n points needs
 void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
                        int *d_counts, int num_loops, float thresh2, cudaStream_t st);
 

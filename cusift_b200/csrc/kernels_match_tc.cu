@@ -11,24 +11,34 @@
 //                    any block of rows of one 64-wide K half is ONE contiguous range.
 //  2. k_match_tc     persistent-style CTA per (256 queries, slice of the candidates):
 //                      warp 0   producer: 1-D bulk copies (cp.async.bulk -> UBLKCP) of the
-//                               query tiles (once) and of the 256-candidate tiles (2 stages),
+//                               query tiles (once) and of the 128-candidate tiles (4 stages),
 //                               completion on mbarriers (expect_tx);
 //                      warp 1   one elected lane issues tcgen05.mma.cta_group::1.kind::f16
-//                               M128 x N256 x K16, 8 per accumulator, operands straight from
+//                               M128 x N128 x K16, 8 per accumulator, operands straight from
 //                               shared memory (smem descriptors, SWIZZLE_128B), fp32
-//                               accumulators in TMEM: two 128x256 accumulators (512 columns),
-//                               one per 128-query half, so every candidate tile is used twice;
+//                               accumulators in TMEM: FOUR 128x128 accumulators (512 columns),
+//                               two per 128-query half, so the MMAs of tile i+1 run while the
+//                               epilogue still reads tile i (with one 128x256 accumulator per half
+//                               the tensor pipe idled for the whole arithmetic of the epilogue:
+//                               measured 25 us of MMA + 15 us of exposed epilogue per 8192^2);
 //                               tcgen05.commit releases the smem stage / publishes the accumulator;
 //                      warps 2-9  epilogue: thread = one query row (one TMEM lane), tcgen05.ld 32
-//                               columns at a time.  The candidate slice is swept TWICE (the
-//                               tensor pipe has time to spare, the epilogue does not):
-//                               sweep 1 keeps the two largest approximate dot products
-//                               m1 >= m2 per row, branch-free (3 FMNMX per value);
-//                               sweep 2 lists every candidate with approximate dot >= m2 - 2 eps
-//                               (chunk-max filter, so the divergent append path is rare).
+//                               columns at a time.
+//                               sweep 1 runs over the FIRST QUARTER of the slice only and keeps
+//                               m1 >= m2, the largest approximate dot product and a lower bound of
+//                               the second largest (any subset of the columns gives a valid lower
+//                               bound);
+//                               sweep 2 runs over the whole slice, the tiles sweep 1 has not seen
+//                               first: it lists every candidate with approximate dot >= m2 - 2 eps
+//                               (chunk-max filter, so the divergent append path is rare) and keeps
+//                               raising m2 from the chunk maxima of the unseen tiles, so that the
+//                               threshold has its final value when the seen quarter comes round
+//                               again.  The threshold never decreases, so a candidate at or above
+//                               the FINAL threshold is always listed; the expected over-listing is
+//                               2 ln 4 - 1.5 ~ 1.3 entries per query and split.
 //                               Any candidate left out has exact dot < m2 - eps <= the exact dots
 //                               of at least two listed ones, so the exact best and second best
-//                               are always in the list.
+//                               are always in the list.  1.25 passes of MMA instead of 2.
 //  3. k_rescore      warp per query: exact fp32 scores of the listed candidates in the
 //                    reference's rotated k order (bit-identical to ComputeDistance), then the
 //                    reference's best / second-best rule incl. its tie-breaking
@@ -53,17 +63,21 @@
 namespace {
 
 constexpr int TC_QT = 256;        // queries per CTA (two 128-row accumulators)
-constexpr int TC_CT = 256;        // candidates per tile (UMMA N)
-constexpr int TC_STAGES = 2;
-constexpr int TC_TOPK = 8;
+constexpr int TC_CT = 128;        // candidates per tile (UMMA N)
+constexpr int TC_STAGES = 4;
+#ifndef TC_S1_DIV
+#define TC_S1_DIV 4               // sweep 1 covers the last 1/TC_S1_DIV of the candidate slice
+#endif
+constexpr int TC_TOPK = 8;         // listed candidates per query and split handed to the rescoring kernel
+constexpr int TC_RAW = 16;         // candidates per query a CTA can hold while the threshold is still rising
 constexpr int KHALF_BYTES_PER_ROW = 128;          // 64 fp16
 constexpr uint32_t A_HALF_BYTES = 128 * KHALF_BYTES_PER_ROW;      // one 128-row x 64-K operand block: 16 KB
-constexpr uint32_t B_HALF_BYTES = TC_CT * KHALF_BYTES_PER_ROW;    // 32 KB
+constexpr uint32_t B_HALF_BYTES = TC_CT * KHALF_BYTES_PER_ROW;    // 16 KB
 constexpr uint32_t SMEM_A = 2 /*query halves*/ * 2 /*K halves*/ * A_HALF_BYTES;   // 64 KB
-constexpr uint32_t SMEM_B_STAGE = 2 * B_HALF_BYTES;                                 // 64 KB
-constexpr uint32_t SMEM_TC = SMEM_A + TC_STAGES * SMEM_B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t SMEM_B_STAGE = 2 * B_HALF_BYTES;                                 // 32 KB
+constexpr uint32_t SMEM_RAW = TC_RAW * TC_QT * 8;                                   // raw list: value + index per entry, 32 KB
+constexpr uint32_t SMEM_TC = SMEM_A + TC_STAGES * SMEM_B_STAGE + SMEM_RAW + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 32 * (2 + 8);
-constexpr int RS_ROWS = 16;        // staged candidate rows per rescoring round (per warp)
 constexpr float TC_MAX_NORM2 = 1.002f;   // squared-norm limit of the domain in which the error bound is derived
 
 // ---- PTX wrappers ---------------------------------------------------------------
@@ -138,8 +152,8 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B
   return d;
 }
-// Instruction descriptor, kind::f16: fp16 x fp16 -> fp32, both operands K-major, M=128, N=256.
-constexpr uint32_t IDESC_F16_M128_N256 = (1u << 4)                 // D format = F32
+// Instruction descriptor, kind::f16: fp16 x fp16 -> fp32, both operands K-major, M=128, N=TC_CT.
+constexpr uint32_t IDESC_F16_M128 = (1u << 4)                 // D format = F32
                                          | (0u << 7) | (0u << 10)   // A, B format = F16
                                          | (0u << 15) | (0u << 16)  // A, B K-major
                                          | ((uint32_t)(TC_CT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -198,13 +212,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
   unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char *sA = base;                          // [qhalf][khalf][128 rows][128 B]
   unsigned char *sB = base + SMEM_A;                 // [stage][khalf][256 rows][128 B]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(base + SMEM_A + TC_STAGES * SMEM_B_STAGE);
+  float2 *s_raw = reinterpret_cast<float2 *>(base + SMEM_A + TC_STAGES * SMEM_B_STAGE);   // [TC_RAW][TC_QT] {value, index}
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base + SMEM_A + TC_STAGES * SMEM_B_STAGE + SMEM_RAW);
   uint64_t *a_full = bars + 0;
   uint64_t *b_full = bars + 1;                       // [TC_STAGES]
   uint64_t *b_empty = bars + 1 + TC_STAGES;          // [TC_STAGES]
-  uint64_t *acc_full = bars + 1 + 2 * TC_STAGES;     // [2]
-  uint64_t *acc_empty = bars + 3 + 2 * TC_STAGES;    // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 + 2 * TC_STAGES);
+  uint64_t *acc_full = bars + 1 + 2 * TC_STAGES;     // [4]: accumulator 2 qh + (iteration & 1)
+  uint64_t *acc_empty = bars + 5 + 2 * TC_STAGES;    // [4]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9 + 2 * TC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qtile = blockIdx.x, split = blockIdx.y;
@@ -212,6 +227,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
   const int t0 = split * tiles_per_split;
   const int t1 = min(t0 + tiles_per_split, n_tiles_total);
   const int n_tiles = max(t1 - t0, 0);
+  // iteration schedule (producer, MMA issuer and epilogue all follow it): sweep 1 = the first n1 tiles of the
+  // slice (padding, if any, is at the end), then sweep 2 = the other tiles followed by those n1 tiles again
+  const int n1 = (n_tiles + TC_S1_DIV - 1) / TC_S1_DIV;
+  const int n_iter = n1 + n_tiles;
+  auto tile_of = [&](int it) { return t0 + (it < n_tiles ? it : it - n_tiles); };
 
   if (warp == 1 && lane == 0) {
     mbar_init(a_full, 1);
@@ -219,13 +239,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
       mbar_init(b_full + s, 1);
       mbar_init(b_empty + s, 1);
     }
-    for (int a = 0; a < 2; a++) {
+    for (int a = 0; a < 4; a++) {
       mbar_init(acc_full + a, 1);
       mbar_init(acc_empty + a, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {   // TMEM: all 512 columns (two 128 x 256 fp32 accumulators)
+  if (warp == 0) {   // TMEM: all 512 columns (four 128 x 128 fp32 accumulators)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -244,10 +264,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
                    reinterpret_cast<const char *>(q_packed) + (size_t)kb * nq_pad * KHALF_BYTES_PER_ROW +
                        (size_t)(qtile * TC_QT + qh * 128) * KHALF_BYTES_PER_ROW,
                    A_HALF_BYTES, a_full);
-      for (int i = 0; i < 2 * n_tiles; i++) {      // two sweeps over the candidate slice
+      for (int i = 0; i < n_iter; i++) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (i / TC_STAGES) & 1;
-        const int tile = t0 + (i < n_tiles ? i : i - n_tiles);
+        const int tile = tile_of(i);
         mbar_wait(b_empty + s, ph ^ 1);
         mbar_expect_tx(b_full + s, SMEM_B_STAGE);
         for (int kb = 0; kb < 2; kb++)
@@ -262,26 +282,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
     if (lane == 0) {
       mbar_wait(a_full, 0);
       tc_fence_after();
-      for (int i = 0; i < 2 * n_tiles; i++) {
+      for (int i = 0; i < n_iter; i++) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (i / TC_STAGES) & 1;
         mbar_wait(b_full + s, ph);
         tc_fence_after();
         for (int qh = 0; qh < 2; qh++) {
-          // accumulator qh is reused every tile: wait until the epilogue drained the previous one
-          mbar_wait(acc_empty + qh, (i & 1) ^ 1);
+          // accumulator (qh, i & 1) is reused every other iteration: wait until the epilogue drained its previous use
+          const int a = qh * 2 + (i & 1);
+          mbar_wait(acc_empty + a, ((i >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(qh * TC_CT);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_CT);
 #pragma unroll
           for (int kb = 0; kb < 2; kb++) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               const uint64_t ad = smem_desc_k128(smem_u32(sA + (qh * 2 + kb) * A_HALF_BYTES) + k * 32);
               const uint64_t bd = smem_desc_k128(smem_u32(sB + s * SMEM_B_STAGE + kb * B_HALF_BYTES) + k * 32);
-              tc_mma_f16(d_tmem, ad, bd, IDESC_F16_M128_N256, (kb | k) ? 1u : 0u);
+              tc_mma_f16(d_tmem, ad, bd, IDESC_F16_M128, (kb | k) ? 1u : 0u);
             }
           }
-          tc_commit(acc_full + qh);       // accumulator qh complete -> epilogue
+          tc_commit(acc_full + a);        // accumulator complete -> epilogue
         }
         tc_commit(b_empty + s);           // both MMAs of this stage done -> producer may refill
       }
@@ -289,20 +310,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
   } else {
     // ===== epilogue: 8 warps, thread = one query row =====
     const int ew = warp - 2;                 // 0..7
-    const int qh = ew >> 2;                  // query half (accumulator)
+    const int qh = ew >> 2;                  // query half
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = qh * 128 + quad * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qh * TC_CT);
-    // ---- sweep 1: m1 = largest approximate dot product of this row, m2 = second largest CHUNK maximum
-    // (chunks of 32 columns).  m2 <= the true second largest value, so thr = m2 - 2 eps is still a valid
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qh * 2 * TC_CT);
+    // ---- sweep 1: m1 = largest approximate dot product of this row among the tiles seen, m2 = second largest
+    // CHUNK maximum (chunks of 32 columns).  m2 <= the true second largest value, so thr = m2 - 2 eps is a valid
     // (slightly more inclusive) listing threshold, and a chunk costs 16 three-input max + 3 ops instead
-    // of 96 (FMNMX runs at half rate: this epilogue is ALU-pipe bound).  Padding columns hold 0.
+    // of 96 (FMNMX runs at half rate).  Padding columns hold 0.
     // TMEM reads are software-pipelined: the tcgen05.ld of the next 64 columns is in flight while the
     // current 64 are reduced (tcgen05.wait::ld waits for every outstanding load, so it sits after the
     // arithmetic), and the accumulator is handed back to the MMA warp as soon as its last columns are in
     // registers, before they are reduced.
     float m1 = -1.0f, m2 = -1.0f;
+    auto top2 = [&](float c) {
+      const float lo = fminf(m1, c);
+      m1 = fmaxf(m1, c);
+      m2 = fmaxf(m2, lo);
+    };
     auto reduce64 = [&](const uint32_t (&r)[32], const uint32_t (&q)[32]) {
+#ifdef TC_NOALU
+      m1 = fmaxf(m1, __uint_as_float(r[0] ^ q[31] ^ r[17])); m2 = 0.2f;
+      return;
+#endif
       float g[8];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -315,18 +345,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
         g[4 + k] = fmaxf(fmaxf(g[4 + k], __uint_as_float(q[8 * k + 5])), __uint_as_float(q[8 * k + 6]));
         g[4 + k] = fmaxf(g[4 + k], __uint_as_float(q[8 * k + 7]));
       }
-      const float ca = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-      const float cb = fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]));
-      float lo = fminf(m1, ca);
-      m1 = fmaxf(m1, ca);
-      m2 = fmaxf(m2, lo);
-      lo = fminf(m1, cb);
-      m1 = fmaxf(m1, cb);
-      m2 = fmaxf(m2, lo);
+      top2(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])));
+      top2(fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
     };
-    static_assert(TC_CT / 64 == 4, "sweep 1 is unrolled for four 64-column chunks per tile");
-    for (int i = 0; i < n_tiles; i++) {
-      mbar_wait(acc_full + qh, i & 1);
+    static_assert((TC_RAW & (TC_RAW - 1)) == 0, "raw list slots wrap with a mask");
+    static_assert(TC_CT == 128, "both sweeps are unrolled for four 32-column chunks per tile");
+    int it = 0;
+    for (; it < n1; it++) {
+      const int a = it & 1;
+      const uint32_t taddr = tlane + (uint32_t)(a * TC_CT);
+      mbar_wait(acc_full + qh * 2 + a, (it >> 1) & 1);
       tc_fence_after();
       uint32_t ra[32], qa[32], rb[32], qb[32];
       tc_ld32(taddr + 0, ra);
@@ -336,73 +364,102 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
       tc_ld32(taddr + 96, qb);
       reduce64(ra, qa);
       tc_ld_wait();
-      tc_ld32(taddr + 128, ra);
-      tc_ld32(taddr + 160, qa);
-      reduce64(rb, qb);
-      tc_ld_wait();
-      tc_ld32(taddr + 192, rb);
-      tc_ld32(taddr + 224, qb);
-      reduce64(ra, qa);
-      tc_ld_wait();
       tc_fence_before();
-      mbar_arrive(acc_empty + qh);           // 128 arrivals free the accumulator
+      mbar_arrive(acc_empty + qh * 2 + a);   // 128 arrivals free the accumulator
       reduce64(rb, qb);
     }
     // ---- sweep 2: list every candidate with approximate dot >= m2 - 2 eps ----
     // eps of this pair of sets from the rounding-error norms measured at pack time (header comment)
-    const float eps = 1.002f * (sqrtf(__int_as_float(q_info[1])) + sqrtf(__int_as_float(c_info[1]))) + 2.0e-5f;
-    const float thr = m2 - 2.0f * eps;
-    // Hits (about 2 per query and split) are appended straight to the global short list.  The append path
-    // runs for the whole warp whenever ANY lane has a hit in an 8-column group (about a quarter of the
-    // groups), so it must be short: a bit mask of the group's hits, then one iteration per set bit.
-    int *const out_list = out_idx + ((size_t)(qtile * TC_QT + row) * n_splits + split) * TC_TOPK;
+    const float eps2 = 2.0f * (1.002f * (sqrtf(__int_as_float(q_info[1])) + sqrtf(__int_as_float(c_info[1]))) + 2.0e-5f);
+    float thr = m2 - eps2;
+    // Hits go to a per-row raw list in shared memory ([entry][row]: the lanes of a warp write consecutive words),
+    // value and index, because the threshold is still rising: once it is final the row's entries are filtered
+    // again and only the survivors reach the global short list.  The append path runs for the whole warp whenever
+    // ANY lane has a hit in an 8-column group, so it is kept short and branch-free inside.
     int cnt = 0;
-    auto list32 = [&](const uint32_t (&r)[32], int cbase) {
+    // one 32-column chunk: the four 8-column groups are tested against the threshold as it stands, then (tiles
+    // that sweep 1 has not seen only: a value must not enter the top-2 twice) the chunk maximum raises it
+    auto list32 = [&](const uint32_t (&r)[32], int cbase, bool unseen) {
+#ifdef TC_NOALU
+      if (__uint_as_float(r[3] ^ r[30]) == 123.25f) cnt++;
+      return;
+#endif
+      float g[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        float g = fmaxf(fmaxf(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])), __uint_as_float(r[8 * k + 2]));
-        g = fmaxf(fmaxf(g, __uint_as_float(r[8 * k + 3])), __uint_as_float(r[8 * k + 4]));
-        g = fmaxf(fmaxf(g, __uint_as_float(r[8 * k + 5])), __uint_as_float(r[8 * k + 6]));
-        g = fmaxf(g, __uint_as_float(r[8 * k + 7]));
-        if (g >= thr) {
+        g[k] = fmaxf(fmaxf(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1])), __uint_as_float(r[8 * k + 2]));
+        g[k] = fmaxf(fmaxf(g[k], __uint_as_float(r[8 * k + 3])), __uint_as_float(r[8 * k + 4]));
+        g[k] = fmaxf(fmaxf(g[k], __uint_as_float(r[8 * k + 5])), __uint_as_float(r[8 * k + 6]));
+        g[k] = fmaxf(g[k], __uint_as_float(r[8 * k + 7]));
+        if (g[k] >= thr) {
+          // Rare per lane, but the whole warp waits for the lanes in here, so the usual case (one hit in the group)
+          // is straight-line code: a mask of the group's hits (8 independent compares), the first hit goes to slot
+          // cnt mod TC_RAW with the GROUP maximum as its value (exact for a single hit, an upper bound otherwise: the
+          // final filter then keeps a superset, never less).  A count above TC_RAW means the list wrapped and the
+          // row is handed to the exact kernel.  Padding columns (score 0) are removed by the final filter.
           unsigned int m = 0;
 #pragma unroll
           for (int j = 0; j < 8; j++) m |= (__uint_as_float(r[8 * k + j]) >= thr) ? (1u << j) : 0u;
-          while (m) {
-            const int cidx = cbase + 8 * k + (__ffs(m) - 1);
+          s_raw[(cnt & (TC_RAW - 1)) * TC_QT + row] = make_float2(g[k], __int_as_float(cbase + 8 * k + (__ffs(m) - 1)));
+          cnt++;
+          m &= m - 1;
+          while (m) {                                // further hits in the same 8 columns: near-duplicates
+            s_raw[(cnt & (TC_RAW - 1)) * TC_QT + row] = make_float2(g[k], __int_as_float(cbase + 8 * k + (__ffs(m) - 1)));
+            cnt++;
             m &= m - 1;
-            if (cidx < nc) {
-              if (cnt < TC_TOPK) out_list[cnt] = cidx;
-              cnt++;
-            }
           }
         }
       }
+      if (unseen) {
+        top2(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])));
+        thr = m2 - eps2;
+      }
     };
-    for (int i = 0; i < n_tiles; i++) {
-      mbar_wait(acc_full + qh, (n_tiles + i) & 1);
+    for (; it < n_iter; it++) {
+      const int a = it & 1;
+      const uint32_t taddr = tlane + (uint32_t)(a * TC_CT);
+      const bool unseen = it < n_iter - n1;
+      const int col0 = tile_of(it) * TC_CT;
+      mbar_wait(acc_full + qh * 2 + a, (it >> 1) & 1);
       tc_fence_after();
-      const int col0 = (t0 + i) * TC_CT;
       uint32_t ra[32], rb[32];
       tc_ld32(taddr, ra);
       tc_ld_wait();
-#pragma unroll 1
-      for (int ch = 0; ch < TC_CT / 32; ch += 2) {        // same double buffering as sweep 1
-        tc_ld32(taddr + (uint32_t)((ch + 1) * 32), rb);
-        list32(ra, col0 + ch * 32);
-        tc_ld_wait();
-        if (ch + 2 < TC_CT / 32) {
-          tc_ld32(taddr + (uint32_t)((ch + 2) * 32), ra);
-        } else {
-          tc_fence_before();
-          mbar_arrive(acc_empty + qh);
+      tc_ld32(taddr + 32, rb);
+      list32(ra, col0, unseen);
+      tc_ld_wait();
+      tc_ld32(taddr + 64, ra);
+      list32(rb, col0 + 32, unseen);
+      tc_ld_wait();
+      tc_ld32(taddr + 96, rb);
+      list32(ra, col0 + 64, unseen);
+      tc_ld_wait();
+      tc_fence_before();
+      mbar_arrive(acc_empty + qh * 2 + a);
+      list32(rb, col0 + 96, unseen);
+    }
+    // the threshold is final: keep the entries that reach it (each thread reads back its own writes only).
+    // Short list of this (row, split): index -1 = unused slot, -2 in slot 0 = the list proves nothing (overflow);
+    // value = approximate dot product (an upper bound for hits that shared an 8-column group); plus the
+    // split's (m1, m2), from which the rescoring kernel derives the threshold over ALL splits.
+    const size_t slot = (size_t)(qtile * TC_QT + row) * n_splits + split;
+    int *const out_list = out_idx + slot * TC_TOPK;
+    float *const out_lval = out_val + slot * TC_TOPK;
+    int kept = 0;
+    for (int e = 0; e < min(cnt, TC_RAW); e++) {
+      const float2 en = s_raw[e * TC_QT + row];
+      const int cidx = __float_as_int(en.y);
+      if (en.x >= thr && cidx < nc) {
+        if (kept < TC_TOPK) {
+          out_list[kept] = cidx;
+          out_lval[kept] = en.x;
         }
-        list32(rb, col0 + (ch + 1) * 32);
-        if (ch + 2 < TC_CT / 32) tc_ld_wait();
+        kept++;
       }
     }
-    for (int k = min(cnt, TC_TOPK); k < TC_TOPK; k++) out_list[k] = -1;
-    out_val[(size_t)(qtile * TC_QT + row) * n_splits + split] = (float)cnt;   // entries found (may exceed TC_TOPK)
+    for (int k = min(kept, TC_TOPK); k < TC_TOPK; k++) out_list[k] = -1;
+    if (cnt > TC_RAW || kept > TC_TOPK) out_list[0] = -2;   // wrapped raw list or more survivors than slots
+    reinterpret_cast<float2 *>(out_val + (size_t)nq_pad * 4 * TC_TOPK)[slot] = make_float2(m1, m2);
   }
 
   tc_fence_before();
@@ -416,113 +473,202 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
 // ---- 3. exact rescoring -----------------------------------------------------------------
 __device__ __forceinline__ int bitrev4(int x) { return ((x & 1) << 3) | ((x & 2) << 1) | ((x & 4) >> 1) | ((x & 8) >> 3); }
 
-template <bool kL2>
-__global__ void __launch_bounds__(128) k_rescore(csb_sift_point *__restrict__ s1, int n1,
-                                                 const csb_sift_point *__restrict__ s2, int n2,
-                                                 const float *__restrict__ sl_val, const int *__restrict__ sl_idx,
-                                                 int n_splits, int *__restrict__ redo_flags) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n1) return;
-  const int q = warp;
-  const int n_list = n_splits * TC_TOPK;          // <= 32
-  int ci = -1;
-  if (lane < n_list) ci = sl_idx[(size_t)q * n_list + lane];
-  // a split that found more candidates above its threshold than fit in its list: redo exactly
-  bool overflow = false;
-  if (lane < n_splits) overflow = sl_val[(size_t)q * n_splits + lane] > (float)TC_TOPK;
-  const bool proven = !__any_sync(0xffffffffu, overflow);
+// One warp rescoring RS_QPW queries at a time.  (The first version gave every query its own warp: about ten listed
+// candidates = ten busy lanes, each walking a 128-step chain with two shared-memory reads per step, so the kernel
+// was bound by the shared-memory pipe at a third of its lane capacity, and every split's private top-2 was rescored
+// although only the top-2 over all splits matter.)
+//   1. filter: lane = list entry of one query (n_splits x TC_TOPK <= 32).  The splits' (m1, m2) pairs give a lower
+//      bound of the second largest approximate dot product over ALL candidates (their chunks are disjoint); entries
+//      whose value (an upper bound) is below it minus 2 eps cannot be best or second best and are dropped.
+//      About 2.3 entries per query survive instead of 10.
+//   2. the survivors of the warp's queries are packed into consecutive lanes (work items); their descriptors and
+//      the queries' are staged in shared memory with asynchronous copies (all rows in flight at once);
+//   3. lane = work item: exact score in the reference's rotated k order (matching.cu:84-89);
+//   4. lane = query: FindMinCorr/FindMaxCorr's best / second-best rule over the query's few items.
+constexpr int RS_QPW = 8;           // queries per warp and round (the (m1, m2) merge maps lane = 4 query + split)
+constexpr int RS_WARPS = 4;
+constexpr int RS_QS = 129, RS_CS = 129;   // row strides (words): rows spread over the banks
+constexpr size_t RS_SMEM_WARP = sizeof(float) * (RS_QPW * RS_QS + 32 * RS_CS) + sizeof(int) * (32 + 32);
 
-  // exact score in the reference's rotated k order (matching.cu:84-89), lane = one listed candidate.
-  // The listed descriptors are first staged in shared memory by the whole warp (coalesced 512-byte row
-  // reads; 32 lanes each walking their own global row cost ~10 sectors per load instruction and made
-  // this kernel as slow as the tensor-core scan), then every lane runs its 128-step FFMA chain from
-  // shared memory: row stride 129 words spreads the lanes' rows over the banks.
-  __shared__ float s_q[4][128];
-  __shared__ float s_c[4][RS_ROWS * 129];
-  const int wib = threadIdx.x >> 5;
-  float *sq = s_q[wib], *sc = s_c[wib];
+template <bool kL2>
+__global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__restrict__ s1, int n1,
+                                                           const csb_sift_point *__restrict__ s2, int n2,
+                                                           const float *__restrict__ sl_val, const int *__restrict__ sl_idx,
+                                                           int n_splits, int nq_pad, const int *__restrict__ q_info,
+                                                           const int *__restrict__ c_info, int *__restrict__ redo_flags) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *sq = reinterpret_cast<float *>(rs_smem + wib * RS_SMEM_WARP);   // [RS_QPW][RS_QS]
+  float *sc = sq + RS_QPW * RS_QS;                                       // [32][RS_CS]
+  int *s_ci = reinterpret_cast<int *>(sc + 32 * RS_CS);                  // candidate index of work item
+  int *s_qi = s_ci + 32;                                                 // local query of work item
+  const int n_list = n_splits * TC_TOPK;          // <= 32
+  const float eps2 = 2.0f * (1.002f * (sqrtf(__int_as_float(q_info[1])) + sqrtf(__int_as_float(c_info[1]))) + 2.0e-5f);
+  const float2 *sl_top = reinterpret_cast<const float2 *>(sl_val + (size_t)nq_pad * 4 * TC_TOPK);
+  const float NONE = kL2 ? 999.0f : -1.0f;
+  const unsigned FULLM = 0xffffffffu;
+
+  for (int q0 = (blockIdx.x * RS_WARPS + wib) * RS_QPW; q0 < n1; q0 += gridDim.x * RS_WARPS * RS_QPW) {
+    // ---- 1. filter; survivors stay in registers: lane l of query j -> keepm[j] bit l.  All loads of the warp's
+    // queries are issued before the first is used (one L2 round trip, not eight).
+    int my_ci[RS_QPW];
+    float my_v[RS_QPW];
 #pragma unroll
-  for (int j = 0; j < 4; j++) sq[lane + 32 * j] = s1[q].data[lane + 32 * j];
-  float score = kL2 ? 999.0f : -1.0f;
-  // listed candidates are compacted to rows 0.. of the staging tile, RS_ROWS at a time (usually one round)
-  const unsigned int have = __ballot_sync(0xffffffffu, ci >= 0);
-  const int my_row = __popc(have & ((1u << lane) - 1u));
-  const int n_have = __popc(have);
-  for (int r0 = 0; r0 < n_have; r0 += RS_ROWS) {
-    __syncwarp();
-    unsigned int m = have;
-    for (int r = 0; m; r++) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      if (r < r0 || r >= r0 + RS_ROWS) continue;
-      const int c = __shfl_sync(0xffffffffu, ci, src);
-      const float *pb = s2[c].data;
-      // asynchronous global -> shared copies (LDGSTS): the rows of ALL listed candidates are in flight at once;
-      // with ordinary loads every row waited for the previous row's data (load -> store dependency in a loop of
-      // unknown length), i.e. one L2 round trip per candidate.  4-byte copies: data[] is only 4-byte aligned.
-#pragma unroll
-      for (int j = 0; j < 4; j++) __pipeline_memcpy_async(&sc[(r - r0) * 129 + lane + 32 * j], &pb[lane + 32 * j], 4);
-    }
-    __pipeline_commit();
-    __pipeline_wait_prior(0);
-    __syncwarp();
-    if (ci >= 0 && my_row >= r0 && my_row < r0 + RS_ROWS) {
-      const float *pb = sc + (my_row - r0) * 129;
-      const int tx = ci & 15;
-      float sum = 0.0f;
-      // k = (i + tx) & 127 for i = 0..127: the first 112 steps never wrap (tx <= 15), so they run off two
-      // base pointers with immediate offsets; only the last 16 need the mask.  Same FFMA order.
-      const float *qa = sq + tx, *pa = pb + tx;
-#pragma unroll
-      for (int i = 0; i < 112; i++) sum = __fmaf_rn(qa[i], pa[i], sum);
-#pragma unroll
-      for (int i = 112; i < 128; i++) {
-        const int k = (i + tx) & 127;
-        sum = __fmaf_rn(sq[k], pb[k], sum);
+    for (int j = 0; j < RS_QPW; j++) {
+      my_ci[j] = -1;
+      my_v[j] = -3.0e38f;
+      if (q0 + j < n1 && lane < n_list) {
+        my_ci[j] = sl_idx[(size_t)(q0 + j) * n_list + lane];
+        my_v[j] = sl_val[(size_t)(q0 + j) * n_list + lane];
       }
-      score = kL2 ? __fsub_rn(2.0f, __fadd_rn(sum, sum)) : sum;
     }
-  }
-  // best: FindMinCorr's winner = lowest (score, bitrev4(col % 16), col / 16); second = best of the rest
-  // (an equal duplicate lands in `second`, matching.cu:229-235)
-  auto better = [](float sa, int ia, float sb, int ib) {   // is a strictly preferred to b ?
-    if (ib < 0) return ia >= 0;
-    if (ia < 0) return false;
-    if (sa != sb) return kL2 ? (sa < sb) : (sa > sb);
-    const int ra = bitrev4(ia & 15), rb = bitrev4(ib & 15);
-    if (ra != rb) return ra < rb;
-    return ia < ib;
-  };
-  float bs = score;
-  int bi = ci;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (better(os, oi, bs, bi)) {
-      bs = os;
-      bi = oi;
-    }
-  }
-  float ss = (ci >= 0 && ci != bi) ? score : (kL2 ? 999.0f : -1.0f);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float os = __shfl_xor_sync(0xffffffffu, ss, o);
-    ss = kL2 ? fminf(ss, os) : fmaxf(ss, os);
-  }
-  if (lane == 0) {
-    if (!proven) {
-      redo_flags[q >> 4] = 1;              // the exact kernel redoes this block of 16 queries
-    } else {
-      csb_sift_point *o = s1 + q;
-      o->score = bs;
-      if (kL2) o->ambiguity = (float)((double)bs / ((double)ss + 1e-6));
-      else o->ambiguity = (float)((double)__fsub_rn(1.0f, bs) / ((double)__fsub_rn(1.0f, ss) + 1e-6));
-      o->match = bi;
-      if (bi >= 0) {
-        o->match_xpos = s2[bi].coords2D[0];
-        o->match_ypos = s2[bi].coords2D[1];
+    // second largest approximate value over all splits, from below: merge the splits' (m1, m2); lane = 4 j + split
+    float a1 = -3.0e38f, a2 = -3.0e38f;
+    {
+      const int j = lane >> 2, sp = lane & 3;
+      if (q0 + j < n1 && sp < n_splits) {
+        const float2 t = sl_top[(size_t)(q0 + j) * n_splits + sp];
+        a1 = t.x, a2 = t.y;
       }
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {
+        const float b1 = __shfl_xor_sync(FULLM, a1, o), b2 = __shfl_xor_sync(FULLM, a2, o);
+        const float lo = fminf(a1, b1);
+        a1 = fmaxf(a1, b1);
+        a2 = fmaxf(fmaxf(a2, b2), lo);
+      }
+    }
+    unsigned int keepm[RS_QPW];
+    unsigned int overflow_q = 0;                  // bit j: a split of query j proves nothing
+#pragma unroll
+    for (int j = 0; j < RS_QPW; j++) {
+      if (__any_sync(FULLM, my_ci[j] == -2)) overflow_q |= 1u << j;
+      const float thr = __shfl_sync(FULLM, a2, 4 * j) - eps2;
+      const bool keep = my_ci[j] >= 0 && my_v[j] >= thr;
+      if (!keep) my_ci[j] = -1;
+      keepm[j] = __ballot_sync(FULLM, keep);
+    }
+    // ---- rounds: consecutive queries whose survivors fit the 32 lanes (a single query always fits)
+    int jb = 0;
+    while (jb < RS_QPW) {
+      int je = jb, n_items = 0;
+      int start[RS_QPW + 1];
+#pragma unroll
+      for (int j = 0; j < RS_QPW; j++) {
+        start[j] = n_items;
+        if (j >= jb && j == je && n_items + __popc(keepm[j]) <= 32) {
+          n_items += __popc(keepm[j]);
+          je = j + 1;
+        }
+      }
+      start[RS_QPW] = n_items;
+      // start[j] for j in [jb, je) is the first item of query j; queries outside the round have empty ranges
+      __syncwarp();
+      // ---- 2. work list + staging
+#pragma unroll
+      for (int j = 0; j < RS_QPW; j++) {
+        if (j >= jb && j < je && my_ci[j] >= 0) {
+          const int w = start[j] + __popc(keepm[j] & ((1u << lane) - 1u));
+          s_ci[w] = my_ci[j];
+          s_qi[w] = j;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < RS_QPW; j++) {
+        if (j >= jb && j < je && q0 + j < n1 && keepm[j]) {
+          const float *pq = s1[q0 + j].data;
+#pragma unroll
+          for (int t = 0; t < 4; t++) __pipeline_memcpy_async(&sq[j * RS_QS + lane + 32 * t], &pq[lane + 32 * t], 4);
+        }
+      }
+      // candidate rows are stored ROTATED by tx = index % 16 (element k at (k - tx) mod 128), so that the chain below
+      // reads its row front to back: lane w, step i -> bank (w + i) mod 32, conflict-free whatever the indices are
+      for (int w = 0; w < n_items; w++) {
+        const int cw = s_ci[w];
+        const float *pb = s2[cw].data;            // 4-byte copies: data[] is only 4-byte aligned
+        const int tx = cw & 15;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          __pipeline_memcpy_async(&sc[w * RS_CS + ((lane + 32 * t - tx) & 127)], &pb[lane + 32 * t], 4);
+      }
+      __pipeline_commit();
+      // lane = work item from here on; its candidate's coordinates are fetched now and used in step 4
+      int ci = -1, qi = 0;
+      float cx = 0.0f, cy = 0.0f;
+      if (lane < n_items) {
+        ci = s_ci[lane];
+        qi = s_qi[lane];
+        cx = s2[ci].coords2D[0];
+        cy = s2[ci].coords2D[1];
+      }
+      __pipeline_wait_prior(0);
+      __syncwarp();
+      // ---- 3. exact scores: sum over i of q[(i + tx) & 127] * c[(i + tx) & 127], i = 0..127 (matching.cu:84-89)
+      float score = NONE;
+      if (lane < n_items) {
+        const float *pq = sq + qi * RS_QS, *pb = sc + lane * RS_CS;
+        const int tx = ci & 15;
+        float sum = 0.0f;
+        // the first 112 steps never wrap on the query side (tx <= 15); only the last 16 need the mask
+        const float *qa = pq + tx;
+#pragma unroll
+        for (int i = 0; i < 112; i++) sum = __fmaf_rn(qa[i], pb[i], sum);
+#pragma unroll
+        for (int i = 112; i < 128; i++) sum = __fmaf_rn(pq[(i + tx) & 127], pb[i], sum);
+        score = kL2 ? __fsub_rn(2.0f, __fadd_rn(sum, sum)) : sum;
+      }
+      __syncwarp();
+      // scores and indices of the items go through shared memory (the staging tile's first row is done with)
+      float *s_sc = sc, *s_xy = sc + 32;          // 32 + 64 floats
+      if (lane < n_items) {
+        s_sc[lane] = score;
+        s_xy[2 * lane] = cx;
+        s_xy[2 * lane + 1] = cy;
+      }
+      __syncwarp();
+      // ---- 4. lane j = query j of the round: best = lowest (score, bitrev4(col % 16), col / 16) as FindMinCorr's
+      // winner, second = best score of the rest (an equal duplicate lands in `second`, matching.cu:229-235)
+      if (lane >= jb && lane < je && q0 + lane < n1) {
+        const int q = q0 + lane;
+        int a = 0, b = 0;
+#pragma unroll
+        for (int j = 0; j < RS_QPW; j++)
+          if (j == lane) a = start[j], b = start[j] + __popc(keepm[j]);
+        if (overflow_q & (1u << lane)) {
+          redo_flags[q >> 4] = 1;                 // the exact kernel redoes this block of 16 queries
+        } else {
+          auto better = [](float sa, int ia, float sb, int ib) {   // is a strictly preferred to b ?
+            if (ib < 0) return ia >= 0;
+            if (ia < 0) return false;
+            if (sa != sb) return kL2 ? (sa < sb) : (sa > sb);
+            const int ra = bitrev4(ia & 15), rb = bitrev4(ib & 15);
+            if (ra != rb) return ra < rb;
+            return ia < ib;
+          };
+          float bs = NONE;
+          int bi = -1, bw = 0;
+          for (int w = a; w < b; w++) {
+            const float os = s_sc[w];
+            const int oi = s_ci[w];
+            if (better(os, oi, bs, bi)) bs = os, bi = oi, bw = w;
+          }
+          float ss = NONE;
+          for (int w = a; w < b; w++)
+            if (s_ci[w] != bi) ss = kL2 ? fminf(ss, s_sc[w]) : fmaxf(ss, s_sc[w]);
+          csb_sift_point *o = s1 + q;
+          o->score = bs;
+          if (kL2) o->ambiguity = (float)((double)bs / ((double)ss + 1e-6));
+          else o->ambiguity = (float)((double)__fsub_rn(1.0f, bs) / ((double)__fsub_rn(1.0f, ss) + 1e-6));
+          o->match = bi;
+          if (bi >= 0) {
+            o->match_xpos = s_xy[2 * bw];
+            o->match_ypos = s_xy[2 * bw + 1];
+          }
+        }
+      }
+      __syncwarp();
+      jb = je;
     }
   }
 }
@@ -572,13 +718,29 @@ void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2,
                                                sl_val, sl_idx, n_splits, q_info, c_info);
 }
 
+size_t tc_shortlist_floats(int n) { return (size_t)tc_pad(n) * 4 * (TC_TOPK + 2); }   // entry values + (m1, m2) per split
+
 void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,
-                    int n_splits, int distance, int *redo_flags, int *redo_list, int *redo_count, cudaStream_t st) {
+                    int n_splits, int distance, const int *q_info, const int *c_info, int *redo_flags, int *redo_list,
+                    int *redo_count, cudaStream_t st) {
   const int n_blocks16 = (n1 + 15) / 16;
   cudaMemsetAsync(redo_flags, 0, sizeof(int) * n_blocks16, st);
   cudaMemsetAsync(redo_count, 0, sizeof(int), st);
-  const int blocks = (n1 * 32 + 127) / 128;
-  if (distance == 1) k_rescore<true><<<blocks, 128, 0, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, redo_flags);
-  else k_rescore<false><<<blocks, 128, 0, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, redo_flags);
+  constexpr size_t smem = RS_SMEM_WARP * RS_WARPS;
+  {   // > 48 KB of dynamic shared memory needs the opt-in, once per device
+    static bool opted[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
+      cudaFuncSetAttribute(k_rescore<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_rescore<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (dev >= 0 && dev < 64) opted[dev] = true;
+    }
+  }
+  const int blocks = (n1 + RS_WARPS * RS_QPW - 1) / (RS_WARPS * RS_QPW);
+  if (distance == 1)
+    k_rescore<true><<<blocks, RS_WARPS * 32, smem, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, tc_pad(n1), q_info, c_info, redo_flags);
+  else
+    k_rescore<false><<<blocks, RS_WARPS * 32, smem, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, tc_pad(n1), q_info, c_info, redo_flags);
   k_collect_redo<<<(n_blocks16 + 255) / 256, 256, 0, st>>>(redo_flags, n_blocks16, redo_list, redo_count);
 }

@@ -30,6 +30,10 @@ __global__ void __launch_bounds__(256) k(unsigned *out, unsigned a, unsigned b, 
       } else if (MODE == 4) {                                                     // HSET2
         x[i] = __heq2_mask(*reinterpret_cast<__half2 *>(&x[i]), *reinterpret_cast<__half2 *>(&x[(i + 1) & 7])) ^ a;
       } else if (MODE == 5) x[i] = __shfl_down_sync(0xffffffffu, x[i], 1) + a;    // SHFL
+      else if (MODE == 7) x[i] = hmax2(x[i], x[(i + 3) & 7]);                     // 2-input alone
+      else if (MODE == 8) { __half2 h = __hmax2(*reinterpret_cast<__half2 *>(&x[i]), *reinterpret_cast<__half2 *>(&x[(i + 3) & 7])); x[i] = *reinterpret_cast<unsigned *>(&h); }
+      else if (MODE == 9) { __half2 h = __hfma2(*reinterpret_cast<__half2 *>(&x[i]), *reinterpret_cast<__half2 *>(&x[(i + 3) & 7]), *reinterpret_cast<__half2 *>(&a)); x[i] = *reinterpret_cast<unsigned *>(&h); }
+      else if (MODE == 10) { f[i] = -f[i] * fa; __half2 p = __floats2half2_rn(f[i], f[(i + 1) & 7]); x[i] = *reinterpret_cast<unsigned *>(&p); }   // F2FP + FMUL
       else if (MODE == 6) f[i] = fmaxf(fmaxf(f[i], fa), f[(i + 1) & 7]);           // FMNMX3 fp32
     }
   }
@@ -63,5 +67,9 @@ int main() {
   run<4>("HSET2.EQ + LOP3");
   run<5>("SHFL + IADD");
   run<6>("FMNMX3 fp32");
+  run<7>("max.f16x2 2-input");
+  run<8>("__hmax2");
+  run<9>("HFMA2");
+  run<10>("F2FP + FMUL");
   return 0;
 }
