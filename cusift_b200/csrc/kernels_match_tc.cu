@@ -39,6 +39,16 @@
 //                               Any candidate left out has exact dot < m2 - eps <= the exact dots
 //                               of at least two listed ones, so the exact best and second best
 //                               are always in the list.  1.25 passes of MMA instead of 2.
+//     What bounds it (measured on the B200, 8192 x 8192, ablation builds): with the epilogue arithmetic removed the
+//     kernel takes 23 us for 1.25 sweeps - the TMEM READ PORT: 64 B/clk per SM, i.e. 14.4 us for one pass over the
+//     8192^2 fp32 scores on 148 SMs, whatever the MMA shape (N = 256 with two accumulators: 70 B/clk, N = 128 with four:
+//     57 B/clk, 16-column loads from sixteen warps: 64 B/clk).  The MMAs themselves need 15.6 us.  With the arithmetic
+//     the kernel takes 31 us: one epilogue warp turns over ~6 B/clk (load -> wait -> dependent max chains -> rare
+//     divergent append), eight of them 45 B/clk.  Tried on top of this design and measured slower or equal: sixteen
+//     epilogue warps on column halves (more threads per row = more hits: each thread's threshold only knows its own
+//     columns), thresholds shared between the CTAs of a query tile through global memory (the hits a shared bound
+//     would save happen in the first tiles of sweep 2, before anything published can arrive), a common sample of tiles
+//     as sweep 1 in every CTA (1.5 sweeps of TMEM reads), sweep 1 over an eighth of the slice (raw lists overflow).
 //  3. k_rescore      warp per query: exact fp32 scores of the listed candidates in the
 //                    reference's rotated k order (bit-identical to ComputeDistance), then the
 //                    reference's best / second-best rule incl. its tie-breaking
@@ -162,7 +172,9 @@ constexpr uint32_t IDESC_F16_M128 = (1u << 4)                 // D format = F32
 // Packed layout (per set): two K-halves; half kb is a [n_pad][64] fp16 matrix (128-byte rows) in
 // which the 16-byte chunk c of row r is stored at chunk position c ^ (r & 7) (128B swizzle).
 // Also validates the domain of the error bound and measures its ingredients (see the header): info[0] is set when a
-// row has a non-finite / fp16-overflowing element or a squared norm above TC_MAX_NORM2; info[1] receives (as float
+// row has a non-finite / fp16-overflowing element or a squared norm above TC_MAX_NORM2, or when a set that needs
+// padding rows (n not a multiple of 256) has a negative element (the scan treats the padding's score 0 as a lower
+// bound of real scores, which only holds for non-negative descriptors - every SIFT / RootSIFT descriptor is); info[1] receives (as float
 // bits) the largest squared rounding-error norm |q - fp16(q)|^2 over the rows.  The caller zeroes info[0..1].
 __global__ void __launch_bounds__(256) k_pack_f16(const csb_sift_point *__restrict__ pts, int n, int n_pad,
                                                   __half *__restrict__ packed, int *__restrict__ info) {
@@ -183,6 +195,7 @@ __global__ void __launch_bounds__(256) k_pack_f16(const csb_sift_point *__restri
       const float de = f - __half2float(v[i]);             // exact (Sterbenz / representable difference)
       es = __fmaf_rn(de, de, es);
       bad = bad || !(fabsf(f) <= 65504.0f);               // NaN, inf, or beyond the fp16 range
+      bad = bad || (f < 0.0f && n < n_pad);               // padding rows score 0: only below every real score if those are >= 0
     }
   } else {
 #pragma unroll
@@ -317,7 +330,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
     // ---- sweep 1: m1 = largest approximate dot product of this row among the tiles seen, m2 = second largest
     // CHUNK maximum (chunks of 32 columns).  m2 <= the true second largest value, so thr = m2 - 2 eps is a valid
     // (slightly more inclusive) listing threshold, and a chunk costs 16 three-input max + 3 ops instead
-    // of 96 (FMNMX runs at half rate).  Padding columns hold 0.
+    // of 96 (FMNMX runs at half rate).  Padding columns hold 0: never above a real score, because sets with
+    // padding rows are checked to be non-negative (k_pack_f16).
     // TMEM reads are software-pipelined: the tcgen05.ld of the next 64 columns is in flight while the
     // current 64 are reduced (tcgen05.wait::ld waits for every outstanding load, so it sits after the
     // arithmetic), and the accumulator is handed back to the MMA warp as soon as its last columns are in
@@ -415,15 +429,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
         thr = m2 - eps2;
       }
     };
+    // The first 32 columns of tile it + 1 are requested before the last 32 of tile it are examined (the MMA warp is
+    // up to two accumulators ahead), so the TMEM read port does not wait for the arithmetic at a tile boundary.
+    uint32_t ra[32], rb[32];
+    if (it < n_iter) {
+      mbar_wait(acc_full + qh * 2 + (it & 1), (it >> 1) & 1);
+      tc_fence_after();
+      tc_ld32(tlane + (uint32_t)((it & 1) * TC_CT), ra);
+    }
     for (; it < n_iter; it++) {
       const int a = it & 1;
       const uint32_t taddr = tlane + (uint32_t)(a * TC_CT);
       const bool unseen = it < n_iter - n1;
       const int col0 = tile_of(it) * TC_CT;
-      mbar_wait(acc_full + qh * 2 + a, (it >> 1) & 1);
-      tc_fence_after();
-      uint32_t ra[32], rb[32];
-      tc_ld32(taddr, ra);
       tc_ld_wait();
       tc_ld32(taddr + 32, rb);
       list32(ra, col0, unseen);
@@ -436,6 +454,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
       tc_ld_wait();
       tc_fence_before();
       mbar_arrive(acc_empty + qh * 2 + a);
+      if (it + 1 < n_iter) {
+        mbar_wait(acc_full + qh * 2 + (a ^ 1), ((it + 1) >> 1) & 1);
+        tc_fence_after();
+        tc_ld32(tlane + (uint32_t)((a ^ 1) * TC_CT), ra);
+      }
       list32(rb, col0 + 96, unseen);
     }
     // the threshold is final: keep the entries that reach it (each thread reads back its own writes only).
@@ -698,8 +721,8 @@ void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *info, 
   k_pack_f16<<<(threads + 255) / 256, 256, 0, st>>>(pts, n, n_pad, reinterpret_cast<__half *>(packed), info);
 }
 
-void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
-                     const int *q_info, const int *c_info, cudaStream_t st) {
+int launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
+                    const int *q_info, const int *c_info, cudaStream_t st) {
   const int nq_pad = tc_pad(n1), nc_pad = tc_pad(n2);
   const int ctiles = nc_pad / TC_CT;
   const int tiles_per_split = (ctiles + n_splits - 1) / n_splits;
@@ -716,6 +739,7 @@ void launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2,
   k_match_tc<<<grd, TC_THREADS, SMEM_TC, st>>>(reinterpret_cast<const __half *>(q_packed), nq_pad,
                                                reinterpret_cast<const __half *>(c_packed), n2, nc_pad, tiles_per_split,
                                                sl_val, sl_idx, n_splits, q_info, c_info);
+  return (int)cudaPeekAtLastError();   // a failed launch must not be overwritten by the launches that follow
 }
 
 size_t tc_shortlist_floats(int n) { return (size_t)tc_pad(n) * 4 * (TC_TOPK + 2); }   // entry values + (m1, m2) per split

@@ -805,21 +805,24 @@ def test_allpairs_with_improve_vs_oracle(gpu_ctx):
             gpu_ctx.free(d)
 
 
-@pytest.mark.parametrize("kind", ["scaled_x10", "signed", "range_0_255", "huge", "norm_1p01"])
+@pytest.mark.parametrize("kind", ["scaled_x10", "signed", "signed_padded", "range_0_255", "huge", "norm_1p01"])
 def test_match_descriptors_outside_the_fp16_domain_use_the_exact_kernel(gpu_ctx, kind):
     """MatchSiftData accepts ANY SiftPoint.data (extras/matching.cu:232-362 is plain fp32).  The tensor-core prefilter's
-    error bound needs descriptors that are finite in fp16 with squared norm <= 1.002; k_pack_f16 checks that and the
-    call falls back to the exact fp32 kernel otherwise.  Results must equal the oracle bit for bit either way."""
-    n1, n2 = 700, 1500
+    error bound needs descriptors that are finite in fp16 with squared norm <= 1.002 - and non-negative when the set
+    needs padding rows (their score 0 must not exceed a real score); k_pack_f16 checks that and the call falls back to
+    the exact fp32 kernel otherwise.  Results must equal the oracle bit for bit either way."""
+    n1, n2 = (700, 1536) if kind == "signed" else (700, 1500)
     a, b = _rand_set(n1, 501), _rand_set(n2, 502)
     r = np.random.default_rng(9)
     expect_fallback = True
     if kind == "scaled_x10":
         a["data"] *= 10.0
         b["data"] *= 10.0
-    elif kind == "signed":                                    # unit norm, mixed signs: still inside the domain
+    elif kind == "signed":                                    # unit norm, mixed signs, no padding rows: inside the domain
         b["data"] *= r.choice([-1.0, 1.0], b["data"].shape).astype(np.float32)
         expect_fallback = False
+    elif kind == "signed_padded":                             # the same with 36 padding rows in the candidate set
+        b["data"] *= r.choice([-1.0, 1.0], b["data"].shape).astype(np.float32)
     elif kind == "range_0_255":
         a["data"] = np.round(a["data"] * 512).clip(0, 255)
         b["data"] = np.round(b["data"] * 512).clip(0, 255)
