@@ -1165,7 +1165,7 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
     {
       LaunchScope ls(ctx, s, "match_tc");
       CSB_CHECK(ctx, (cudaError_t)launch_match_tc(ctx->tc_pack[0], n1, ctx->tc_pack[1], n2, splits, ctx->tc_val, ctx->tc_idx,
-                                                  ctx->tc_count + 4, ctx->tc_count + 6, s->stream));
+                                                  ctx->tc_count + 4, ctx->tc_count + 6, ctx->tc_flags, ctx->tc_count, s->stream));
     }
     {
       LaunchScope ls(ctx, s, "match_rescore");
@@ -1463,7 +1463,7 @@ int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_s
       if (use_tc && n1 >= 256 && n2 >= 256 && in_domain) {
         const int splits = tc_splits(n1, n2, ctx->sm_count);
         CSB_CHECK(ctx, (cudaError_t)launch_match_tc(packed[i], n1, packed[j], n2, splits, c.sl_val, c.sl_idx, ctx->ap_flags + 2 * i,
-                                                    ctx->ap_flags + 2 * j, c.st));
+                                                    ctx->ap_flags + 2 * j, c.flags, c.cnt, c.st));
         launch_rescore(s1, n1, s2, n2, c.sl_val, c.sl_idx, splits, distance, ctx->ap_flags + 2 * i, ctx->ap_flags + 2 * j, c.flags,
                        c.list, c.cnt, c.st);
         launch_match_blocks(s1, n1, s2, n2, distance, c.list, c.cnt, (n1 + 15) / 16, c.part, c.st);

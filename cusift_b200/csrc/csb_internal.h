@@ -139,8 +139,9 @@ int tc_splits(int n1, int n2, int sm_count);
 // info = 2 device ints zeroed by the caller: [0] set when the set violates the fp16 error bound's precondition,
 // [1] = float bits of the largest squared fp16 rounding-error norm of a row (the pair's eps is derived from it)
 void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *info, cudaStream_t st);
+// resets redo_flags[(n1 + 15) / 16] and *redo_count for the launch_rescore that must follow; returns the launch's cudaError_t
 int launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
-                    const int *q_info, const int *c_info, cudaStream_t st);   // returns the launch's cudaError_t
+                    const int *q_info, const int *c_info, int *redo_flags, int *redo_count, cudaStream_t st);
 void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,
                     int n_splits, int distance, const int *q_info, const int *c_info, int *redo_flags, int *redo_list,
                     int *redo_count, cudaStream_t st);

@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
                                                             const __half *__restrict__ c_packed, int nc, int nc_pad,
                                                             int tiles_per_split, float *__restrict__ out_val,
                                                             int *__restrict__ out_idx, int n_splits,
-                                                            const int *__restrict__ q_info, const int *__restrict__ c_info) {
+                                                            const int *__restrict__ q_info, const int *__restrict__ c_info,
+                                                            int *__restrict__ redo_flags, int n_redo_flags,
+                                                            int *__restrict__ redo_count) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment for the swizzle atoms
   unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -266,6 +268,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the rescoring kernel that follows appends the 16-query blocks it cannot prove to this list: reset it here
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < n_redo_flags; i += blockDim.x) redo_flags[i] = 0;
+    if (threadIdx.x == 0) *redo_count = 0;
+  }
 
   if (warp == 0) {
     // ===== producer =====
@@ -518,7 +525,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__res
                                                            const csb_sift_point *__restrict__ s2, int n2,
                                                            const float *__restrict__ sl_val, const int *__restrict__ sl_idx,
                                                            int n_splits, int nq_pad, const int *__restrict__ q_info,
-                                                           const int *__restrict__ c_info, int *__restrict__ redo_flags) {
+                                                           const int *__restrict__ c_info, int *__restrict__ redo_flags,
+                                                           int *__restrict__ redo_list, int *__restrict__ redo_count) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *sq = reinterpret_cast<float *>(rs_smem + wib * RS_SMEM_WARP);   // [RS_QPW][RS_QS]
@@ -659,7 +667,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__res
         for (int j = 0; j < RS_QPW; j++)
           if (j == lane) a = start[j], b = start[j] + __popc(keepm[j]);
         if (overflow_q & (1u << lane)) {
-          redo_flags[q >> 4] = 1;                 // the exact kernel redoes this block of 16 queries
+          // the exact kernel redoes this block of 16 queries; the first query to flag a block lists it
+          if (atomicExch(redo_flags + (q >> 4), 1) == 0) redo_list[atomicAdd(redo_count, 1)] = q >> 4;
         } else {
           auto better = [](float sa, int ia, float sb, int ib) {   // is a strictly preferred to b ?
             if (ib < 0) return ia >= 0;
@@ -696,12 +705,6 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__res
   }
 }
 
-// Compacts the flagged 16-query blocks into a list for the exact kernel.
-__global__ void k_collect_redo(const int *__restrict__ flags, int n_blocks, int *__restrict__ list, int *__restrict__ count) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_blocks && flags[i]) list[atomicAdd(count, 1)] = i;
-}
-
 }  // namespace
 
 size_t tc_packed_bytes(int n) { return (size_t)((n + TC_QT - 1) / TC_QT * TC_QT) * 256; }
@@ -722,7 +725,7 @@ void launch_pack_f16(const csb_sift_point *pts, int n, void *packed, int *info, 
 }
 
 int launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, int n_splits, float *sl_val, int *sl_idx,
-                    const int *q_info, const int *c_info, cudaStream_t st) {
+                    const int *q_info, const int *c_info, int *redo_flags, int *redo_count, cudaStream_t st) {
   const int nq_pad = tc_pad(n1), nc_pad = tc_pad(n2);
   const int ctiles = nc_pad / TC_CT;
   const int tiles_per_split = (ctiles + n_splits - 1) / n_splits;
@@ -738,7 +741,7 @@ int launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, 
   dim3 grd(nq_pad / TC_QT, n_splits);
   k_match_tc<<<grd, TC_THREADS, SMEM_TC, st>>>(reinterpret_cast<const __half *>(q_packed), nq_pad,
                                                reinterpret_cast<const __half *>(c_packed), n2, nc_pad, tiles_per_split,
-                                               sl_val, sl_idx, n_splits, q_info, c_info);
+                                               sl_val, sl_idx, n_splits, q_info, c_info, redo_flags, (n1 + 15) / 16, redo_count);
   return (int)cudaPeekAtLastError();   // a failed launch must not be overwritten by the launches that follow
 }
 
@@ -747,9 +750,7 @@ size_t tc_shortlist_floats(int n) { return (size_t)tc_pad(n) * 4 * (TC_TOPK + 2)
 void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,
                     int n_splits, int distance, const int *q_info, const int *c_info, int *redo_flags, int *redo_list,
                     int *redo_count, cudaStream_t st) {
-  const int n_blocks16 = (n1 + 15) / 16;
-  cudaMemsetAsync(redo_flags, 0, sizeof(int) * n_blocks16, st);
-  cudaMemsetAsync(redo_count, 0, sizeof(int), st);
+  // redo_flags / redo_count were reset by k_match_tc (launch_match_tc), which must precede this call on the stream
   constexpr size_t smem = RS_SMEM_WARP * RS_WARPS;
   {   // > 48 KB of dynamic shared memory needs the opt-in, once per device
     static bool opted[64] = {};
@@ -763,8 +764,7 @@ void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2
   }
   const int blocks = (n1 + RS_WARPS * RS_QPW - 1) / (RS_WARPS * RS_QPW);
   if (distance == 1)
-    k_rescore<true><<<blocks, RS_WARPS * 32, smem, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, tc_pad(n1), q_info, c_info, redo_flags);
+    k_rescore<true><<<blocks, RS_WARPS * 32, smem, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, tc_pad(n1), q_info, c_info, redo_flags, redo_list, redo_count);
   else
-    k_rescore<false><<<blocks, RS_WARPS * 32, smem, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, tc_pad(n1), q_info, c_info, redo_flags);
-  k_collect_redo<<<(n_blocks16 + 255) / 256, 256, 0, st>>>(redo_flags, n_blocks16, redo_list, redo_count);
+    k_rescore<false><<<blocks, RS_WARPS * 32, smem, st>>>(s1, n1, s2, n2, sl_val, sl_idx, n_splits, tc_pad(n1), q_info, c_info, redo_flags, redo_list, redo_count);
 }
