@@ -10,6 +10,7 @@
 //                     Crout LU / implicit pivoting in the reference's operation order
 //   k_score         : one warp per hypothesis, inlier test with the reference's
 //                     round-toward-zero products (__fmul_rz), shuffle sum
+#include <cooperative_groups.h>
 #include "csb_internal.h"
 
 namespace {
@@ -184,17 +185,46 @@ struct ImproveJob {
   int *numfit_out;
 };
 #define IH_NT 256
+#define IH_CL 8             // CTAs per job: one thread-block cluster
+#define IH_PPT 4            // points per thread kept in registers
 #define IH_NACC 44          // 36 upper-triangle entries of M + 8 of X
 __device__ __forceinline__ int ih_tri(int r, int c) { return r * 8 - r * (r - 1) / 2 + (c - r); }   // r <= c
 
-__global__ void __launch_bounds__(IH_NT) k_improve_homography(const ImproveJob *__restrict__ jobs, int num_loops,
-                                                              float min_score, float max_amb, float limit) {
+// One CLUSTER of IH_CL CTAs per job (the first version ran a job on one CTA: 270 us for 8192 points and 5 loops, all of it
+// latency - 32 points per thread and loop, each a chain of fp64 divisions and multiply-adds).  Every CTA accumulates the
+// normal equations over its share of the points; the partial sums meet in CTA 0 through distributed shared memory
+// (fixed order: results do not depend on timing), thread 0 there solves the 8 x 8 system, and the new H travels back
+// the same way.  Two cluster barriers per loop.
+__global__ void __cluster_dims__(IH_CL, 1, 1) __launch_bounds__(IH_NT)
+    k_improve_homography(const ImproveJob *__restrict__ jobs, int num_loops, float min_score, float max_amb, float limit) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ double s_part[IH_NT / 32][IH_NACC];
+  __shared__ double s_cta[IH_NACC];      // this CTA's sums (read by CTA 0)
+  __shared__ double s_tot[IH_NACC];      // CTA 0: sums over the cluster
+  __shared__ double s_new[8];            // CTA 0: the solution of this loop (read by everybody)
   __shared__ double s_A[8];
   __shared__ int s_cnt[IH_NT / 32];
-  const ImproveJob J = jobs[blockIdx.x];
+  __shared__ int s_fit;
+  const ImproveJob J = jobs[blockIdx.x / IH_CL];
+  const int rank = (int)cluster.block_rank();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < 8) s_A[threadIdx.x] = (double)(J.H_in[threadIdx.x] / J.H_in[8]);   // float division, as the reference
+  // the thread's first IH_PPT points stay in registers for all loops (8192 points = 4 per thread): the loops then
+  // run without memory latency and the points' division chains overlap
+  float px[IH_PPT], py[IH_PPT], pmx[IH_PPT], pmy[IH_PPT];
+  bool pok[IH_PPT];
+#pragma unroll
+  for (int k = 0; k < IH_PPT; k++) {
+    const int i = rank * IH_NT + threadIdx.x + k * IH_CL * IH_NT;
+    pok[k] = false;
+    px[k] = py[k] = pmx[k] = pmy[k] = 0.0f;
+    if (i < J.n) {
+      const csb_sift_point &pt = J.pts[i];
+      pok[k] = !(pt.score < min_score || pt.ambiguity > max_amb);
+      px[k] = pt.coords2D[0], py[k] = pt.coords2D[1], pmx[k] = pt.match_xpos, pmy[k] = pt.match_ypos;
+    }
+  }
   __syncthreads();
   for (int loop = 0; loop < num_loops; loop++) {
     double A[8];
@@ -203,10 +233,7 @@ __global__ void __launch_bounds__(IH_NT) k_improve_homography(const ImproveJob *
     double acc[IH_NACC];
 #pragma unroll
     for (int i = 0; i < IH_NACC; i++) acc[i] = 0.0;
-    for (int i = threadIdx.x; i < J.n; i += IH_NT) {
-      const csb_sift_point &pt = J.pts[i];
-      if (pt.score < min_score || pt.ambiguity > max_amb) continue;
-      const float x = pt.coords2D[0], y = pt.coords2D[1], mx = pt.match_xpos, my = pt.match_ypos;
+    auto add_point = [&](float x, float y, float mx, float my) {
       const float den = (float)(A[6] * x + A[7] * y + 1.0f);
       const float dx = (float)((A[0] * x + A[1] * y + A[2]) / den - mx);
       const float dy = (float)((A[3] * x + A[4] * y + A[5]) / den - my);
@@ -228,6 +255,14 @@ __global__ void __launch_bounds__(IH_NT) k_improve_homography(const ImproveJob *
         if (r < 3 || r >= 6) acc[36 + r] += Yx[r] * ax;
         if (r >= 3) acc[36 + r] += Yy[r] * ay;
       }
+    };
+#pragma unroll
+    for (int k = 0; k < IH_PPT; k++)
+      if (pok[k]) add_point(px[k], py[k], pmx[k], pmy[k]);
+    for (int i = rank * IH_NT + threadIdx.x + IH_PPT * IH_CL * IH_NT; i < J.n; i += IH_CL * IH_NT) {   // sets beyond 8192 points
+      const csb_sift_point &pt = J.pts[i];
+      if (pt.score < min_score || pt.ambiguity > max_amb) continue;
+      add_point(pt.coords2D[0], pt.coords2D[1], pt.match_xpos, pt.match_ypos);
     }
 #pragma unroll
     for (int i = 0; i < IH_NACC; i++) {
@@ -237,52 +272,74 @@ __global__ void __launch_bounds__(IH_NT) k_improve_homography(const ImproveJob *
       if (lane == 0) s_part[warp][i] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double M[8][8], X[8], L[8][8];
-      for (int r = 0; r < 8; r++) {
-        for (int c = r; c < 8; c++) {
-          double v = 0.0;
-          for (int w = 0; w < IH_NT / 32; w++) v += s_part[w][ih_tri(r, c)];
-          M[r][c] = M[c][r] = v;
-        }
+    if (threadIdx.x < IH_NACC) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < IH_NT / 32; w++) v += s_part[w][threadIdx.x];
+      s_cta[threadIdx.x] = v;
+    }
+    cluster.sync();                                  // every CTA's s_cta is complete
+    if (rank == 0) {
+      if (threadIdx.x < IH_NACC) {
         double v = 0.0;
-        for (int w = 0; w < IH_NT / 32; w++) v += s_part[w][36 + r];
-        X[r] = v;
+        for (int r = 0; r < IH_CL; r++) v += cluster.map_shared_rank(s_cta, r)[threadIdx.x];
+        s_tot[threadIdx.x] = v;
       }
-      bool spd = true;
-      for (int i = 0; i < 8 && spd; i++)
-        for (int j = 0; j <= i; j++) {
-          double sacc = M[i][j];
-          for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
-          if (i == j) {
-            if (!(sacc > 0.0)) { spd = false; break; }
-            L[i][i] = sqrt(sacc);
-          } else {
-            L[i][j] = sacc / L[j][j];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        // Cholesky M = L L^T with reciprocal diagonals (one rsqrt per column instead of a square root and up to
+        // seven fp64 divisions, which were 8 us of serial latency per loop), then the two triangular solves.  Fully
+        // unrolled: L lives in registers, M and X are read from shared memory where they are needed.
+        double L[8][8], inv[8];
+        bool spd = true;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          double d = s_tot[ih_tri(j, j)];
+#pragma unroll
+          for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+          spd = spd && (d > 0.0);
+          inv[j] = rsqrt(d);
+          L[j][j] = d * inv[j];
+#pragma unroll
+          for (int i = j + 1; i < 8; i++) {
+            double sacc = s_tot[ih_tri(j, i)];
+#pragma unroll
+            for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
+            L[i][j] = sacc * inv[j];
           }
         }
-      if (spd) {
-        double yv[8], Av[8];
+        double Av[8], yv[8];
+#pragma unroll
         for (int i = 0; i < 8; i++) {
-          double sacc = X[i];
+          double sacc = s_tot[36 + i];
+#pragma unroll
           for (int k = 0; k < i; k++) sacc -= L[i][k] * yv[k];
-          yv[i] = sacc / L[i][i];
+          yv[i] = sacc * inv[i];
         }
+#pragma unroll
         for (int i = 7; i >= 0; i--) {
           double sacc = yv[i];
+#pragma unroll
           for (int k = i + 1; k < 8; k++) sacc -= L[k][i] * Av[k];
-          Av[i] = sacc / L[i][i];
+          Av[i] = sacc * inv[i];
         }
-        for (int i = 0; i < 8; i++) s_A[i] = Av[i];
+        if (!spd) {                                  // not positive definite (NaNs above are discarded): H stays as it is
+#pragma unroll
+          for (int i = 0; i < 8; i++) Av[i] = s_A[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) s_new[i] = Av[i];
       }
     }
+    cluster.sync();                                  // CTA 0's s_new is complete; nobody reads s_cta any more
+    if (threadIdx.x < 8) s_A[threadIdx.x] = cluster.map_shared_rank(s_new, 0)[threadIdx.x];
     __syncthreads();
   }
   double A[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) A[i] = s_A[i];
   int numfit = 0;
-  for (int i = threadIdx.x; i < J.n; i += IH_NT) {
+  for (int i = rank * IH_NT + threadIdx.x; i < J.n; i += IH_CL * IH_NT) {
     csb_sift_point &pt = J.pts[i];
     const float x = pt.coords2D[0], y = pt.coords2D[1];
     const float den = (float)(A[6] * x + A[7] * y + 1.0);
@@ -299,10 +356,19 @@ __global__ void __launch_bounds__(IH_NT) k_improve_homography(const ImproveJob *
   if (threadIdx.x == 0) {
     int tot = 0;
     for (int w = 0; w < IH_NT / 32; w++) tot += s_cnt[w];
-    *J.numfit_out = tot;
+    s_fit = tot;
   }
-  if (threadIdx.x < 8) J.H_out[threadIdx.x] = (float)A[threadIdx.x];
-  if (threadIdx.x == 8) J.H_out[8] = 1.0f;
+  cluster.sync();
+  if (rank == 0) {
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int r = 0; r < IH_CL; r++) tot += *cluster.map_shared_rank(&s_fit, r);
+      *J.numfit_out = tot;
+    }
+    if (threadIdx.x < 8) J.H_out[threadIdx.x] = (float)A[threadIdx.x];
+    if (threadIdx.x == 8) J.H_out[8] = 1.0f;
+  }
+  cluster.sync();                                    // remote shared memory stays valid until CTA 0 has read it
 }
 
 // TestHomographies (homography.cu:139-192): inliers of every hypothesis over ALL numPts points.
@@ -486,7 +552,7 @@ void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_c
 void launch_improve_homography(const void *d_jobs, int n_jobs, int num_loops, float min_score, float max_amb, float limit,
                                cudaStream_t st) {
   if (n_jobs <= 0) return;
-  k_improve_homography<<<n_jobs, IH_NT, 0, st>>>(reinterpret_cast<const ImproveJob *>(d_jobs), num_loops, min_score, max_amb,
+  k_improve_homography<<<n_jobs * IH_CL, IH_NT, 0, st>>>(reinterpret_cast<const ImproveJob *>(d_jobs), num_loops, min_score, max_amb,
                                                  limit);
 }
 size_t improve_job_bytes() { return sizeof(ImproveJob); }
