@@ -51,8 +51,12 @@ __global__ void __launch_bounds__(256) k_match(csb_sift_point *__restrict__ s1, 
                                                const csb_sift_point *__restrict__ s2, int n2, int chunks,
                                                const int *__restrict__ block_list, const int *__restrict__ block_count,
                                                int cps, MatchPart *__restrict__ part) {
-  __shared__ float A[16][128];
-  __shared__ float B[16][128];
+  // MG candidate chunks (of 16) are scored together: thread (tx, ty) runs MG independent chains - candidates tx,
+  // tx + 16, ... of the super-chunk share the rotation tx, hence the query operand - which hides the FFMA latency
+  // and quarters the barriers (one chain at a time cost 3 us per chunk: 50 us to redo a single block of 16 queries).
+  constexpr int MG = 4;
+  __shared__ float A[16][144];   // row stride 144: the two query rows of a warp (ty, ty + 1) read disjoint halves of the banks
+  __shared__ float B[16 * MG][128];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int n_blk = kPartial ? *block_count : (int)gridDim.x;
   for (int bi = blockIdx.x; bi < n_blk; bi += gridDim.x) {
@@ -70,37 +74,48 @@ __global__ void __launch_bounds__(256) k_match(csb_sift_point *__restrict__ s1, 
   float best = init, second = init;
   int idx = -1;
 
-  float pre[8];                                   // next chunk of candidates, in flight during the dot products
-  if (c_begin < c_end) {
-    const float *ptr2 = s2[min(n2 - 1, c_begin * 16 + ty)].data;
+  float pre[MG][8];                               // next super-chunk of candidates, in flight during the dot products
+  auto fetch = [&](int c) {                       // rows 16 (c + g) + ty, clamped (chunks past the end are never scored)
 #pragma unroll
-    for (int i = 0; i < 8; i++) pre[i] = ptr2[16 * i + tx];
-  }
-  for (int c = c_begin; c < c_end; c++) {
-    __syncthreads();
+    for (int g = 0; g < MG; g++) {
+      const float *ptr2 = s2[min(n2 - 1, (c + g) * 16 + ty)].data;
 #pragma unroll
-    for (int i = 0; i < 8; i++) B[ty][16 * i + tx] = pre[i];
-    __syncthreads();
-    if (c + 1 < c_end) {
-      const float *ptr2 = s2[min(n2 - 1, (c + 1) * 16 + ty)].data;
-#pragma unroll
-      for (int i = 0; i < 8; i++) pre[i] = ptr2[16 * i + tx];
+      for (int i = 0; i < 8; i++) pre[g][i] = ptr2[16 * i + tx];
     }
-    float sum = 0.0f;
-#pragma unroll 16
+  };
+  if (c_begin < c_end) fetch(c_begin);
+  for (int c = c_begin; c < c_end; c += MG) {
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < MG; g++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) B[16 * g + ty][16 * i + tx] = pre[g][i];
+    __syncthreads();
+    if (c + MG < c_end) fetch(c + MG);
+    float sum[MG];
+#pragma unroll
+    for (int g = 0; g < MG; g++) sum[g] = 0.0f;
+#pragma unroll 8
     for (int i = 0; i < 128; i++) {
       const int k = (i + tx) & 127;
-      sum = __fmaf_rn(A[ty][k], B[tx][k], sum);
+      const float a = A[ty][k];
+#pragma unroll
+      for (int g = 0; g < MG; g++) sum[g] = __fmaf_rn(a, B[16 * g + tx][k], sum[g]);
     }
-    const int p2 = c * 16 + tx;
-    float val = (p2 < n2) ? sum : -1.0f;
-    if (kL2) val = (val > -1.0f) ? __fsub_rn(2.0f, __fadd_rn(val, val)) : 999.0f;
-    if (better<kL2>(val, best)) {
-      second = best;
-      best = val;
-      idx = p2;
-    } else if (better<kL2>(val, second)) {
-      second = val;
+#pragma unroll
+    for (int g = 0; g < MG; g++) {               // ascending columns: the running scan of FindMinCorr's lane
+      if (c + g < c_end) {
+        const int p2 = (c + g) * 16 + tx;
+        float val = (p2 < n2) ? sum[g] : -1.0f;
+        if (kL2) val = (val > -1.0f) ? __fsub_rn(2.0f, __fadd_rn(val, val)) : 999.0f;
+        if (better<kL2>(val, best)) {
+          second = best;
+          best = val;
+          idx = p2;
+        } else if (better<kL2>(val, second)) {
+          second = val;
+        }
+      }
     }
   }
 
@@ -131,40 +146,52 @@ __global__ void __launch_bounds__(256) k_match(csb_sift_point *__restrict__ s1, 
 
 __device__ __forceinline__ int bitrev4(int x) { return ((x & 1) << 3) | ((x & 2) << 1) | ((x & 4) >> 1) | ((x & 8) >> 3); }
 
-// Merges the candidate slices of the redo pass: thread = one query of one listed block.
+// Merges the candidate slices of the redo pass: WARP = one query of one listed block, lane = slice (the first
+// version walked the 32 slices in one thread: 32 dependent L2 round trips, 22 us for a handful of blocks).  The
+// merge - winner = minimum of the total order (score, bitrev4(col % 16), col / 16), runner-up = best of all the
+// other scores - is associative and commutative, so a shuffle tree gives the result of the serial scan.
 template <bool kL2>
-__global__ void k_match_finish(csb_sift_point *__restrict__ s1, int n1, const csb_sift_point *__restrict__ s2,
-                               const int *__restrict__ block_list, const int *__restrict__ block_count, int n_slices,
-                               const MatchPart *__restrict__ part) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = t >> 4, ty = t & 15;
-  if (b >= *block_count) return;
+__global__ void __launch_bounds__(128) k_match_finish(csb_sift_point *__restrict__ s1, int n1, const csb_sift_point *__restrict__ s2,
+                                                      const int *__restrict__ block_list, const int *__restrict__ block_count,
+                                                      int n_slices, const MatchPart *__restrict__ part) {
+  static_assert(CSB_REDO_SLICES <= 32, "one lane per slice");
+  const int lane = threadIdx.x & 31;
+  const int n_q = *block_count * 16;
+  for (int wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wq < n_q; wq += (gridDim.x * blockDim.x) >> 5) {
+  const int b = wq >> 4, ty = wq & 15;
   const float init = kL2 ? 999.0f : -1.0f;
   float best = init, second = init;
   int idx = -1;
-  for (int y = 0; y < n_slices; y++) {
-    const MatchPart p = part[((size_t)b * n_slices + y) * 16 + ty];
-    if (p.idx < 0) continue;                         // empty slice
-    bool take;                                       // is p's winner preferred to the running one ?
+  if (lane < n_slices) {
+    const MatchPart p = part[((size_t)b * n_slices + lane) * 16 + ty];
+    if (p.idx >= 0) best = p.best, second = p.second, idx = p.idx;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (oi < 0) continue;                            // the other side is empty (warp-uniform per pair of lanes: no shuffle follows)
+    bool take;                                       // is the other side's winner preferred to ours ?
     if (idx < 0) take = true;
-    else if (p.best != best) take = better<kL2>(p.best, best);
+    else if (ob != best) take = better<kL2>(ob, best);
     else {
-      const int ra = bitrev4(p.idx & 15), rb = bitrev4(idx & 15);
-      take = ra != rb ? ra < rb : p.idx < idx;
+      const int ra = bitrev4(oi & 15), rb = bitrev4(idx & 15);
+      take = ra != rb ? ra < rb : oi < idx;
     }
     float loser;
     if (take) {
       loser = best;
-      best = p.best;
-      idx = p.idx;
+      best = ob;
+      idx = oi;
     } else {
-      loser = p.best;
+      loser = ob;
     }
     if (better<kL2>(loser, second)) second = loser;
-    if (better<kL2>(p.second, second)) second = p.second;
+    if (better<kL2>(os, second)) second = os;
   }
   const int p1 = block_list[b] * 16 + ty;
-  if (p1 < n1) write_match<kL2>(s1 + p1, s2, best, second, idx);
+  if (lane == 0 && p1 < n1) write_match<kL2>(s1 + p1, s2, best, second, idx);
+  }
 }
 
 }  // namespace
@@ -191,7 +218,7 @@ void launch_match_blocks(csb_sift_point *d_sift1, int n1, const csb_sift_point *
   const int slices = (chunks + cps - 1) / cps;
   dim3 blk(16, 16), grd(max_blocks < 64 ? max_blocks : 64, slices);
   MatchPart *mp = (MatchPart *)part;
-  const int fin_blocks = (max_blocks * 16 + 127) / 128;
+  const int fin_blocks = min((max_blocks * 16 + 3) / 4, 148 * 2);   // one warp per query, grid-stride
   if (distance == 1) {
     k_match<true, true><<<grd, blk, 0, st>>>(d_sift1, n1, d_sift2, n2, chunks, block_list, block_count, cps, mp);
     k_match_finish<true><<<fin_blocks, 128, 0, st>>>(d_sift1, n1, d_sift2, block_list, block_count, slices, mp);
