@@ -377,8 +377,20 @@ __global__ void __cluster_dims__(IH_CL, 1, 1) __launch_bounds__(IH_NT)
 // with atomicAdd, so the result does not depend on the slicing.
 #define SCORE_HYP 128
 #define SCORE_PTS 256
+// kPick (batched all-pairs path): the CTA that finishes last - a ticket counter in pick.ticket, reset for the next pair -
+// also selects the first-maximum hypothesis (homography.cu:259-264) and writes the pair's result record
+// {H[9], inliers, n_valid}: one launch less per pair than a separate arg-max kernel.
+struct PickArgs {
+  int *ticket;
+  const int *n_valid;
+  int n_pts;
+  float *H_out;
+  int *inl_out, *nvalid_out;
+};
+template <bool kPick>
 __global__ void __launch_bounds__(SCORE_HYP) k_score(const float *__restrict__ coord, const float *__restrict__ homo,
-                                                     int *__restrict__ counts, int numPts, int numLoops, float thresh2) {
+                                                     int *__restrict__ counts, int numPts, int numLoops, float thresh2,
+                                                     PickArgs pick) {
   __shared__ float4 pts[SCORE_PTS];
   const int p0 = blockIdx.y * SCORE_PTS;
   const int np = min(SCORE_PTS, numPts - p0);
@@ -387,44 +399,119 @@ __global__ void __launch_bounds__(SCORE_HYP) k_score(const float *__restrict__ c
                          coord[p0 + i + 3 * numPts]);
   __syncthreads();
   const int loop = blockIdx.x * SCORE_HYP + threadIdx.x;
-  if (loop >= numLoops) return;
-  float a[8];
+  if (loop < numLoops) {
+    float a[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) a[i] = homo[loop + i * numLoops];
-  int cnt = 0;
+    for (int i = 0; i < 8; i++) a[i] = homo[loop + i * numLoops];
+    int cnt = 0;
 #pragma unroll 4
-  for (int i = 0; i < np; i++) {
-    const float4 p = pts[i];
-    const float x1 = p.x, y1 = p.y, x2 = p.z, y2 = p.w;
-    // homography.cu:165-171, every product rounded toward zero
-    const float nomx = __fadd_rn(__fadd_rn(__fmul_rz(a[0], x1), __fmul_rz(a[1], y1)), a[2]);
-    const float nomy = __fadd_rn(__fadd_rn(__fmul_rz(a[3], x1), __fmul_rz(a[4], y1)), a[5]);
-    const float deno = __fadd_rn(__fadd_rn(__fmul_rz(a[6], x1), __fmul_rz(a[7], y1)), 1.0f);
-    const float errx = __fsub_rn(__fmul_rz(x2, deno), nomx);
-    const float erry = __fsub_rn(__fmul_rz(y2, deno), nomy);
-    const float err2 = __fadd_rn(__fmul_rz(errx, errx), __fmul_rz(erry, erry));
-    if (err2 < __fmul_rz(thresh2, __fmul_rz(deno, deno))) cnt++;
+    for (int i = 0; i < np; i++) {
+      const float4 p = pts[i];
+      const float x1 = p.x, y1 = p.y, x2 = p.z, y2 = p.w;
+      // homography.cu:165-171, every product rounded toward zero
+      const float nomx = __fadd_rn(__fadd_rn(__fmul_rz(a[0], x1), __fmul_rz(a[1], y1)), a[2]);
+      const float nomy = __fadd_rn(__fadd_rn(__fmul_rz(a[3], x1), __fmul_rz(a[4], y1)), a[5]);
+      const float deno = __fadd_rn(__fadd_rn(__fmul_rz(a[6], x1), __fmul_rz(a[7], y1)), 1.0f);
+      const float errx = __fsub_rn(__fmul_rz(x2, deno), nomx);
+      const float erry = __fsub_rn(__fmul_rz(y2, deno), nomy);
+      const float err2 = __fadd_rn(__fmul_rz(errx, errx), __fmul_rz(erry, erry));
+      if (err2 < __fmul_rz(thresh2, __fmul_rz(deno, deno))) cnt++;
+    }
+    if (cnt) atomicAdd(counts + loop, cnt);
   }
-  if (cnt) atomicAdd(counts + loop, cnt);
+  if constexpr (kPick) {
+    __shared__ int s_last;
+    __shared__ int s_cnt[SCORE_HYP], s_idx[SCORE_HYP];
+    __threadfence();                                 // this CTA's counts are visible before its ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(pick.ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    int best = -1, bidx = 0x7fffffff;
+    for (int i = threadIdx.x; i < numLoops; i += SCORE_HYP) {
+      const int c = __ldcg(counts + i);              // other CTAs' atomics: read at L2
+      if (c > best) { best = c; bidx = i; }
+    }
+    s_cnt[threadIdx.x] = best;
+    s_idx[threadIdx.x] = bidx;
+    __syncthreads();
+    for (int len = SCORE_HYP / 2; len > 0; len >>= 1) {
+      if (threadIdx.x < len) {
+        const int oc = s_cnt[threadIdx.x + len], oi = s_idx[threadIdx.x + len];
+        if (oc > s_cnt[threadIdx.x] || (oc == s_cnt[threadIdx.x] && oi < s_idx[threadIdx.x])) {
+          s_cnt[threadIdx.x] = oc;
+          s_idx[threadIdx.x] = oi;
+        }
+      }
+      __syncthreads();
+    }
+    const int nv = *pick.n_valid;
+    const bool ok = nv >= 8 && pick.n_pts >= 8;      // homography.cu:207,231: otherwise identity, 0 matches
+    if (threadIdx.x < 9) {
+      float v = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.0f : 0.0f;
+      if (ok && threadIdx.x < 8) v = homo[threadIdx.x * numLoops + s_idx[0]];
+      pick.H_out[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) {
+      *pick.inl_out = ok ? s_cnt[0] : 0;
+      *pick.nvalid_out = nv;
+      *pick.ticket = 0;
+    }
+  }
 }
 
 // ---- batched (all-pairs) RANSAC support: everything stays on the device ----------------------
-// Valid points (score > min_score && ambiguity < max_ambiguity, homography.cu:225-228) in increasing
-// index order, like the reference's validPts.  One CTA, ordered block scan.
-__global__ void __launch_bounds__(1024) k_valid_compact(const csb_sift_point *__restrict__ d_sift, int n, float min_score,
-                                                        float max_amb, int *__restrict__ valid, int *__restrict__ n_valid) {
+// Counter-based generator for the 4-point samples (the reference draws them with libc rand(),
+// homography.cu:232-244 — unseeded and continuing across calls, so no particular sequence is part
+// of its contract).  csb_sample_hash is restated in Python by the tests.
+__host__ __device__ inline unsigned int csb_hash5(unsigned int seed, unsigned int pair, unsigned int loop,
+                                                        unsigned int k, unsigned int attempt) {
+  unsigned int x = seed ^ (pair * 0x9E3779B9u) ^ (loop * 0x85EBCA6Bu) ^ (k * 0xC2B2AE35u) ^ (attempt * 0x27D4EB2Fu);
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+
+// ONE single-CTA kernel prepares a pair's RANSAC (three launches in the first version):
+//   1. valid points (score > min_score && ambiguity < max_ambiguity, homography.cu:225-228) in increasing index
+//      order, like the reference's validPts: thread t owns a contiguous range, one block-wide exclusive scan orders
+//      everything; the range's loads are all issued before the first is used;
+//   2. AoS SiftPoint -> SoA x1, y1, x2, y2 (pad slots zeroed), hypothesis counters and the arg-max ticket zeroed;
+//   3. the 4-point samples of every hypothesis, drawn from the valid list with the counter-based generator.
+constexpr int PREP_IPT = 8;                          // points per thread whose loads are batched (n <= 8192)
+__global__ void __launch_bounds__(1024) k_ransac_prep(const csb_sift_point *__restrict__ d_sift, int n, int n_up, float min_score,
+                                                      float max_amb, int *__restrict__ valid, int *__restrict__ n_valid,
+                                                      float *__restrict__ coord, int *__restrict__ counts, int num_loops,
+                                                      unsigned int seed, unsigned int pair, int *__restrict__ rand_pts) {
   __shared__ int warp_sums[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // thread t owns the contiguous range [t*ipt, (t+1)*ipt): one block-wide exclusive scan orders everything
   const int ipt = (n + 1023) / 1024;
   const int i0 = threadIdx.x * ipt, i1 = min(n, i0 + ipt);
   unsigned int mask = 0;
   int cnt = 0;
-  for (int i = i0; i < i1; i++) {
-    const bool ok = d_sift[i].score > min_score && d_sift[i].ambiguity < max_amb;
-    if (ok) {
-      if (i - i0 < 32) mask |= 1u << (i - i0);
-      cnt++;
+  if (ipt <= PREP_IPT) {
+    float sc[PREP_IPT], am[PREP_IPT];
+#pragma unroll
+    for (int k = 0; k < PREP_IPT; k++) {
+      sc[k] = am[k] = 0.0f;
+      if (i0 + k < i1) {
+        sc[k] = d_sift[i0 + k].score;
+        am[k] = d_sift[i0 + k].ambiguity;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PREP_IPT; k++)
+      if (i0 + k < i1 && sc[k] > min_score && am[k] < max_amb) {
+        mask |= 1u << k;
+        cnt++;
+      }
+  } else {
+    for (int i = i0; i < i1; i++) {
+      const bool ok = d_sift[i].score > min_score && d_sift[i].ambiguity < max_amb;
+      if (ok) {
+        if (i - i0 < 32) mask |= 1u << (i - i0);
+        cnt++;
+      }
     }
   }
   int incl = cnt;
@@ -451,75 +538,44 @@ __global__ void __launch_bounds__(1024) k_valid_compact(const csb_sift_point *__
                                   : (d_sift[i].score > min_score && d_sift[i].ambiguity < max_amb);
     if (ok) valid[pos++] = i;
   }
-  if (threadIdx.x == 0) *n_valid = warp_sums[31];
-}
-
-// Counter-based generator for the 4-point samples (the reference draws them with libc rand(),
-// homography.cu:232-244 — unseeded and continuing across calls, so no particular sequence is part
-// of its contract).  csb_sample_hash is restated in Python by the tests.
-__host__ __device__ inline unsigned int csb_hash5(unsigned int seed, unsigned int pair, unsigned int loop,
-                                                        unsigned int k, unsigned int attempt) {
-  unsigned int x = seed ^ (pair * 0x9E3779B9u) ^ (loop * 0x85EBCA6Bu) ^ (k * 0xC2B2AE35u) ^ (attempt * 0x27D4EB2Fu);
-  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return x;
-}
-
-__global__ void k_make_samples(const int *__restrict__ valid, const int *__restrict__ n_valid, int num_loops,
-                               unsigned int seed, unsigned int pair, int *__restrict__ rand_pts) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= num_loops) return;
-  const int nv = *n_valid;
-  int p[4] = {0, 0, 0, 0};
-  if (nv >= 8) {
-    for (int k = 0; k < 4; k++) {
-      unsigned int attempt = 0;
-      for (;;) {
-        const int c = (int)(csb_hash5(seed, pair, (unsigned int)l, (unsigned int)k, attempt++) % (unsigned int)nv);
-        bool dup = false;
-        for (int q = 0; q < k; q++) dup = dup || (p[q] == c);
-        if (!dup) { p[k] = c; break; }
-      }
-    }
-    for (int k = 0; k < 4; k++) rand_pts[k * num_loops + l] = valid[p[k]];
-  } else {
-    for (int k = 0; k < 4; k++) rand_pts[k * num_loops + l] = 0;
-  }
-}
-
-// First-maximum hypothesis (homography.cu:259-264) -> result record {H[9], inliers, n_valid} on the device.
-__global__ void __launch_bounds__(256) k_pick_best(const int *__restrict__ counts, const float *__restrict__ homo,
-                                                   int num_loops, const int *__restrict__ n_valid, int n_pts,
-                                                   float *__restrict__ H_out, int *__restrict__ inl_out,
-                                                   int *__restrict__ nvalid_out) {
-  __shared__ int s_cnt[256], s_idx[256];
-  int best = -1, bidx = 0x7fffffff;
-  for (int i = threadIdx.x; i < num_loops; i += 256) {
-    const int c = counts[i];
-    if (c > best) { best = c; bidx = i; }
-  }
-  s_cnt[threadIdx.x] = best;
-  s_idx[threadIdx.x] = bidx;
-  __syncthreads();
-  for (int len = 128; len > 0; len >>= 1) {
-    if (threadIdx.x < len) {
-      const int oc = s_cnt[threadIdx.x + len], oi = s_idx[threadIdx.x + len];
-      if (oc > s_cnt[threadIdx.x] || (oc == s_cnt[threadIdx.x] && oi < s_idx[threadIdx.x])) {
-        s_cnt[threadIdx.x] = oc;
-        s_idx[threadIdx.x] = oi;
-      }
-    }
-    __syncthreads();
-  }
-  const int nv = *n_valid;
-  const bool ok = nv >= 8 && n_pts >= 8;       // homography.cu:207,231: otherwise identity, 0 matches
-  if (threadIdx.x < 9) {
-    float v = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.0f : 0.0f;
-    if (ok && threadIdx.x < 8) v = homo[threadIdx.x * num_loops + s_idx[0]];
-    H_out[threadIdx.x] = v;
-  }
+  const int nv = warp_sums[31];
   if (threadIdx.x == 0) {
-    *inl_out = ok ? s_cnt[0] : 0;
-    *nvalid_out = nv;
+    n_valid[0] = nv;
+    n_valid[1] = 0;                            // k_score's ticket
+  }
+  // 2. coordinates and counters
+  for (int i = threadIdx.x; i < num_loops; i += 1024) counts[i] = 0;
+  for (int i = threadIdx.x; i < n_up; i += 1024) {
+    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+    if (i < n) {
+      x1 = d_sift[i].coords2D[0];
+      y1 = d_sift[i].coords2D[1];
+      x2 = d_sift[i].match_xpos;
+      y2 = d_sift[i].match_ypos;
+    }
+    coord[i + 0 * n_up] = x1;
+    coord[i + 1 * n_up] = y1;
+    coord[i + 2 * n_up] = x2;
+    coord[i + 3 * n_up] = y2;
+  }
+  __syncthreads();                             // valid[] (written by this CTA) is complete
+  // 3. samples
+  for (int l = threadIdx.x; l < num_loops; l += 1024) {
+    int p[4] = {0, 0, 0, 0};
+    if (nv >= 8) {
+      for (int k = 0; k < 4; k++) {
+        unsigned int attempt = 0;
+        for (;;) {
+          const int c = (int)(csb_hash5(seed, pair, (unsigned int)l, (unsigned int)k, attempt++) % (unsigned int)nv);
+          bool dup = false;
+          for (int q = 0; q < k; q++) dup = dup || (p[q] == c);
+          if (!dup) { p[k] = c; break; }
+        }
+      }
+      for (int k = 0; k < 4; k++) rand_pts[k * num_loops + l] = valid[p[k]];
+    } else {
+      for (int k = 0; k < 4; k++) rand_pts[k * num_loops + l] = 0;
+    }
   }
 }
 
@@ -534,19 +590,21 @@ void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min
                         int *d_nvalid, float *d_coord, int *d_rand, float *d_homo, int *d_counts, int num_loops,
                         float thresh2, unsigned int seed, unsigned int pair, float *H_out, int *inl_out, int *nvalid_out,
                         cudaStream_t st) {
-  k_valid_compact<<<1, 1024, 0, st>>>(d_sift, n, min_score, max_amb, d_valid, d_nvalid);
-  k_make_samples<<<(num_loops + 127) / 128, 128, 0, st>>>(d_valid, d_nvalid, num_loops, seed, pair, d_rand);
-  k_gather_coords<<<((n_up > num_loops ? n_up : num_loops) + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord, d_counts, num_loops);
+  // d_nvalid: [0] = valid points, [1] = k_score's ticket (256 bytes of scratch)
+  k_ransac_prep<<<1, 1024, 0, st>>>(d_sift, n, n_up, min_score, max_amb, d_valid, d_nvalid, d_coord, d_counts, num_loops, seed, pair,
+                                    d_rand);
   k_hypotheses<<<(num_loops * 8 + 127) / 128, 128, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
-  k_score<<<dim3((num_loops + SCORE_HYP - 1) / SCORE_HYP, (n_up + SCORE_PTS - 1) / SCORE_PTS), SCORE_HYP, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
-  k_pick_best<<<1, 256, 0, st>>>(d_counts, d_homo, num_loops, d_nvalid, n, H_out, inl_out, nvalid_out);
+  const PickArgs pick{d_nvalid + 1, d_nvalid, n, H_out, inl_out, nvalid_out};
+  k_score<true><<<dim3((num_loops + SCORE_HYP - 1) / SCORE_HYP, (n_up + SCORE_PTS - 1) / SCORE_PTS), SCORE_HYP, 0, st>>>(
+      d_coord, d_homo, d_counts, n_up, num_loops, thresh2, pick);
 }
 
 void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
                        int *d_counts, int num_loops, float thresh2, cudaStream_t st) {
   k_gather_coords<<<((n_up > num_loops ? n_up : num_loops) + 255) / 256, 256, 0, st>>>(d_sift, n, n_up, d_coord, d_counts, num_loops);
   k_hypotheses<<<(num_loops * 8 + 127) / 128, 128, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
-  k_score<<<dim3((num_loops + SCORE_HYP - 1) / SCORE_HYP, (n_up + SCORE_PTS - 1) / SCORE_PTS), SCORE_HYP, 0, st>>>(d_coord, d_homo, d_counts, n_up, num_loops, thresh2);
+  k_score<false><<<dim3((num_loops + SCORE_HYP - 1) / SCORE_HYP, (n_up + SCORE_PTS - 1) / SCORE_PTS), SCORE_HYP, 0, st>>>(
+      d_coord, d_homo, d_counts, n_up, num_loops, thresh2, PickArgs{});
 }
 
 void launch_improve_homography(const void *d_jobs, int n_jobs, int num_loops, float min_score, float max_amb, float limit,
