@@ -8,8 +8,13 @@
 //                     reference leaves them uninitialised, homography.cu:215)
 //   k_hypotheses    : eight lanes per 4-point sample, the 8x8 DLT system in registers,
 //                     Crout LU / implicit pivoting in the reference's operation order
-//   k_score         : one warp per hypothesis, inlier test with the reference's
-//                     round-toward-zero products (__fmul_rz), shuffle sum
+//   k_score         : thread per hypothesis over a shared-memory slice of the points, inlier
+//                     test with the reference's round-toward-zero products (__fmul_rz)
+// The batched all-pairs path (everything stays on the device) needs three launches per pair as well:
+//   k_ransac_prep   : valid-point list, coordinates and hash-drawn samples in one single-CTA kernel
+//   k_hypotheses
+//   k_score<true>   : the CTA that finishes last also picks the first-maximum hypothesis
+// and k_improve_homography (ImproveHomography, homography.cu:271-337) runs as one 8-CTA cluster per pair.
 #include <cooperative_groups.h>
 #include "csb_internal.h"
 
