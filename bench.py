@@ -527,6 +527,11 @@ def main():
                               "peak_source": tsrc + " bf16_tflops (burst; the scan is timed alone)",
                               "input_type": "fp16 operands, fp32 accumulation in TMEM, exact fp32 rescoring of the short lists",
                               "call_wall_us": round(wall_us, 1), "Mmatches_per_s_one_pair_at_a_time": round(n / wall_us, 2)}
+            # what actually bounds the scan: every score is read once from tensor memory, whose read port delivers
+            # 64 B/clk per SM (measured); the scan makes 1.25 passes over the n x n fp32 scores
+            tmem_floor_us = 1.25 * n * n * 4.0 / (148 * 64.0 * 1.965e9) * 1e6
+            roofline_match["tmem_read"] = {"passes": 1.25, "bytes": 1.25 * n * n * 4.0, "port_bytes_per_clk_per_sm": 64,
+                                           "floor_us": round(tmem_floor_us, 2), "frac": round(tmem_floor_us / scan, 4)}
             from oracle import oracle as O
             if O.ref_available():
                 work = ROOT / "gpurun_out"

@@ -11,7 +11,7 @@
 //   k_score         : thread per hypothesis over a shared-memory slice of the points, inlier
 //                     test with the reference's round-toward-zero products (__fmul_rz)
 // The batched all-pairs path (everything stays on the device) needs three launches per pair as well:
-//   k_ransac_prep   : valid-point list, coordinates and hash-drawn samples in one single-CTA kernel
+//   k_ransac_prep   : valid-point list and hash-drawn samples (CTA 0), coordinates (the other CTAs)
 //   k_hypotheses
 //   k_score<true>   : the CTA that finishes last also picks the first-maximum hypothesis
 // and k_improve_homography (ImproveHomography, homography.cu:271-337) runs as one 8-CTA cluster per pair.
@@ -477,7 +477,7 @@ __host__ __device__ inline unsigned int csb_hash5(unsigned int seed, unsigned in
   return x;
 }
 
-// ONE single-CTA kernel prepares a pair's RANSAC (three launches in the first version):
+// ONE kernel prepares a pair's RANSAC (three launches in the first version); CTA 0 does steps 1 and 3, the other CTAs step 2:
 //   1. valid points (score > min_score && ambiguity < max_ambiguity, homography.cu:225-228) in increasing index
 //      order, like the reference's validPts: thread t owns a contiguous range, one block-wide exclusive scan orders
 //      everything; the range's loads are all issued before the first is used;
@@ -489,6 +489,26 @@ __global__ void __launch_bounds__(1024) k_ransac_prep(const csb_sift_point *__re
                                                       float *__restrict__ coord, int *__restrict__ counts, int num_loops,
                                                       unsigned int seed, unsigned int pair, int *__restrict__ rand_pts) {
   __shared__ int warp_sums[32];
+  if (blockIdx.x > 0) {
+    // CTAs 1 .. : coordinates and counters (no dependency on the valid list)
+    const int nt = (gridDim.x - 1) * 1024, t = (blockIdx.x - 1) * 1024 + threadIdx.x;
+    for (int i = t; i < num_loops; i += nt) counts[i] = 0;
+    for (int i = t; i < n_up; i += nt) {
+      float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+      if (i < n) {
+        x1 = d_sift[i].coords2D[0];
+        y1 = d_sift[i].coords2D[1];
+        x2 = d_sift[i].match_xpos;
+        y2 = d_sift[i].match_ypos;
+      }
+      coord[i + 0 * n_up] = x1;
+      coord[i + 1 * n_up] = y1;
+      coord[i + 2 * n_up] = x2;
+      coord[i + 3 * n_up] = y2;
+    }
+    return;
+  }
+  // CTA 0: valid list, then the samples
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ipt = (n + 1023) / 1024;
   const int i0 = threadIdx.x * ipt, i1 = min(n, i0 + ipt);
@@ -548,21 +568,6 @@ __global__ void __launch_bounds__(1024) k_ransac_prep(const csb_sift_point *__re
     n_valid[0] = nv;
     n_valid[1] = 0;                            // k_score's ticket
   }
-  // 2. coordinates and counters
-  for (int i = threadIdx.x; i < num_loops; i += 1024) counts[i] = 0;
-  for (int i = threadIdx.x; i < n_up; i += 1024) {
-    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-    if (i < n) {
-      x1 = d_sift[i].coords2D[0];
-      y1 = d_sift[i].coords2D[1];
-      x2 = d_sift[i].match_xpos;
-      y2 = d_sift[i].match_ypos;
-    }
-    coord[i + 0 * n_up] = x1;
-    coord[i + 1 * n_up] = y1;
-    coord[i + 2 * n_up] = x2;
-    coord[i + 3 * n_up] = y2;
-  }
   __syncthreads();                             // valid[] (written by this CTA) is complete
   // 3. samples
   for (int l = threadIdx.x; l < num_loops; l += 1024) {
@@ -596,7 +601,7 @@ void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min
                         float thresh2, unsigned int seed, unsigned int pair, float *H_out, int *inl_out, int *nvalid_out,
                         cudaStream_t st) {
   // d_nvalid: [0] = valid points, [1] = k_score's ticket (256 bytes of scratch)
-  k_ransac_prep<<<1, 1024, 0, st>>>(d_sift, n, n_up, min_score, max_amb, d_valid, d_nvalid, d_coord, d_counts, num_loops, seed, pair,
+  k_ransac_prep<<<1 + 8, 1024, 0, st>>>(d_sift, n, n_up, min_score, max_amb, d_valid, d_nvalid, d_coord, d_counts, num_loops, seed, pair,
                                     d_rand);
   k_hypotheses<<<(num_loops * 8 + 127) / 128, 128, 0, st>>>(d_coord, d_rand, d_homo, n_up, num_loops);
   const PickArgs pick{d_nvalid + 1, d_nvalid, n, H_out, inl_out, nvalid_out};

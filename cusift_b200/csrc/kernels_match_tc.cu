@@ -487,7 +487,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
         kept++;
       }
     }
-    for (int k = min(kept, TC_TOPK); k < TC_TOPK; k++) out_list[k] = -1;
+    for (int k = min(kept, TC_TOPK); k < TC_TOPK; k++) {
+      out_list[k] = -1;
+      out_lval[k] = 0.0f;                            // the rescoring kernel loads values and indices together
+    }
     if (cnt > TC_RAW || kept > TC_TOPK) out_list[0] = -2;   // wrapped raw list or more survivors than slots
     reinterpret_cast<float2 *>(out_val + (size_t)nq_pad * 4 * TC_TOPK)[slot] = make_float2(m1, m2);
   }

@@ -195,7 +195,8 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
  * proven complete and were redone exactly, accumulated since the context was created. */
 long long csb_match_redo_blocks(const csb_ctx *ctx);
 /* The tensor-core path prefilters with fp16 dot products whose error bound holds for descriptors that are
- * finite in fp16 with squared norm <= 1.002 (SIFT / RootSIFT descriptors are unit vectors).  The packing kernel
+ * finite in fp16 with squared norm <= 1.002 (SIFT / RootSIFT descriptors are unit vectors) and, when the set's size
+ * is not a multiple of 256, non-negative (the scan pads the set with zero rows).  The packing kernel
  * checks this (and measures the actual rounding-error norms, from which the per-pair bound ~6e-4 is derived); calls whose
  * sets fall outside are computed by the exact fp32 kernel instead, so csb_match equals the
  * reference for ANY SiftPoint.data.  Number of calls / pairs that took that route since the context was created: */

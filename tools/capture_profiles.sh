@@ -19,4 +19,12 @@ timeout 300 $FULL -k regex:k_orient_desc --launch-skip 2 --launch-count 1 -o gpu
 timeout 300 $FULL -k regex:k_match_tc --launch-skip 2 --launch-count 1 -o gpurun_out/prof_${tag}_match_tc python tools/run_match.py > /dev/null 2>&1
 timeout 300 $FULL -k regex:k_rescore --launch-skip 2 --launch-count 1 -o gpurun_out/prof_${tag}_rescore python tools/run_match.py > /dev/null 2>&1
 timeout 300 $FULL -k regex:k_hypotheses --launch-skip 1 --launch-count 1 -o gpurun_out/prof_${tag}_hypotheses python tools/allpairs_bench.py --sets 3 --points 2048 --size 640x480 --loops 1024 > /dev/null 2>&1
+# all-pairs path: launch list + the kernels that only run there (cluster ImproveHomography, exact redo pass, fused RANSAC prep / score)
+AP="python tools/allpairs_bench.py --sets 4 --points 8192 --improve 5 --reps 1"
+timeout 300 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_allpairs_$tag.csv $AP > /dev/null 2>&1
+timeout 300 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_match_$tag.csv python tools/run_match.py > /dev/null 2>&1
+timeout 300 $FULL -k regex:k_improve_homography --launch-skip 2 --launch-count 1 -o gpurun_out/prof_${tag}_improve_homography $AP > /dev/null 2>&1
+timeout 300 $FULL -k regex:k_match\< --launch-skip 2 --launch-count 1 -o gpurun_out/prof_${tag}_match_redo $AP > /dev/null 2>&1
+timeout 300 $FULL -k regex:k_ransac_prep --launch-skip 2 --launch-count 1 -o gpurun_out/prof_${tag}_ransac_prep $AP > /dev/null 2>&1
+timeout 300 $FULL -k regex:k_score --launch-skip 2 --launch-count 1 -o gpurun_out/prof_${tag}_score $AP > /dev/null 2>&1
 ls -la gpurun_out/ | grep $tag
