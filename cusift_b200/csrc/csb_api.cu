@@ -1130,7 +1130,7 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
       }
     }
     const int splits = tc_splits(n1, n2, ctx->sm_count);
-    const size_t sl_need = (size_t)tc_pad(n1) * 4 * 8;      // up to 4 splits x top-8
+    const size_t sl_need = tc_shortlist_ints(n1);           // up to 4 splits x TC_TOPK entries per query
     if (ctx->tc_sl_cap < sl_need) {
       if (ctx->tc_val) cudaFree(ctx->tc_val);
       if (ctx->tc_idx) cudaFree(ctx->tc_idx);
@@ -1366,7 +1366,7 @@ int csb_allpairs_match_ransac_improve(csb_ctx *ctx, int n_sets, void *const *d_s
     CSB_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ap_packed, cudaEventDisableTiming));
   }
   {
-    const size_t sl_need = (size_t)tc_pad(max_n > 0 ? max_n : 1) * 4 * 8;
+    const size_t sl_need = tc_shortlist_ints(max_n > 0 ? max_n : 1);
     const size_t nblk = (size_t)max_n / 16 + 2;
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };

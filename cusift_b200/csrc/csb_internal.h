@@ -146,6 +146,7 @@ void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2
                     int n_splits, int distance, const int *q_info, const int *c_info, int *redo_flags, int *redo_list,
                     int *redo_count, cudaStream_t st);
 size_t tc_shortlist_floats(int n);   // floats of short-list scratch (sl_val) a query set of n points needs
+size_t tc_shortlist_ints(int n);     // ints of short-list scratch (sl_idx)
 void launch_homography(const csb_sift_point *d_sift, int n, int n_up, float *d_coord, const int *d_rand, float *d_homo,
                        int *d_counts, int num_loops, float thresh2, cudaStream_t st);
 

@@ -78,7 +78,8 @@ constexpr int TC_STAGES = 4;
 #ifndef TC_S1_DIV
 #define TC_S1_DIV 4               // sweep 1 covers the last 1/TC_S1_DIV of the candidate slice
 #endif
-constexpr int TC_TOPK = 8;         // listed candidates per query and split handed to the rescoring kernel
+constexpr int TC_TOPK = 16;        // listed candidates per query and split handed to the rescoring kernel (8 made clusters of
+                                   // near-identical descriptors overflow: one to five 16-query blocks per 8192^2 match went to the exact kernel)
 constexpr int TC_RAW = 16;         // candidates per query a CTA can hold while the threshold is still rising
 constexpr int KHALF_BYTES_PER_ROW = 128;          // 64 fp16
 constexpr uint32_t A_HALF_BYTES = 128 * KHALF_BYTES_PER_ROW;      // one 128-row x 64-K operand block: 16 KB
@@ -475,6 +476,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
     const size_t slot = (size_t)(qtile * TC_QT + row) * n_splits + split;
     int *const out_list = out_idx + slot * TC_TOPK;
     float *const out_lval = out_val + slot * TC_TOPK;
+    // all slots are first cleared with 128-bit stores (a list is 64-byte aligned), then the survivors - a few - are
+    // written over them (same thread: ordered)
+    static_assert(TC_TOPK % 4 == 0, "vector clears");
+#pragma unroll
+    for (int k = 0; k < TC_TOPK / 4; k++) {
+      reinterpret_cast<int4 *>(out_list)[k] = make_int4(-1, -1, -1, -1);
+      reinterpret_cast<float4 *>(out_lval)[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // the rescoring kernel loads values and indices together
+    }
     int kept = 0;
     for (int e = 0; e < min(cnt, TC_RAW); e++) {
       const float2 en = s_raw[e * TC_QT + row];
@@ -486,10 +495,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
         }
         kept++;
       }
-    }
-    for (int k = min(kept, TC_TOPK); k < TC_TOPK; k++) {
-      out_list[k] = -1;
-      out_lval[k] = 0.0f;                            // the rescoring kernel loads values and indices together
     }
     if (cnt > TC_RAW || kept > TC_TOPK) out_list[0] = -2;   // wrapped raw list or more survivors than slots
     reinterpret_cast<float2 *>(out_val + (size_t)nq_pad * 4 * TC_TOPK)[slot] = make_float2(m1, m2);
@@ -510,7 +515,7 @@ __device__ __forceinline__ int bitrev4(int x) { return ((x & 1) << 3) | ((x & 2)
 // candidates = ten busy lanes, each walking a 128-step chain with two shared-memory reads per step, so the kernel
 // was bound by the shared-memory pipe at a third of its lane capacity, and every split's private top-2 was rescored
 // although only the top-2 over all splits matter.)
-//   1. filter: lane = list entry of one query (n_splits x TC_TOPK <= 32).  The splits' (m1, m2) pairs give a lower
+//   1. filter: lane = RS_H list entries of one query (n_splits x TC_TOPK <= 32 RS_H).  The splits' (m1, m2) pairs give a lower
 //      bound of the second largest approximate dot product over ALL candidates (their chunks are disjoint); entries
 //      whose value (an upper bound) is below it minus 2 eps cannot be best or second best and are dropped.
 //      About 2.3 entries per query survive instead of 10.
@@ -520,6 +525,7 @@ __device__ __forceinline__ int bitrev4(int x) { return ((x & 1) << 3) | ((x & 2)
 //   4. lane = query: FindMinCorr/FindMaxCorr's best / second-best rule over the query's few items.
 constexpr int RS_QPW = 8;           // queries per warp and round (the (m1, m2) merge maps lane = 4 query + split)
 constexpr int RS_WARPS = 4;
+constexpr int RS_H = (4 * TC_TOPK + 31) / 32;   // list entries per lane (up to four splits x TC_TOPK entries per query)
 constexpr int RS_QS = 129, RS_CS = 129;   // row strides (words): rows spread over the banks
 constexpr size_t RS_SMEM_WARP = sizeof(float) * (RS_QPW * RS_QS + 32 * RS_CS) + sizeof(int) * (32 + 32);
 
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__res
   float *sc = sq + RS_QPW * RS_QS;                                       // [32][RS_CS]
   int *s_ci = reinterpret_cast<int *>(sc + 32 * RS_CS);                  // candidate index of work item
   int *s_qi = s_ci + 32;                                                 // local query of work item
-  const int n_list = n_splits * TC_TOPK;          // <= 32
+  const int n_list = n_splits * TC_TOPK;          // <= 32 RS_H
   const float eps2 = 2.0f * (1.002f * (sqrtf(__int_as_float(q_info[1])) + sqrtf(__int_as_float(c_info[1]))) + 2.0e-5f);
   const float2 *sl_top = reinterpret_cast<const float2 *>(sl_val + (size_t)nq_pad * 4 * TC_TOPK);
   const float NONE = kL2 ? 999.0f : -1.0f;
@@ -545,15 +551,18 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__res
   for (int q0 = (blockIdx.x * RS_WARPS + wib) * RS_QPW; q0 < n1; q0 += gridDim.x * RS_WARPS * RS_QPW) {
     // ---- 1. filter; survivors stay in registers: lane l of query j -> keepm[j] bit l.  All loads of the warp's
     // queries are issued before the first is used (one L2 round trip, not eight).
-    int my_ci[RS_QPW];
-    float my_v[RS_QPW];
+    int my_ci[RS_QPW][RS_H];
+    float my_v[RS_QPW][RS_H];
 #pragma unroll
     for (int j = 0; j < RS_QPW; j++) {
-      my_ci[j] = -1;
-      my_v[j] = -3.0e38f;
-      if (q0 + j < n1 && lane < n_list) {
-        my_ci[j] = sl_idx[(size_t)(q0 + j) * n_list + lane];
-        my_v[j] = sl_val[(size_t)(q0 + j) * n_list + lane];
+#pragma unroll
+      for (int h = 0; h < RS_H; h++) {
+        my_ci[j][h] = -1;
+        my_v[j][h] = -3.0e38f;
+        if (q0 + j < n1 && lane + 32 * h < n_list) {
+          my_ci[j][h] = sl_idx[(size_t)(q0 + j) * n_list + lane + 32 * h];
+          my_v[j][h] = sl_val[(size_t)(q0 + j) * n_list + lane + 32 * h];
+        }
       }
     }
     // second largest approximate value over all splits, from below: merge the splits' (m1, m2); lane = 4 j + split
@@ -572,17 +581,33 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__res
         a2 = fmaxf(fmaxf(a2, b2), lo);
       }
     }
-    unsigned int keepm[RS_QPW];
-    unsigned int overflow_q = 0;                  // bit j: a split of query j proves nothing
+    unsigned int keepm[RS_QPW][RS_H];
+    int kcnt[RS_QPW];
+    unsigned int overflow_q = 0;                  // bit j: the lists of query j prove nothing
 #pragma unroll
     for (int j = 0; j < RS_QPW; j++) {
-      if (__any_sync(FULLM, my_ci[j] == -2)) overflow_q |= 1u << j;
       const float thr = __shfl_sync(FULLM, a2, 4 * j) - eps2;
-      const bool keep = my_ci[j] >= 0 && my_v[j] >= thr;
-      if (!keep) my_ci[j] = -1;
-      keepm[j] = __ballot_sync(FULLM, keep);
+      bool ovf = false;
+      kcnt[j] = 0;
+#pragma unroll
+      for (int h = 0; h < RS_H; h++) {
+        ovf = ovf || my_ci[j][h] == -2;
+        const bool keep = my_ci[j][h] >= 0 && my_v[j][h] >= thr;
+        if (!keep) my_ci[j][h] = -1;
+        keepm[j][h] = __ballot_sync(FULLM, keep);
+        kcnt[j] += __popc(keepm[j][h]);
+      }
+      if (__any_sync(FULLM, ovf) || kcnt[j] > 32) {   // (more than 32 survivors of one query do not fit a round either)
+        overflow_q |= 1u << j;
+        kcnt[j] = 0;
+#pragma unroll
+        for (int h = 0; h < RS_H; h++) {
+          my_ci[j][h] = -1;
+          keepm[j][h] = 0;
+        }
+      }
     }
-    // ---- rounds: consecutive queries whose survivors fit the 32 lanes (a single query always fits)
+    // ---- rounds: consecutive queries whose survivors fit the 32 lanes (a single query fits: kcnt <= 32)
     int jb = 0;
     while (jb < RS_QPW) {
       int je = jb, n_items = 0;
@@ -590,8 +615,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__res
 #pragma unroll
       for (int j = 0; j < RS_QPW; j++) {
         start[j] = n_items;
-        if (j >= jb && j == je && n_items + __popc(keepm[j]) <= 32) {
-          n_items += __popc(keepm[j]);
+        if (j >= jb && j == je && n_items + kcnt[j] <= 32) {
+          n_items += kcnt[j];
           je = j + 1;
         }
       }
@@ -601,16 +626,20 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__res
       // ---- 2. work list + staging
 #pragma unroll
       for (int j = 0; j < RS_QPW; j++) {
-        if (j >= jb && j < je && my_ci[j] >= 0) {
-          const int w = start[j] + __popc(keepm[j] & ((1u << lane) - 1u));
-          s_ci[w] = my_ci[j];
-          s_qi[w] = j;
+#pragma unroll
+        for (int h = 0; h < RS_H; h++) {
+          if (j >= jb && j < je && my_ci[j][h] >= 0) {
+            int w = start[j] + __popc(keepm[j][h] & ((1u << lane) - 1u));
+            for (int g = 0; g < h; g++) w += __popc(keepm[j][g]);
+            s_ci[w] = my_ci[j][h];
+            s_qi[w] = j;
+          }
         }
       }
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < RS_QPW; j++) {
-        if (j >= jb && j < je && q0 + j < n1 && keepm[j]) {
+        if (j >= jb && j < je && q0 + j < n1 && kcnt[j]) {
           const float *pq = s1[q0 + j].data;
 #pragma unroll
           for (int t = 0; t < 4; t++) __pipeline_memcpy_async(&sq[j * RS_QS + lane + 32 * t], &pq[lane + 32 * t], 4);
@@ -668,7 +697,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rescore(csb_sift_point *__res
         int a = 0, b = 0;
 #pragma unroll
         for (int j = 0; j < RS_QPW; j++)
-          if (j == lane) a = start[j], b = start[j] + __popc(keepm[j]);
+          if (j == lane) a = start[j], b = start[j] + kcnt[j];
         if (overflow_q & (1u << lane)) {
           // the exact kernel redoes this block of 16 queries; the first query to flag a block lists it
           if (atomicExch(redo_flags + (q >> 4), 1) == 0) redo_list[atomicAdd(redo_count, 1)] = q >> 4;
@@ -748,6 +777,7 @@ int launch_match_tc(const void *q_packed, int n1, const void *c_packed, int n2, 
   return (int)cudaPeekAtLastError();   // a failed launch must not be overwritten by the launches that follow
 }
 
+size_t tc_shortlist_ints(int n) { return (size_t)tc_pad(n) * 4 * TC_TOPK; }
 size_t tc_shortlist_floats(int n) { return (size_t)tc_pad(n) * 4 * (TC_TOPK + 2); }   // entry values + (m1, m2) per split
 
 void launch_rescore(csb_sift_point *s1, int n1, const csb_sift_point *s2, int n2, const float *sl_val, const int *sl_idx,

@@ -36,7 +36,7 @@ sets = [np.ascontiguousarray(k1[:1536]), np.ascontiguousarray(k2[:1536]), np.asc
 dp = [ctx.upload_sift(s) for s in sets]
 ap = ctx.allpairs(dp, [len(s) for s in sets], csb.all_pairs(3), 'l2', 256, 0.0, 0.80, 5.0, 7, improve_loops=3)
 a, b = rs(600, 5), rs(2048, 6)
-for c in range(40, 40 + 13 * 16, 16):
+for c in range(40, 40 + 21 * 16, 16):
     b['data'][c] = a['data'][5]
 before = csb.lib().csb_match_redo_blocks(ctx.h)
 m3 = ctx.match(a, b, 'l2')
