@@ -381,7 +381,7 @@ __global__ void __cluster_dims__(IH_CL, 1, 1) __launch_bounds__(IH_NT)
 // SCORE_PTS points read from shared memory as broadcasts; the integer partial counts are summed
 // with atomicAdd, so the result does not depend on the slicing.
 #define SCORE_HYP 128
-#define SCORE_PTS 256
+#define SCORE_PTS 64
 // kPick (batched all-pairs path): the CTA that finishes last - a ticket counter in pick.ticket, reset for the next pair -
 // also selects the first-maximum hypothesis (homography.cu:259-264) and writes the pair's result record
 // {H[9], inliers, n_valid}: one launch less per pair than a separate arg-max kernel.
