@@ -770,8 +770,35 @@ def test_improve_homography_host_shim_device_oracle_reference(gpu_ctx, frames, w
     assert nfit_z == nfit_zo and np.allclose(H_z, H_zo, rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("n", [7, 300, 8192, 12345])
+def test_improve_homography_cluster_kernel_sizes(gpu_ctx, n):
+    """The device ImproveHomography runs as one 8-CTA cluster per job; a thread keeps its first four points in
+    registers and reads further ones from memory.  Sizes around those limits (fewer points than threads, exactly
+    8192 = 4 per thread, more), with outliers and filtered-out points, against the oracle."""
+    r = np.random.default_rng(100 + n)
+    pts = np.zeros(n, csb.SIFT_DTYPE)
+    xy = r.uniform(0, 1000, (n, 2)).astype(np.float32)
+    Ht = np.array([1.02, 0.01, 3.0, -0.015, 0.98, -2.0, 1e-5, -2e-5, 1.0])
+    den = Ht[6] * xy[:, 0] + Ht[7] * xy[:, 1] + 1.0
+    mx = (Ht[0] * xy[:, 0] + Ht[1] * xy[:, 1] + Ht[2]) / den + r.normal(0, 0.4, n)
+    my = (Ht[3] * xy[:, 0] + Ht[4] * xy[:, 1] + Ht[5]) / den + r.normal(0, 0.4, n)
+    out = r.random(n) < 0.2
+    mx[out] = r.uniform(0, 1000, out.sum())
+    my[out] = r.uniform(0, 1000, out.sum())
+    pts["coords2D"] = xy
+    pts["match_xpos"], pts["match_ypos"] = mx.astype(np.float32), my.astype(np.float32)
+    pts["score"] = r.uniform(0.0, 1.0, n).astype(np.float32)
+    pts["ambiguity"] = r.uniform(0.3, 1.0, n).astype(np.float32)      # about 30 % fail the 0.80 filter
+    H0 = (Ht + np.array([0.01, -0.004, 1.0, 0.003, 0.01, -1.0, 0, 0, 0])).astype(np.float32)
+    H_o, nfit_o, pts_o = O.improve_homography(pts, H0, 5, 0.1, 0.80, 3.0)
+    H_d, nfit_d, pts_d = gpu_ctx.improve_homography(pts, H0, 5, 0.1, 0.80, 3.0)
+    assert abs(nfit_d - nfit_o) <= 1, (n, nfit_d, nfit_o)            # a point exactly on the limit may round either way
+    assert np.allclose(H_d, H_o, rtol=1e-5, atol=1e-6), (n, H_d, H_o)
+    assert np.allclose(pts_d["match_error"], pts_o["match_error"], rtol=1e-4, atol=1e-4)
+
+
 def test_allpairs_with_improve_vs_oracle(gpu_ctx):
-    """The batched pipeline with ImproveHomography appended to every pair (device IRLS, one CTA per pair)."""
+    """The batched pipeline with ImproveHomography appended to every pair (device IRLS, one 8-CTA cluster per pair)."""
     imgs = [csb.synth(640, 480, 3100 + i) for i in range(3)]
     p = csb.make_params(5, 0.0, 0.5)
     sets = []
