@@ -418,7 +418,7 @@ def _rand_set(n, seed):
     return s
 
 
-@pytest.mark.parametrize("n1,n2", [(256, 256), (300, 700), (1000, 3000), (257, 4097)])
+@pytest.mark.parametrize("n1,n2", [(256, 256), (300, 700), (1000, 3000), (257, 4097), (512, 384), (9000, 2100)])
 def test_match_tensor_core_path_bit_exact(gpu_ctx, n1, n2):
     """Sets of >= 256 points go through the tcgen05 matcher (fp16 tensor-core scan, fp32 rescoring in
     the reference's k order): still bit-identical to the oracle, incl. exact duplicates / ties."""
