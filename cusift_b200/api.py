@@ -417,7 +417,7 @@ class Context:
         return out
 
     def sample_points(self, valid: np.ndarray, num_loops: int, seed: int, pair_id: int) -> np.ndarray:
-        """Host restatement of the device sample generator (k_make_samples): int32 [4][num_loops]."""
+        """Host restatement of the device sample generator (k_ransac_prep): int32 [4][num_loops]."""
         nv = len(valid)
         rp = np.zeros((4, num_loops), np.int32)
         if nv < 8:

@@ -1117,7 +1117,7 @@ int csb_match(csb_ctx *ctx, void *d_sift1, int n1, const void *d_sift2, int n2, 
     LaunchScope ls(ctx, s, "match");
     launch_match((csb_sift_point *)d_sift1, n1, (const csb_sift_point *)d_sift2, n2, distance, s->stream);
   } else {
-    // tensor-core path: pack -> tcgen05 scan (top-8 short list per query and split) -> exact rescoring
+    // tensor-core path: pack -> tcgen05 scan (short list per query and split) -> exact rescoring
     const int ns[2] = {n1, n2};
     const void *sets[2] = {d_sift1, d_sift2};
     for (int i = 0; i < 2; i++) {

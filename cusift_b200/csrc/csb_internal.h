@@ -154,7 +154,7 @@ void launch_pair_ransac(const csb_sift_point *d_sift, int n, int n_up, float min
                         int *d_nvalid, float *d_coord, int *d_rand, float *d_homo, int *d_counts, int num_loops,
                         float thresh2, unsigned int seed, unsigned int pair, float *H_out, int *inl_out, int *nvalid_out,
                         cudaStream_t st);
-// device ImproveHomography: one CTA per job (kernels_homography.cu); jobs = array of improve_job_bytes() records
+// device ImproveHomography: one 8-CTA cluster per job (kernels_homography.cu); jobs = array of improve_job_bytes() records
 void launch_improve_homography(const void *d_jobs, int n_jobs, int num_loops, float min_score, float max_amb, float limit,
                                cudaStream_t st);
 size_t improve_job_bytes();

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) k_hypotheses(const float *__restrict__ co
   }
 }
 
-// ImproveHomography (homography.cu:280-346) on the device, one CTA per homography: iteratively re-weighted
+// ImproveHomography (homography.cu:280-346) on the device, one cluster of CTAs per homography: iteratively re-weighted
 // least squares, weights limit / (err + limit), the 8x8 normal equations accumulated in fp64 and solved by
 // Cholesky, then the inlier count and match_error of every point.  Per-point arithmetic follows the reference
 // (projection in double rounded to float, float error and weight); the fp64 sums are formed in a different
