@@ -49,12 +49,13 @@
 //     columns), thresholds shared between the CTAs of a query tile through global memory (the hits a shared bound
 //     would save happen in the first tiles of sweep 2, before anything published can arrive), a common sample of tiles
 //     as sweep 1 in every CTA (1.5 sweeps of TMEM reads), sweep 1 over an eighth of the slice (raw lists overflow).
-//  3. k_rescore      warp per query: exact fp32 scores of the listed candidates in the
+//  3. k_rescore      eight queries per warp: the splits' (m1, m2) give a threshold over ALL candidates that drops
+//                    most listed entries; exact fp32 scores of the survivors in the
 //                    reference's rotated k order (bit-identical to ComputeDistance), then the
 //                    reference's best / second-best rule incl. its tie-breaking
-//                    (FindMinCorr/FindMaxCorr).  A query whose list overflowed (> 8 entries per
-//                    split: massive near-ties) is flagged and redone by the exact fp32 kernel
-//                    (kernels_match.cu).
+//                    (FindMinCorr/FindMaxCorr).  A query whose list overflowed (> 16 entries per
+//                    split: massive near-ties) is appended to the redo list and recomputed by the exact
+//                    fp32 kernel (kernels_match.cu).
 //
 // fp16 inputs and the error bound eps.  With q^ = fp16(q), dq = q - q^ (same for c):
 //   |q.c - q^.c^| = |dq.c + q^.dc| <= |dq| |c| + |q^| |dc|            (Cauchy-Schwarz, any signs)
