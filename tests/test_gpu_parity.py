@@ -418,10 +418,11 @@ def _rand_set(n, seed):
     return s
 
 
-@pytest.mark.parametrize("n1,n2", [(256, 256), (300, 700), (1000, 3000), (257, 4097), (512, 384), (9000, 2100)])
+@pytest.mark.parametrize("n1,n2", [(256, 256), (300, 700), (1000, 3000), (257, 4097), (512, 384), (9000, 2100), (13000, 700), (20000, 600)])
 def test_match_tensor_core_path_bit_exact(gpu_ctx, n1, n2):
     """Sets of >= 256 points go through the tcgen05 matcher (fp16 tensor-core scan, fp32 rescoring in
-    the reference's k order): still bit-identical to the oracle, incl. exact duplicates / ties."""
+    the reference's k order): still bit-identical to the oracle, incl. exact duplicates / ties.  The sizes cover one
+    tile per candidate slice, a slice of pure padding, more query tiles than SMs / 4 (3, 2 and 1 candidate slices)."""
     a, b = _rand_set(n1, n1), _rand_set(n2, n2 + 1)
     b["data"][17] = b["data"][3]
     b["data"][24] = b["data"][3]
