@@ -438,13 +438,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
         thr = m2 - eps2;
       }
     };
-    // The first 32 columns of tile it + 1 are requested before the last 32 of tile it are examined (the MMA warp is
-    // up to two accumulators ahead), so the TMEM read port does not wait for the arithmetic at a tile boundary.
-    uint32_t ra[32], rb[32];
+    // 64 columns (8 KB per warp) are in flight while the previous 64 are examined, and the first 64 of tile it + 1 are
+    // requested before the last 64 of tile it are examined (the MMA warp is up to two accumulators ahead): with
+    // 64 KB outstanding per SM the TMEM read port - 64 B/clk - always has a queue.  (32-column double buffering left
+    // it idle whenever most warps were in their arithmetic; tcgen05.wait::ld waits for ALL outstanding loads, so
+    // deeper pipelines have to come as larger batches.)
+    uint32_t ra[32], qa[32], rb[32], qb[32];
     if (it < n_iter) {
       mbar_wait(acc_full + qh * 2 + (it & 1), (it >> 1) & 1);
       tc_fence_after();
       tc_ld32(tlane + (uint32_t)((it & 1) * TC_CT), ra);
+      tc_ld32(tlane + (uint32_t)((it & 1) * TC_CT + 32), qa);
     }
     for (; it < n_iter; it++) {
       const int a = it & 1;
@@ -452,14 +456,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
       const bool unseen = it < n_iter - n1;
       const int col0 = tile_of(it) * TC_CT;
       tc_ld_wait();
-      tc_ld32(taddr + 32, rb);
+      tc_ld32(taddr + 64, rb);
+      tc_ld32(taddr + 96, qb);
       list32(ra, col0, unseen);
-      tc_ld_wait();
-      tc_ld32(taddr + 64, ra);
-      list32(rb, col0 + 32, unseen);
-      tc_ld_wait();
-      tc_ld32(taddr + 96, rb);
-      list32(ra, col0 + 64, unseen);
+      list32(qa, col0 + 32, unseen);
       tc_ld_wait();
       tc_fence_before();
       mbar_arrive(acc_empty + qh * 2 + a);
@@ -467,8 +467,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(const __half *__rest
         mbar_wait(acc_full + qh * 2 + (a ^ 1), ((it + 1) >> 1) & 1);
         tc_fence_after();
         tc_ld32(tlane + (uint32_t)((a ^ 1) * TC_CT), ra);
+        tc_ld32(tlane + (uint32_t)((a ^ 1) * TC_CT + 32), qa);
       }
-      list32(rb, col0 + 96, unseen);
+      list32(rb, col0 + 64, unseen);
+      list32(qb, col0 + 96, unseen);
     }
     // the threshold is final: keep the entries that reach it (each thread reads back its own writes only).
     // Short list of this (row, split): index -1 = unused slot, -2 in slot 0 = the list proves nothing (overflow);
